@@ -1,0 +1,217 @@
+/*
+ * pb200.h -- C ABI of libpb200.so: the B200 (sm_100a) implementation of PROSPECT's
+ * simulated-annealing / Metropolis-Hastings hot path over the analytic Gaussian kernels.
+ *
+ * The reference (AarhusCosmology/prospect_public, pure Python) has no FFI; each entry point
+ * below names the reference call site it replaces (paths relative to the reference root).
+ * INTEGRATION.md shows the ctypes binding a PROSPECT maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, non-zero on failure; pb200_last_error() gives the text
+ *     (thread-local); no exception ever crosses the ABI;
+ *   - "device pointer" arguments are raw CUDA device addresses owned by the caller (the Python host
+ *     allocates them through torch); `stream` is a cudaStream_t passed as void* (NULL = default);
+ *     launches are asynchronous on that stream;
+ *   - all matrices are zero-padded to npad = 32*ceil(n/32) and stored "input-major":
+ *     M_t[j*npad + i] multiplies input j into output i, so a warp reads one input row coalesced;
+ *   - chains are enumerated c = repetition * n_points + point
+ *     (prospect/tasks/initialise_profile_task.py:16-26);
+ *   - loglkl always means -log L (prospect/kernels/base_kernel.py:104-107).
+ */
+#ifndef PB200_H
+#define PB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PB200_ABI_VERSION 1
+
+/* chain status (pb200_chains.status) */
+#define PB200_ACTIVE     0
+#define PB200_CONVERGED  1   /* chi2_tolerance stop, tasks/optimise_task.py:33-50 */
+#define PB200_FAILED     2   /* the reference task would have raised (optimiser.py:99-112 unbound local) */
+
+/* step-size schedule modes (profile.step_size_schedule / step_size_adaptive_multiplier) */
+#define PB200_STEP_EXPONENTIAL      0   /* optimiser.py:92-93 */
+#define PB200_STEP_ADAPTIVE_FIXED   1   /* optimiser.py:138-147 */
+#define PB200_STEP_ADAPTIVE_SECANT  2   /* optimiser.py:95-137 ('adaptive' multiplier) */
+
+/* sample recording modes of pb200_mh_run */
+#define PB200_RECORD_NONE      0
+#define PB200_RECORD_ACCEPTED  1   /* accepted points + multiplicities == prospect/mcmc.py Chain */
+#define PB200_RECORD_THINNED   2   /* current position every `thin` steps, weight 1 */
+
+/*
+ * The Gaussian target and the per-point proposal, precomputed on the host in FP64.
+ * Replaces the data held by AnalyticalKernel (prospect/kernels/analytical_kernel.py:10-66)
+ * plus the per-task `covmat` of optimise_settings (tasks/initialise_optimiser_task.py:78-92).
+ *
+ * With S = sym(inv(C)) and the reference's residual order [varying..., fixed]:
+ *   loglkl(x) = 1/2 q^T S_aa q + f s_ab^T q + c0,   q = x - mu,  f = fixed_value - mu_fixed,
+ *   c0 = 1/2 s_bb f^2.   (free runs: n = d, f = c0 = 0)
+ * Proposal covariance of point p: Sigma_p = F F^T.  M = F^T S_aa F = Q diag(lam) Q^T and
+ * Lt = F Q, so a proposal x' = x + step * Lt z (z ~ N(0, I)) changes loglkl by exactly
+ *   Delta = step * z.gt + 1/2 step^2 sum_i lam_i z_i^2,   gt = Lt^T (S_aa q + f s_ab) = G q + h.
+ */
+typedef struct pb200_problem {
+    int32_t d;            /* kernel dimension */
+    int32_t n;            /* varying parameters (d-1 for jobtype profile, d otherwise) */
+    int32_t npad;         /* 32, 64, 128 or 256 */
+    int32_t n_points;     /* P: profile values (1 for global_optimisation / mcmc) */
+    const double* saa;    /* device [npad*npad]  S_aa (symmetric) */
+    const double* sab;    /* device [npad]       s_ab (zeros for free runs) */
+    const double* mu;     /* device [npad]       means of the varying parameters, varying order */
+    const double* lo;     /* device [npad]       prior box (pads / ignore_prior: -inf) */
+    const double* hi;     /* device [npad]       prior box (pads / ignore_prior: +inf) */
+    const double* f;      /* device [P] */
+    const double* c0;     /* device [P] */
+    const float*  lt_t;   /* device [P][npad*npad]  lt_t[j*npad+i] = Lt[i][j]  (FP32) */
+    const float*  lam;    /* device [P][npad]       eigenvalues (FP32) */
+    const double* g_t;    /* device [P][npad*npad]  g_t[j*npad+i] = G[i][j] */
+    const double* h;      /* device [P][npad] */
+} pb200_problem;
+
+/*
+ * Per-chain state, resident in HBM between launches.  Replaces the `optimise_settings` dict that
+ * OptimiseTask hands from iteration to iteration (prospect/optimiser.py:151-162) and the tail of the
+ * Chain object (prospect/mcmc.py:25-82).
+ */
+typedef struct pb200_chains {
+    int32_t   n_chains;        /* B (local to this GPU) */
+    double*   x;               /* device [B][npad]  current position (varying order, pads 0) */
+    double*   loglkl;          /* device [B]        loglkl of x */
+    double*   temperature;     /* device [B] */
+    double*   step_size;       /* device [B] */
+    double*   current_best;    /* device [B]  'current_best_loglkl' (optimiser.py:152) */
+    const int32_t*  point;     /* device [B]  profile-point index of the chain */
+    const uint32_t* chain_id;  /* device [B]  global chain id -> Philox counter word (GPU-count independent) */
+    uint32_t* steps_done;      /* device [B]  MH steps taken so far -> Philox counter word */
+    int32_t*  iteration;       /* device [B]  next iteration_number */
+    int32_t*  status;          /* device [B]  PB200_ACTIVE / CONVERGED / FAILED */
+    int32_t*  secant_stage;    /* device [B]  0,1: hard-coded multipliers; 2: secant (optimiser.py:96-137) */
+    double*   secant_prev_mult;/* device [B] */
+    double*   secant_cur_mult; /* device [B] */
+    double*   secant_prev_ar;  /* device [B] */
+} pb200_chains;
+
+/* The `profile:` schedule knobs (prospect/profile.py:129-362) that the device needs. */
+typedef struct pb200_schedule {
+    int32_t steps_per_iteration;   /* S */
+    int32_t step_mode;             /* PB200_STEP_* */
+    double  temperature_change;    /* (T_end/T_start)^(1/max_iterations), initialise_optimiser_task.py:138 */
+    double  step_size_change;      /* exponential rate, initialise_optimiser_task.py:146 */
+    double  adaptive_lo;           /* step_size_adaptive_interval[0] */
+    double  adaptive_hi;           /* step_size_adaptive_interval[1] */
+    double  adaptive_multiplier;   /* numeric step_size_adaptive_multiplier */
+    double  chi2_tolerance;        /* <= 0 or NaN: disabled (None / 0.0 in the yaml) */
+} pb200_schedule;
+
+/*
+ * One record per (iteration, chain): what SimulatedAnnealing.set_bestfit produces
+ * (prospect/optimiser.py:74-85) plus the settings the task ran with.  Row k = iteration_number.
+ * accepted = -1 marks "chain did not run this iteration" (converged / failed earlier).
+ */
+typedef struct pb200_records {
+    int32_t  max_iterations;    /* rows allocated */
+    double*  best_loglkl;       /* device [K][B]  exact FP64 loglkl of best_x */
+    double*  last_loglkl;       /* device [K][B] */
+    double*  temperature;       /* device [K][B] */
+    double*  step_size;         /* device [K][B] */
+    int32_t* accepted;          /* device [K][B]  accepted proposals (AR = (1+accepted)/(1+S)) */
+    double*  best_x;            /* device [K][B][npad]  (may be NULL) */
+    double*  last_x;            /* device [K][B][npad]  (may be NULL) */
+} pb200_records;
+
+/* Sample recording for jobtype mcmc (prospect/mcmc.py:69-73, tasks/mcmc_task.py:17-23). */
+typedef struct pb200_samples {
+    int32_t  mode;          /* PB200_RECORD_* */
+    int32_t  thin;          /* PB200_RECORD_THINNED: keep every thin-th step */
+    int32_t  capacity;      /* rows per chain */
+    double*  x;             /* device [B][capacity][npad] */
+    double*  loglkl;        /* device [B][capacity] */
+    int32_t* mult;          /* device [B][capacity] */
+    int32_t* count;         /* device [B]  rows used so far (in/out; the open last row is included) */
+} pb200_samples;
+
+const char* pb200_last_error(void);
+int pb200_abi_version(void);
+
+/* Number of SMs etc. of `device` (for grid sizing reports). */
+int pb200_device_info(int device, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor);
+
+/*
+ * loglkl + prior box for M positions.  Replaces BaseKernel.loglkl / logprior
+ * (prospect/kernels/base_kernel.py:72-102) -> AnalyticalKernel.Gaussian
+ * (prospect/kernels/analytical_kernel.py:59-66).
+ *   x [M][npad] device, point [M] device (NULL: all point 0), out_loglkl [M] device,
+ *   out_outside [M] device int32 (1 = outside the prior box; may be NULL).
+ */
+int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t* point, int32_t m,
+                       double* out_loglkl, int32_t* out_outside, void* stream);
+
+/*
+ * n_iter annealing iterations of every active chain in ONE launch: proposal, quadratic form,
+ * Philox accept/reject at the chain's temperature, running bestfit, then set_bestfit and
+ * get_next_iteration_settings on the device.  Replaces, per chain and iteration,
+ * OptimiseTask.run + emit_tasks (prospect/tasks/optimise_task.py:16-54),
+ * SimulatedAnnealing.__init__/optimise/set_bestfit/get_next_iteration_settings
+ * (prospect/optimiser.py:40-162) and MetropolisHastings.step/get_proposal (prospect/mcmc.py:163-190).
+ */
+int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                     const pb200_records* rec, int32_t n_iter, uint64_t seed, void* stream);
+
+/*
+ * n_steps Metropolis-Hastings steps per chain at the chain's temperature / step size, optionally
+ * recording the chain.  Replaces MCMCTask.run -> BaseMCMC.run_steps
+ * (prospect/tasks/mcmc_task.py:17-23, prospect/mcmc.py:131-138).  accepted_out [B] device (may be NULL).
+ */
+int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,
+                 const pb200_samples* samples, int32_t* accepted_out, void* stream);
+
+/*
+ * Stand-alone adaptive step-size / temperature bookkeeping for B chains (the same device function the
+ * fused kernel calls).  Replaces SimulatedAnnealing.get_next_iteration_settings
+ * (prospect/optimiser.py:87-162) + the chi2_tolerance test of OptimiseTask.emit_tasks.
+ *   accepted [B], best_loglkl [B] device: this iteration's result.
+ */
+int pb200_schedule_update(const pb200_chains* chains, const pb200_schedule* sched,
+                          const int32_t* accepted, const double* best_loglkl, void* stream);
+
+/*
+ * Running-bestfit reductions of the analysis side.  Replaces AnalyseProfileTask.sort_tasks
+ * (prospect/tasks/analyse_profile_task.py:91-121): per chain the first minimum over iterations,
+ * per point the first-minimum repetition and the mean over repetitions with a finite bestfit.
+ *   best_loglkl [K][B] + accepted [K][B] (records); n_iter rows used; B = R * P (rep-major).
+ *   out_chain_best [B], out_chain_iter [B], out_point_best [P], out_point_rep [P], out_point_avg [P].
+ */
+int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int32_t n_iter, int32_t b,
+                         int32_t n_points, int32_t reps,
+                         double* out_chain_best, int32_t* out_chain_iter,
+                         double* out_point_best, int32_t* out_point_rep, double* out_point_avg, void* stream);
+
+/*
+ * Weighted moments of N rows: sum w, sum w x_i, sum w x_i x_j (FP64).  Replaces
+ * compute_covariance_matrix (prospect/mcmc.py:84-97, np.cov(..., bias=True, fweights=mults)).
+ *   x [N][ld] device (first n columns used), w [N] device int32 (NULL: all 1),
+ *   out [1 + n + n*n] device, zeroed by the call.
+ */
+int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, int32_t ld, int32_t n,
+                           double* out, void* stream);
+
+/*
+ * Test hook: the N(0,1) / Exp(1) variates the samplers draw for one chain, steps [step0, step0+n_steps).
+ *   out_z [n_steps][n] device float, out_e [n_steps] device float.
+ */
+int pb200_rng_variates(uint64_t seed, uint32_t chain_id, uint32_t step0, int32_t n_steps, int32_t n,
+                       float* out_z, float* out_e, void* stream);
+
+/* Test hook: raw Philox-4x32-10 block (host side, no GPU needed). */
+void pb200_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PB200_H */

@@ -1,0 +1,225 @@
+// pb200_device.cuh -- device building blocks shared by the sampler kernels (sm_100a).
+//
+// Mapping: ONE WARP PER CHAIN.  Lane l owns coordinates l, l+32, ... (CPL = npad/32 per lane).
+// A chain is strictly sequential in steps, so the parallelism inside a step is what fills the SM:
+// the n normals, the O(n) whitened quadratic form and (on accept) the n x n proposal matvec are
+// spread over the 32 lanes and reduced with xor-shuffles.  The accept decision is warp-uniform,
+// so the expensive matvec only runs for steps whose likelihood test passed (no divergence).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pb200.h"
+
+namespace pb200 {
+
+constexpr int kWarpsPerCta = 4;
+constexpr unsigned kFull = 0xffffffffu;
+constexpr uint32_t kAcceptSlot = 0xffffffffu;   // Philox counter word of the accept/reject variates
+
+// ----------------------------------------------------------------------------------------------
+// Philox-4x32-10 (Salmon et al., SC'11).  Counter = (step_block, slot, chain_id, 0), key = seed.
+// slot = coordinate index for the proposal normals, kAcceptSlot for the accept variates, so the
+// stream of a chain depends only on (seed, chain_id, step) -- not on the thread mapping, the launch
+// partitioning or the number of GPUs.
+// ----------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                        uint32_t k0, uint32_t k1, uint32_t out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+#ifdef __CUDA_ARCH__
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), hi1 = __umulhi(0xCD9E8D57u, c2);
+#else
+        const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
+        const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
+#endif
+        const uint32_t lo0 = 0xD2511F53u * c0, lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 32 random bits -> uniform in (0, 1]:  u = w * 2^-32 + 2^-33 (rounds to 1.0f for the top words).
+__device__ __forceinline__ float u01(uint32_t w) {
+    return __fmaf_rn(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
+}
+
+// Box-Muller on the MUFU pipe: r = sqrt(-2 ln u1), theta = 2 pi u2 - pi.
+__device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
+    const float u1 = u01(w0), u2 = u01(w1);
+    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));       // -2 ln2 * log2(u1)
+    float s, c;
+    __sincosf(__fmaf_rn(u2, 6.283185307179586f, -3.141592653589793f), &s, &c);
+    z0 = r * c;
+    z1 = r * s;
+}
+
+// Exp(1) variate e = -ln u; the MH test exp(-Delta/T) > u becomes Delta < T * e.
+__device__ __forceinline__ float exp_variate(uint32_t w) {
+    return -0.6931471805599453f * __log2f(u01(w));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, m));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, m));
+    return v;
+}
+
+// Variates of the 4 steps of Philox block `blk` for this lane's CPL coordinates.
+//   z[r][k]: N(0,1) for coordinate lane+32r at step 4*blk+k (0 for pads);  e[k]: Exp(1) accept variate.
+// When n < npad the spare coordinate n carries the accept slot, otherwise every lane makes one
+// extra (identical) call -- both give the same numbers.
+template <int CPL>
+__device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t blk, int n,
+                                           int lane, float (&z)[CPL][4], float (&e)[4]) {
+    constexpr int NPAD = 32 * CPL;
+    const int acc_r = n >> 5, acc_lane = n & 31;
+    uint32_t w[4];
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int coord = lane + 32 * r;
+        philox4x32_10(blk, coord == n ? kAcceptSlot : (uint32_t)coord, chain_id, 0u, k0, k1, w);
+        box_muller(w[0], w[1], z[r][0], z[r][1]);
+        box_muller(w[2], w[3], z[r][2], z[r][3]);
+        if (coord >= n) { z[r][0] = z[r][1] = z[r][2] = z[r][3] = 0.0f; }
+        if (r == acc_r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = __shfl_sync(kFull, exp_variate(w[k]), acc_lane);
+        }
+    }
+    if (n >= NPAD) {
+        philox4x32_10(blk, kAcceptSlot, chain_id, 0u, k0, k1, w);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e[k] = exp_variate(w[k]);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Exact FP64 evaluation at a position: loglkl = sum_i q_i (1/2 (S_aa q)_i + f s_ab_i) + c0 and,
+// optionally, the whitened gradient gt = G q + h.  `qs` is this warp's [npad] double staging row.
+// ----------------------------------------------------------------------------------------------
+template <int CPL, bool WITH_GRAD>
+__device__ __forceinline__ double exact_eval(const pb200_problem& p, int pt, const double (&x)[CPL], int lane,
+                                             double* qs, double (&gt)[CPL]) {
+    constexpr int NPAD = 32 * CPL;
+    double q[CPL], v[CPL], g[CPL];
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int c = lane + 32 * r;
+        q[r] = x[r] - __ldg(p.mu + c);
+        qs[c] = q[r];
+        v[r] = 0.0;
+        g[r] = 0.0;
+    }
+    __syncwarp();
+    const double* __restrict__ saa = p.saa + lane;
+    const double* __restrict__ gtm = p.g_t + (size_t)pt * NPAD * NPAD + lane;
+    for (int j = 0; j < p.n; ++j) {
+        const double qj = qs[j];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            v[r] = fma(__ldg(saa + j * NPAD + 32 * r), qj, v[r]);
+            if (WITH_GRAD) g[r] = fma(__ldg(gtm + j * NPAD + 32 * r), qj, g[r]);
+        }
+    }
+    __syncwarp();
+    const double f = __ldg(p.f + pt);
+    double part = 0.0;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int c = lane + 32 * r;
+        part = fma(q[r], fma(0.5, v[r], f * __ldg(p.sab + c)), part);
+        if (WITH_GRAD) gt[r] = g[r] + __ldg(p.h + (size_t)pt * NPAD + c);
+    }
+    return warp_sum(part) + __ldg(p.c0 + pt);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Adaptive step-size / temperature bookkeeping of one chain after an iteration
+// (prospect/optimiser.py:87-162 + tasks/optimise_task.py:33-54).  Plain IEEE double ops in the
+// reference's order, no FMA contraction, so the result is bit-identical to the Python arithmetic.
+// ----------------------------------------------------------------------------------------------
+struct SchedState {
+    double temperature, step_size, current_best;
+    double prev_mult, cur_mult, prev_ar;
+    int32_t stage, status, iteration;
+};
+
+__host__ __device__ inline double pb_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+__host__ __device__ inline double pb_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+__host__ __device__ inline double pb_div(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+
+__host__ __device__ inline void schedule_next(const pb200_schedule& s, SchedState& st, int32_t accepted,
+                                              double best_loglkl) {
+    st.iteration += 1;
+    // chi2_tolerance stop: emit_tasks returns [] when the bestfit moved by <= tol and something was accepted
+    if (s.chi2_tolerance > 0.0) {
+        const double improvement = pb_add(st.current_best, -best_loglkl);
+        const bool keep_going = (improvement < 0.0) || (st.current_best == (double)INFINITY) ||
+                                (pb_mul(2.0, improvement) > s.chi2_tolerance);
+        if (!keep_going && accepted >= 1) {
+            st.status = PB200_CONVERGED;
+            return;
+        }
+    }
+    const double ar = pb_div((double)(1 + accepted), (double)(1 + s.steps_per_iteration));
+    const double new_temp = pb_mul(st.temperature, s.temperature_change);
+    double new_step = st.step_size;
+    if (s.step_mode == PB200_STEP_EXPONENTIAL) {
+        new_step = pb_mul(st.step_size, s.step_size_change);
+    } else if (s.step_mode == PB200_STEP_ADAPTIVE_FIXED) {
+        if (ar > s.adaptive_hi) new_step = pb_mul(st.step_size, pb_add(1.0, s.adaptive_multiplier));
+        else if (ar < s.adaptive_lo) new_step = pb_mul(st.step_size, pb_add(1.0, -s.adaptive_multiplier));
+    } else {
+        if (st.stage < 2) {
+            const double mag = st.stage == 0 ? 0.05 : 0.1;
+            double m;
+            if (ar > s.adaptive_hi) m = mag;
+            else if (ar < s.adaptive_lo) m = -mag;
+            else { st.status = PB200_FAILED; return; }        // unbound local in the reference
+            new_step = pb_mul(st.step_size, pb_add(1.0, m));
+            if (st.stage == 0) { st.prev_mult = m; st.prev_ar = ar; }
+            else               { st.cur_mult = m; }
+            st.stage += 1;
+        } else {
+            const double ar_desired = pb_div(pb_add(s.adaptive_lo, s.adaptive_hi), 2.0);
+            double m = pb_add(pb_mul(pb_div(pb_add(ar_desired, -ar), pb_add(ar, -st.prev_ar)),
+                                     pb_add(st.cur_mult, -st.prev_mult)), st.cur_mult);
+            if (1.0 < m) m = 1.0;            // min(m_new, 1.0): NaN stays NaN
+            if (!(m > -0.9)) m = -0.9;       // max(-0.9, m_new): NaN -> -0.9
+            new_step = pb_mul(st.step_size, pb_add(1.0, m));
+            st.prev_ar = ar;
+            st.prev_mult = st.cur_mult;
+            st.cur_mult = m;
+        }
+    }
+    st.current_best = best_loglkl;
+    st.temperature = new_temp;
+    st.step_size = new_step;
+}
+
+}  // namespace pb200

@@ -1,0 +1,51 @@
+"""Shared builders for the test-suite (golden toy problems, synthetic SPD targets)."""
+import os
+
+import numpy as np
+
+from prospect_public_b200.problem import build_problem
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def golden(name):
+    return np.load(os.path.join(GOLDEN, name))
+
+
+def mcmc_rows(d):
+    m = golden(f'toy{d}_mcmc.npz')
+    return np.concatenate([m[f'chain_{i}'] for i in range(4)], axis=0)
+
+
+def toy_profile_problem(d, points=None):
+    """x2-profile of the d-D toy with the reference's own per-value start points / bin covariances."""
+    k, ini = golden(f'toy{d}_kernel.npz'), golden(f'toy{d}_init.npz')
+    sel = np.arange(len(ini['values'])) if points is None else np.asarray(points)
+    hp = build_problem(k['means'], k['covmat'], [-2.5] * d, [2.5] * d, 1, ini['values'][sel], ini['covmat'][sel])
+    starts = ini['position'][sel][:, :-1]
+    return hp, starts, ini['initial_loglkl'][sel], ini['values'][sel], k
+
+
+def toy_free_problem(d, covmat=None):
+    """Nothing fixed (global optimisation / mcmc).  Default proposal: the kernel's default covmat."""
+    k = golden(f'toy{d}_kernel.npz')
+    cov = 0.005 * np.diag(np.full(d, 5.0)) if covmat is None else covmat
+    return build_problem(k['means'], k['covmat'], [-2.5] * d, [2.5] * d, None, None, cov), k
+
+
+def spd_target(d, seed=0, lam_range=(1e-3, 1e-1)):
+    """Synthetic correlated SPD Gaussian for d beyond the reference recipe:
+    C = Q diag(lam) Q^T, lam log-uniform, Q from the QR of a seeded Gaussian matrix, mu ~ U(0,1)."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    lam = np.exp(rng.uniform(np.log(lam_range[0]), np.log(lam_range[1]), d))
+    cov = (q * lam) @ q.T
+    return rng.uniform(0.0, 1.0, d), 0.5 * (cov + cov.T)
+
+
+def conditional_covariance(covmat, fixed_index):
+    """Covariance of the varying block given the fixed one (closed form) -- a good proposal covmat."""
+    s = np.linalg.inv(covmat)
+    s = 0.5 * (s + s.T)
+    n = covmat.shape[0] - 1
+    return np.linalg.inv(s[:n, :n])

@@ -1,0 +1,323 @@
+"""GPU parity tests: the sm_100a kernels (called through the C ABI of libpb200.so) against the CPU
+oracle on the same seeded inputs.
+
+Bit-level checks replay the GPU's own normal/exponential variates (pb200_rng_variates, the same device
+function the samplers call) through oracle/device_model.c, which restates the kernels' arithmetic in
+scalar C.  Everything integer (accept counts, multiplicities, iteration/status bookkeeping, argmin
+indices) must be identical; FP64 state must be bit-identical as well because both sides perform the
+same IEEE operations in the same order.
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import closed_form, device_model as dm, reference_port as rp  # noqa: E402
+from prospect_public_b200 import capi, engine  # noqa: E402
+from prospect_public_b200.problem import DeviceProblem, build_problem  # noqa: E402
+from tests.helpers import (conditional_covariance, golden, spd_target, toy_free_problem,  # noqa: E402
+                           toy_profile_problem)
+
+DEV = 'cuda:0'
+SEED = 0x5EED5EED12345
+
+
+def _gpu_variates(chain_id, step0, n_steps, n):
+    z, e = engine.rng_variates(DEV, SEED, chain_id, step0, n_steps, n)
+    torch.cuda.synchronize()
+    return z.cpu().numpy(), e.cpu().numpy()
+
+
+def test_device_is_blackwell_and_library_loaded():
+    sm, major, minor = (capi.C.c_int32(), capi.C.c_int32(), capi.C.c_int32())
+    capi.check(capi.lib().pb200_device_info(0, sm, major, minor))
+    assert major.value == 10 and sm.value >= 100
+
+
+@pytest.mark.parametrize('n', [19, 29, 32, 40, 255, 256])
+def test_rng_variates_match_model(n):
+    """Philox words are identical; the fast-math Box-Muller agrees with float64 to ~1e-6."""
+    z, e = _gpu_variates(chain_id=11, step0=6, n_steps=203, n=n)
+    zm, em = dm.variates(SEED, 11, 6, 203, n)
+    assert np.all(np.isfinite(z)) and np.all(e >= 0)
+    assert np.max(np.abs(z - zm)) < 2e-5
+    assert np.max(np.abs(e - em) / (1 + em)) < 2e-6
+
+
+def test_rng_variates_are_standard_normal_and_exponential():
+    from scipy import stats
+    z, e = _gpu_variates(chain_id=5, step0=0, n_steps=40000, n=30)
+    assert stats.kstest(z[:, 3], 'norm').pvalue > 1e-4
+    assert stats.kstest(z[::7].ravel(), 'norm').pvalue > 1e-4
+    assert stats.kstest(e, 'expon').pvalue > 1e-4
+    c = np.corrcoef(z[:, :6].T)
+    assert np.max(np.abs(c - np.eye(6))) < 0.03
+    assert abs(np.corrcoef(z[:-1, 0], z[1:, 0])[0, 1]) < 0.03          # consecutive steps
+    z2, _ = _gpu_variates(chain_id=6, step0=0, n_steps=1000, n=30)
+    assert not np.array_equal(z[:1000], z2)                              # chains differ
+    z3, _ = _gpu_variates(chain_id=5, step0=100, n_steps=50, n=30)
+    assert np.array_equal(z3, z[100:150])                                # keyed by absolute step
+
+
+@pytest.mark.parametrize('d', [20, 30])
+def test_loglkl_batch_matches_reference(d):
+    """A10/A11: batch chi^2 + prior box == reference port (1e-12 rel) and == device model (bit-exact)."""
+    hp, starts, init_ll, values, k = toy_profile_problem(d)
+    prob = DeviceProblem(hp, DEV)
+    rng = np.random.default_rng(3)
+    m_rows = 257
+    x = rng.uniform(-1.0, 1.5, (m_rows, hp.npad))
+    x[:, hp.n:] = 0.0
+    x[5, 2] = 2.6          # outside the box
+    x[9, 0] = -2.5000001
+    x[10, 0] = -2.5        # on the edge is inside (strict comparison)
+    pts = rng.integers(0, hp.n_points, m_rows).astype(np.int32)
+    ll, outside = engine.loglkl_batch(prob, torch.as_tensor(x, device=DEV), torch.as_tensor(pts, device=DEV))
+    ll, outside = ll.cpu().numpy(), outside.cpu().numpy()
+    model = dm.Model(hp)
+    t = rp.GaussianTarget(k['means'], k['covmat'])
+    for r in range(0, m_rows, 8):
+        ref = t.fix(1, values[pts[r]]).loglkl(x[r, :hp.n])
+        assert abs(ll[r] - ref) <= 1e-12 * abs(ref)
+        assert ll[r] == model.exact_eval(x[r, :hp.n], pts[r])
+    expect_out = np.zeros(m_rows, dtype=np.int32)
+    expect_out[[5, 9]] = 1
+    assert np.array_equal(outside, expect_out)
+    # start points of the reference's InitialiseOptimiserTask reproduce its initial_loglkl
+    xs = np.zeros((len(values), hp.npad))
+    xs[:, :hp.n] = starts
+    ll0, _ = engine.loglkl_batch(prob, torch.as_tensor(xs, device=DEV),
+                                 torch.arange(len(values), dtype=torch.int32, device=DEV))
+    assert np.allclose(ll0.cpu().numpy(), init_ll, rtol=1e-12, atol=0)
+
+
+def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED):
+    """Run B = reps * P chains on the GPU and through the scalar model with the GPU's variates."""
+    prob = DeviceProblem(hp, DEV)
+    p_count = hp.n_points
+    b = reps * p_count
+    point = np.tile(np.arange(p_count), reps).astype(np.int32)
+    x0 = np.tile(starts, (reps, 1))
+    cb = np.tile(init_ll, reps)
+    chains = engine.ChainBatch(prob, x0, point, temperature=sched_args['t0'], step_size=sched_args['s0'],
+                               current_best=cb)
+    s = sched_args
+    sched = engine.make_schedule(s['S'], s['tc'], mode, s.get('sc', 1.0), s['interval'], s.get('mult', 0.0),
+                                 s.get('tol'))
+    recs = engine.Records(prob, b, n_iter)
+    done = 0
+    for chunk in launches:
+        engine.anneal_run(prob, chains, sched, recs, chunk, SEED)
+        done += chunk
+    assert done == n_iter
+    torch.cuda.synchronize()
+    model = dm.Model(hp)
+    msched = dm.DmSchedule(s['S'], mode, s['tc'], s.get('sc', 1.0), s['interval'][0], s['interval'][1],
+                           s.get('mult', 0.0), s.get('tol') or 0.0)
+    out = {k: getattr(recs, k).cpu().numpy() for k in ('best_loglkl', 'last_loglkl', 'temperature', 'step_size',
+                                                        'accepted', 'best_x', 'last_x')}
+    final = {k: getattr(chains, k).cpu().numpy() for k in ('x', 'loglkl', 'temperature', 'step_size', 'iteration',
+                                                            'status', 'steps_done', 'current_best')}
+    for c in range(b):
+        z, e = _gpu_variates(c, 0, n_iter * s['S'], hp.n)
+        ch = model.new_chain(x0[c], point[c], chain_id=c, temperature=s['t0'], step_size=s['s0'],
+                             current_best=cb[c])
+        mo = model.anneal_chain(ch, msched, n_iter, SEED, z, e)
+        rows = ch.iteration
+        assert np.array_equal(out['accepted'][:rows, c], mo['accepted'][:rows]), c
+        for key in ('best_loglkl', 'last_loglkl', 'temperature', 'step_size'):
+            assert np.array_equal(out[key][:rows, c], mo[key][:rows]), (key, c)
+        assert np.array_equal(out['best_x'][:rows, c], mo['best_x'][:rows]), c
+        assert np.array_equal(out['last_x'][:rows, c], mo['last_x'][:rows]), c
+        assert np.all(out['accepted'][rows:, c] == -1)
+        assert final['iteration'][c] == ch.iteration and final['status'][c] == ch.status
+        assert final['steps_done'][c] == ch.steps_done
+        assert final['temperature'][c] == ch.temperature and final['step_size'][c] == ch.step_size
+        assert np.array_equal(final['x'][c], np.ctypeslib.as_array(ch.x, (hp.npad,)))
+        assert final['loglkl'][c] == ch.loglkl
+    return out, final
+
+
+def _toy_sched(**kw):
+    base = {'S': 250, 'tc': (0.001 / 0.1) ** (1 / 20), 't0': 0.1, 's0': 0.1, 'interval': (0.19, 0.21), 'mult': 0.3}
+    base.update(kw)
+    return base
+
+
+@pytest.mark.parametrize('d', [20, 30])
+def test_anneal_bit_exact_vs_model_replay(d):
+    """K1-style schedule, all profile points x 3 repetitions, 4 iterations in one launch."""
+    hp, starts, init_ll, values, k = toy_profile_problem(d, points=None if d == 20 else list(range(0, 32, 4)))
+    out, _ = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 4, [4])
+    ar = (1 + out['accepted']) / 251.0
+    assert 0.02 < ar.mean() < 0.8
+
+
+def test_anneal_launch_partitioning_is_invisible():
+    """1 launch of 4 iterations == 1+2+1 launches (state round-trips through HBM losslessly)."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0, 4, 9])
+    a, fa = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [4])
+    b, fb = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [1, 2, 1])
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    for key in fa:
+        assert np.array_equal(fa[key], fb[key]), key
+
+
+def test_anneal_exponential_secant_and_tolerance_modes():
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[2, 6])
+    _replay_anneal(hp, starts, init_ll, 2, _toy_sched(s0=0.5, sc=(0.05 / 0.5) ** (1 / 20)), 5, [5],
+                   mode=capi.STEP_EXPONENTIAL)
+    out, fin = _replay_anneal(hp, starts, init_ll, 4, _toy_sched(s0=0.3, interval=(0.24, 0.26), S=400), 8, [8],
+                              mode=capi.STEP_ADAPTIVE_SECANT)
+    _, fin = _replay_anneal(hp, starts, init_ll, 4, _toy_sched(tol=2.5, t0=0.01), 10, [10])
+    assert (fin['status'] == capi.CONVERGED).any()      # the chi2_tolerance stop fires for some chains
+
+
+def test_anneal_wide_path_bit_exact_npad64_and_256():
+    """CPL > 1 kernels (n = 40 -> npad 64; n = 255 -> npad 256) on synthetic SPD targets."""
+    for d, reps, s_steps in ((41, 3, 60), (256, 2, 24)):
+        mu, cov = spd_target(d, seed=d)
+        vals = np.array([mu[1] - 0.05, mu[1] + 0.08])
+        prop = conditional_covariance(cov, 1)
+        hp = build_problem(mu, cov, [-2.5] * d, [2.5] * d, 1, vals, np.stack([prop, prop]))
+        starts = np.stack([np.delete(mu, 1) + 0.01, np.delete(mu, 1) - 0.01])
+        init_ll = np.array([hp.loglkl(starts[p], p) for p in range(2)])
+        _replay_anneal(hp, starts, init_ll, reps, _toy_sched(S=s_steps, s0=2.4 / np.sqrt(d)), 3, [2, 1])
+
+
+def test_prior_box_rejections_bit_exact():
+    """Start next to the box edge with a huge step: many proposals leave the box and must be rejected."""
+    hp, k = toy_free_problem(20)
+    x0 = np.full((4, 20), 2.45)
+    ll0 = np.array([hp.loglkl(x0[0])] * 4)
+    out, _ = _replay_anneal(hp, x0[:1], ll0[:1], 4, _toy_sched(t0=1e6, s0=3.0, S=300, mult=0.0), 2, [2])
+    assert out['accepted'].min() >= 0 and out['accepted'].max() < 300
+    assert np.all(out['last_x'][..., :20] <= 2.5) and np.all(out['last_x'][..., :20] >= -2.5)
+
+
+def test_schedule_update_kernel_bit_exact():
+    """The stand-alone bookkeeping kernel == scalar model for random histories, all three modes."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0])
+    prob = DeviceProblem(hp, DEV)
+    rng = np.random.default_rng(8)
+    b = 512
+    for mode in (0, 1, 2):
+        chains = engine.ChainBatch(prob, np.tile(starts, (b, 1)), 0, temperature=0.1, step_size=0.37,
+                                   current_best=30.0)
+        sched = engine.make_schedule(250, 0.8, mode, 0.9, (0.19, 0.21), 0.3, 2.5 if mode == 1 else None)
+        msched = dm.DmSchedule(250, mode, 0.8, 0.9, 0.19, 0.21, 0.3, 2.5 if mode == 1 else 0.0)
+        mch = [dm.DmChain(None, 0.0, 0.1, 0.37, 30.0, 0.0, 0.0, 0.0, 0, 0, 0, 0, 0, 0) for _ in range(b)]
+        for it in range(6):
+            acc = rng.integers(0, 110, b).astype(np.int32)
+            acc[::9] = 50                                   # AR inside the interval / equal ARs
+            best = rng.uniform(1.0, 30.0, b)
+            engine.schedule_update(chains, sched, torch.as_tensor(acc, device=DEV), torch.as_tensor(best, device=DEV))
+            for c in range(b):
+                if mch[c].status == 0:
+                    dm.schedule_next(msched, mch[c], int(acc[c]), float(best[c]))
+        torch.cuda.synchronize()
+        for key, attr in (('temperature', 'temperature'), ('step_size', 'step_size'), ('status', 'status'),
+                          ('iteration', 'iteration'), ('current_best', 'current_best'),
+                          ('secant_stage', 'stage')):
+            got = getattr(chains, key).cpu().numpy()
+            exp = np.array([getattr(mc, attr) for mc in mch])
+            assert np.array_equal(got, exp, equal_nan=True) if got.dtype.kind == 'f' else np.array_equal(got, exp), \
+                (mode, key)
+
+
+def test_profile_reduce_matches_numpy():
+    """A20 sort_tasks: first minimum over iterations per chain, first-minimum repetition, mean of finite."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0])
+    prob = DeviceProblem(hp, DEV)
+    rng = np.random.default_rng(4)
+    p_count, reps, iters = 7, 45, 9
+    b = p_count * reps
+    recs = engine.Records(prob, b, iters, keep_positions=False)
+    best = rng.uniform(1, 2, (iters, b)).round(2)       # rounding creates exact ties
+    acc = rng.integers(0, 50, (iters, b)).astype(np.int32)
+    acc[5:, ::4] = -1                                   # chains that stopped early
+    acc[:, 3] = -1                                      # a chain that never ran
+    acc[:, [2 + p_count * r for r in range(reps)]] = -1  # a point where nothing finished
+    recs.best_loglkl.copy_(torch.as_tensor(best))
+    recs.accepted.copy_(torch.as_tensor(acc))
+    out = {k_: v.cpu().numpy() for k_, v in engine.profile_reduce(recs, iters, p_count, reps).items()}
+    masked = np.where(acc >= 0, best, np.inf)
+    cb = masked.min(axis=0)
+    ci = np.where(np.isfinite(cb), masked.argmin(axis=0), -1)
+    assert np.array_equal(out['chain_best'], cb) and np.array_equal(out['chain_iter'], ci)
+    per = cb.reshape(reps, p_count)
+    assert np.array_equal(out['point_best'], per.min(axis=0))
+    assert np.array_equal(out['point_rep'], per.argmin(axis=0))
+    avg = np.array([per[np.isfinite(per[:, j]), j].mean() if np.isfinite(per[:, j]).any() else np.inf
+                    for j in range(p_count)])
+    assert np.allclose(out['point_avg'], avg, rtol=1e-14)
+
+
+@pytest.mark.parametrize('n,rows', [(20, 2477), (30, 100000), (70, 5000)])
+def test_weighted_moments_match_np_cov(n, rows):
+    """A16: np.cov(bias=True, fweights=mults) from the FP64 moment reduction."""
+    rng = np.random.default_rng(n)
+    x = rng.normal(0.5, 0.2, (rows, n + 3))             # ld > n
+    w = rng.integers(1, 40, rows).astype(np.int32)
+    sw, swx, swxx = engine.weighted_moments(torch.as_tensor(x, device=DEV), n, torch.as_tensor(w, device=DEV))
+    cov = engine.covariance_from_moments(sw, swx, swxx).cpu().numpy()
+    ref = np.cov(x[:, :n], rowvar=False, bias=True, fweights=w)
+    assert sw.item() == w.sum()
+    assert np.allclose(cov, ref, rtol=1e-9, atol=1e-13)
+    sw1, _, _ = engine.weighted_moments(torch.as_tensor(x, device=DEV), n)
+    assert sw1.item() == rows
+
+
+def test_weighted_moments_on_the_shipped_bootstrap_chain():
+    """The covariance the reference's InitialiseOptimiserTask derives for x2 = 0.0 (golden fixture)."""
+    from tests.helpers import mcmc_rows
+    rows = mcmc_rows(20)
+    ini = golden('toy20_init.npz')
+    i = 3
+    sub = rows[ini['indices'][i]]
+    sw, swx, swxx = engine.weighted_moments(torch.as_tensor(np.ascontiguousarray(sub[:, 2:]), device=DEV), 20,
+                                            torch.as_tensor(sub[:, 0].astype(np.int32), device=DEV))
+    cov = engine.covariance_from_moments(sw, swx, swxx).cpu().numpy()
+    cov = np.delete(np.delete(cov, 1, 0), 1, 1)
+    assert np.allclose(cov, ini['covmat'][i], rtol=1e-9, atol=1e-14)
+
+
+@pytest.mark.parametrize('mode', [capi.RECORD_ACCEPTED, capi.RECORD_THINNED])
+def test_mh_recording_bit_exact_vs_model_replay(mode):
+    """jobtype mcmc: reference defaults (start 0, covmat 0.005*diag(width), T = step = 1), two launches."""
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    b, n1, n2, cap, thin = 6, 700, 333, 1100, 7
+    chains = engine.ChainBatch(prob, np.zeros((b, 20)), 0, temperature=1.0, step_size=1.0)
+    smp = engine.Samples(prob, b, cap, mode, thin)
+    a1 = engine.mh_run(prob, chains, n1, SEED, smp).cpu().numpy()
+    a2 = engine.mh_run(prob, chains, n2, SEED, smp).cpu().numpy()
+    model = dm.Model(hp)
+    cnt = smp.count.cpu().numpy()
+    gx, gl, gm = smp.x.cpu().numpy(), smp.loglkl.cpu().numpy(), smp.mult.cpu().numpy()
+    for c in range(b):
+        z, e = _gpu_variates(c, 0, n1 + n2, 20)
+        ch = model.new_chain(np.zeros(20), 0, chain_id=c, temperature=1.0, step_size=1.0)
+        m1, s = model.mh_chain(ch, n1, SEED, z, e, mode, thin, cap)
+        m2, s = model.mh_chain(ch, n2, SEED, z[n1:], e[n1:], mode, thin, cap, samples=s)
+        assert (a1[c], a2[c]) == (m1, m2)
+        assert cnt[c] == s['count'][0]
+        r = cnt[c]
+        assert np.array_equal(gm[c, :r], s['mult'][:r])
+        assert np.array_equal(gx[c, :r], s['x'][:r])
+        assert np.array_equal(gl[c, :r], s['loglkl'][:r])
+        if mode == capi.RECORD_ACCEPTED:
+            assert gm[c, :r].sum() == n1 + n2 + 1           # sum(mults) = steps + 1 (optimise_task.py:27)
+            assert r == 1 + a1[c] + a2[c]
+    assert np.array_equal(chains.steps_done.cpu().numpy(), np.full(b, n1 + n2))
+
+
+def test_mh_sample_overflow_is_reported():
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    chains = engine.ChainBatch(prob, np.zeros((2, 20)), 0)
+    smp = engine.Samples(prob, 2, 8, capi.RECORD_THINNED, 1)
+    engine.mh_run(prob, chains, 50, SEED, smp)
+    assert np.all(smp.count.cpu().numpy() == 50)            # > capacity: rows were dropped, never written OOB
