@@ -1,0 +1,331 @@
+#!/usr/bin/env python
+"""bench.py -- chain-steps/s of the annealing hot path on the 30-D Gaussian toy.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload global30|profile30]
+
+Workload (BASELINE.json configs[1], the N = 1 bench line): the reference's
+example_global_optimisation_toy.yaml on the 30-D toy (reference recipe, seed 0) with
+`repetitions: 4096` PER GPU -- 4096 chains x 20 iterations x 250 steps = 2.048e7 chain-steps per "step",
+exponential temperature 0.1 -> 1e-3, adaptive step size (interval [0.19, 0.21], multiplier 0.3, initial 0.1),
+start point / proposal covariance from the reference's own bootstrap MCMC (tests/golden/toy30_mcmc.npz).
+`--workload profile30` is BASELINE.json configs[2] (32 profile values x 256 repetitions, sharded by point).
+
+One JSON line is printed by rank 0:
+  value        whole-job chain-steps/s with chain state resident in HBM (CUDA events, max over ranks)
+  e2e          the same job through the host API (SimulatedAnnealing from HOST arrays: H2D of starts and
+               problem matrices, launches, D2H of the records) timed by wall clock around a device sync
+  roofline     fused annealing kernel vs the streaming-formulation HBM bound (SURVEY.md section 8d M4:
+               272 B per chain-step at n_pad = 32) -- see DESIGN.md for why the kernel can exceed it
+  cpu_baseline the oracle port of the reference (oracle/reference_port.py, 1 core) on a bounded sample
+`--impl reference` times that port on all host cores instead (one process per core, as the reference's
+`mode: threaded`), each step a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC, UNIT = 'chain-steps/s', 'chain-steps/s'
+D = 30
+STREAM_BYTES_PER_STEP = 2 * 4 * 32 + 16          # Bytes(n) = 2*4*n_pad + 16
+
+
+def workload_profile_kw(name, n_gpus):
+    base = dict(temperature_range=[0.1, 0.001], max_iterations=20, step_size_schedule='adaptive',
+                step_size_adaptive_interval=[0.19, 0.21], step_size_adaptive_multiplier=0.3,
+                step_size_adaptive_initial=0.1, steps_per_iteration=250)
+    if name == 'global30':
+        return 'global_optimisation', dict(base, repetitions=4096 * n_gpus), 1, 4096 * n_gpus
+    if name == 'profile30':
+        p = 32 * n_gpus
+        return 'profile', dict(base, repetitions=256, values=f'np.linspace(-1.0, 2.0, {p})'), p, 256
+    raise SystemExit(f'unknown workload {name}')
+
+
+def toy_inputs(folder):
+    from prospect_public_b200.toy import write_toy_inputs
+    k = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_kernel.npz'))
+    m = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_mcmc.npz'))
+    chains = [m[f'chain_{i}'] for i in range(4)]
+    return write_toy_inputs(folder, k['means'], k['covmat'], chains), k, np.concatenate(chains, axis=0)
+
+
+class ClockSampler(threading.Thread):
+    """SM clock + throttle reasons of this rank's GPU during the timed region (NVML)."""
+    REASONS = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap',
+               0x80: 'hw_power_brake_slowdown'}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self.stop_flag:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                mask = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h) if hasattr(
+                    pynvml, 'nvmlDeviceGetCurrentClocksEventReasons') else pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.01)
+        except Exception as exc:  # NVML missing: report it rather than fail the bench
+            self.reasons.add(f'nvml_unavailable:{type(exc).__name__}')
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {'sm_mhz': s[len(s) // 2] if s else None, 'sm_max_mhz': self.max_mhz, 'samples': len(s),
+                'reasons': sorted(self.reasons)}
+
+
+def cpu_port_chain_steps(target, mcmc_rows, jobtype, n_chains, seed0, n_iterations, steps):
+    """Full schedule of `n_chains` chains through the oracle port; returns chain-steps executed."""
+    from oracle import reference_port as rp
+    sched = rp.Schedule(steps_per_iteration=steps, max_iterations=20)
+    np.random.seed(seed0)
+    if jobtype == 'global_optimisation':
+        rp.run_annealing_job(target, mcmc_rows, sched, [], n_chains, None, n_iterations=n_iterations)
+    else:
+        vals = np.linspace(-1.0, 2.0, 32)[:n_chains]
+        rp.run_annealing_job(target, mcmc_rows, sched, vals, 1, 1, n_iterations=n_iterations)
+    return n_chains * n_iterations * steps
+
+
+def _cpu_worker(args):
+    k_means, k_cov, rows, jobtype, seed, n_iter, steps = args
+    from oracle import reference_port as rp
+    return cpu_port_chain_steps(rp.GaussianTarget(k_means, k_cov), rows, jobtype, 1, seed, n_iter, steps)
+
+
+def run_reference_arm(args):
+    """The reference's CPU implementation of the path (the pinned port), one process per host core."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, args.gpus)
+    k = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_kernel.npz'))
+    m = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_mcmc.npz'))
+    rows = np.concatenate([m[f'chain_{i}'] for i in range(4)], axis=0)
+    cores = os.cpu_count() or 1
+    n_iter, steps = 4, kw['steps_per_iteration']          # bounded sample: 4 of the 20 iterations per chain
+    per_step = cores * n_iter * steps
+    with mp.get_context('spawn').Pool(cores) as pool:
+        job = lambda s: [(k['means'], k['covmat'], rows, jobtype, 1000 * s + c, n_iter, steps) for c in range(cores)]
+        for w in range(args.warmup):
+            pool.map(_cpu_worker, job(w))
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(args.steps):
+            done += sum(pool.map(_cpu_worker, job(args.warmup + s)))
+        dt = time.perf_counter() - t0
+    value = done / dt
+    sample = (f'{cores} chains (one per core) x {n_iter} iterations x {steps} steps per step of the '
+              f'{args.workload} workload, {args.steps} steps')
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': f'{args.workload}: 30-D toy, {jobtype}, oracle port of the reference CPU path'},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=30)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='global30', choices=['global30', 'profile30'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        return run_reference_arm(args)
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import torch.distributed as dist
+    from prospect_public_b200 import capi, engine
+    from prospect_public_b200.config import Configuration
+    from prospect_public_b200.distributed import init_from_env
+    from prospect_public_b200.initialise import initialise_optimiser
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.optimiser import (SimulatedAnnealing, get_initial_step_size_change,
+                                                get_temperature_change)
+    from prospect_public_b200.toy import annealing_yaml
+
+    capi.lib()                                   # fail loudly if the CUDA extension is missing
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    if world != args.gpus:
+        raise SystemExit(f'--gpus {args.gpus} but WORLD_SIZE={world}: launch with torch.distributed.run')
+    rank, world, active = init_from_env('nccl') if world > 1 else (0, 1, False)
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local)
+    dev = f'cuda:{local}'
+
+    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, world)
+    tmp = tempfile.mkdtemp(prefix=f'pb200_bench_r{rank}_')
+    paths, kgold, rows = toy_inputs(tmp)
+    cfg = Configuration(annealing_yaml(paths, os.path.join(tmp, 'out'), jobtype=jobtype, write=False, **kw))
+    kernel = initialise_kernel(cfg.kernel, None, rank, dev)
+    starts, values = initialise_optimiser(cfg, kernel)
+    n_iter, steps = int(cfg.profile.max_iterations), int(cfg.profile.steps_per_iteration)
+
+    def settings(seed):
+        return {'current_best_loglkl': starts.initial_loglkl, 'initial_position': starts.positions,
+                'covmat': starts.covmats, 'temperature': cfg.profile.temperature_range[0],
+                'temperature_change': get_temperature_change(cfg), 'step_size': cfg.profile.step_size_range[0],
+                'step_size_change': get_initial_step_size_change(cfg), 'iteration_number': 0, 'repetitions': reps,
+                'fixed_param_val': values if jobtype == 'profile' else None, 'max_rows': n_iter, 'seed': seed}
+
+    # ---------------- device-resident arm: state reset + L2 flush between steps are untimed ----------------
+    sa = SimulatedAnnealing(cfg, kernel, settings(1234), keep_positions=True)
+    b_local = sa.n_chains
+    pristine = {k: getattr(sa.batch, k).clone() for k in ('x', 'temperature', 'step_size', 'current_best',
+                                                           'steps_done', 'iteration', 'status', 'secant_stage')}
+    flush = torch.empty(192 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)    # 192 MiB > 126 MB L2
+
+    def reset(step):
+        for k, v in pristine.items():
+            getattr(sa.batch, k).copy_(v)
+        sa.iterations_done = 0
+        sa.seed = 1234 + step
+        sa.records.accepted.fill_(-1)
+        flush.add_(1.0)
+
+    def one_step():
+        sa.run_schedule(n_iter)
+        sa.reduce_over_iterations()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for w in range(args.warmup):
+        reset(w)
+        one_step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    kev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = engine.LAUNCHES['count']
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        reset(args.warmup + s)
+        launches_before = engine.LAUNCHES['count']
+        ev[s][0].record()
+        if world == 1:
+            kev[s][0].record()
+            sa.run_schedule(n_iter)
+            kev[s][1].record()
+            sa.reduce_over_iterations()
+        else:
+            one_step()
+        ev[s][1].record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    gpu_launches = engine.LAUNCHES['count'] - launches0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max = float(t.item())
+    chain_steps_per_step = n_points * reps * n_iter * steps          # global
+    value = chain_steps_per_step * args.steps / (dev_ms_max * 1e-3)
+
+    roofline = None
+    if world == 1:
+        k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
+        achieved = STREAM_BYTES_PER_STEP * b_local * n_iter * steps / (k_ms * 1e-3) / 1e9
+        peak, src = 6650.0, 'fallback'
+        try:
+            with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+                peak, src = float(json.load(f)['hbm_gbs']), 'measured'
+        except Exception:
+            pass
+        roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                    'traffic': None, 'kernel': 'anneal_kernel<1> (20 iterations fused in one launch)',
+                    'kernel_ms': k_ms, 'peak_source': src,
+                    'algorithmic_bytes_per_chain_step': STREAM_BYTES_PER_STEP,
+                    'note': 'streaming-formulation bound; the kernel keeps chain state in registers, so DRAM '
+                            'traffic is ~0 and the binding resource is FP32/MUFU issue (DESIGN.md)'}
+
+    # ---------------- end-to-end arm: host arrays in, host arrays out, every step ----------------
+    e2e_steps = max(3, min(args.steps, 10))
+    h2d = d2h = 0
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(e2e_steps):
+        sa2 = SimulatedAnnealing(cfg, kernel, settings(9000 + s), keep_positions=True)
+        sa2.run_schedule(n_iter)
+        red = sa2.reduce_over_iterations()
+        bf = sa2.set_bestfit(n_iter - 1)
+        out = {k: v.cpu() for k, v in red.items()} if red is not None else None
+        if s == 0:
+            h2d = sum(t_.numel() * t_.element_size() for t_ in sa2.problem.t.values())
+            h2d += sum(getattr(sa2.batch, k).numel() * getattr(sa2.batch, k).element_size()
+                       for k in ('x', 'temperature', 'step_size', 'current_best', 'point', 'chain_id', 'steps_done'))
+            d2h = sa2.n_chains * (8 + 4 + 8 * sa2.problem.n)
+            if out is not None:
+                d2h += sum(v.numel() * v.element_size() for v in out.values())
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = chain_steps_per_step * e2e_steps / float(t.item())
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import reference_port as rp
+        n_sample = 6
+        t0 = time.perf_counter()
+        done = cpu_port_chain_steps(rp.GaussianTarget(kgold['means'], kgold['covmat']), rows, jobtype, n_sample, 0,
+                                    n_iter, steps)
+        dt = time.perf_counter() - t0
+        cpu_baseline = {'value': done / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+                        'sample': f'{n_sample} chains x {n_iter} iterations x {steps} steps of the same workload '
+                                  f'({done} chain-steps, {dt:.1f} s) through oracle/reference_port.py'}
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+                'warmup': args.warmup, 'ms_per_step': dev_ms_max / args.steps, 'higher_is_better': True,
+                'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': {'workload': f'{args.workload}: 30-D Gaussian toy (reference recipe, seed 0), {jobtype}, '
+                                       f'{n_points} point(s) x {reps} repetitions = {n_points * reps} chains '
+                                       f'({b_local} per GPU) x {n_iter} iterations x {steps} steps',
+                           'chain_steps_per_step': chain_steps_per_step, 'l2': 'flushed (192 MiB write) between steps',
+                           'precision': 'FP32 proposal / acceptance arithmetic, FP64 chain state and reported chi^2',
+                           'wall_ms_per_step_incl_reset_and_flush': 1e3 * t_wall / args.steps},
+                'clocks': sampler.summary(),
+                'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                        'steps': e2e_steps},
+                'gpu_launches': gpu_launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

@@ -13,6 +13,13 @@ from . import capi
 from .problem import DeviceProblem
 
 
+LAUNCHES = {'count': 0}     # kernels of libpb200 launched through this module (bench.py reports it)
+
+
+def _count(n=1):
+    LAUNCHES['count'] += n
+
+
 def _stream_ptr(stream=None):
     s = torch.cuda.current_stream() if stream is None else stream
     return C.c_void_p(s.cuda_stream)
@@ -105,18 +112,21 @@ def loglkl_batch(problem: DeviceProblem, x, point=None, stream=None):
     m = x.shape[0]
     out = torch.empty(m, dtype=torch.float64, device=problem.device)
     outside = torch.empty(m, dtype=torch.int32, device=problem.device)
+    _count()
     capi.check(capi.lib().pb200_loglkl_batch(C.byref(problem.c), capi.ptr(x), capi.ptr(point), m, capi.ptr(out),
                                              capi.ptr(outside), _stream_ptr(stream)))
     return out, outside
 
 
 def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, stream=None):
+    _count()
     capi.check(capi.lib().pb200_anneal_run(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
                                            C.byref(records.c), int(n_iter), C.c_uint64(seed), _stream_ptr(stream)))
 
 
 def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None):
     accepted = torch.zeros(chains.n_chains, dtype=torch.int32, device=problem.device)
+    _count()
     capi.check(capi.lib().pb200_mh_run(C.byref(problem.c), C.byref(chains.c), int(n_steps), C.c_uint64(seed),
                                        C.byref(samples.c) if samples is not None else None, capi.ptr(accepted),
                                        _stream_ptr(stream)))
@@ -124,6 +134,7 @@ def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, 
 
 
 def schedule_update(chains: ChainBatch, schedule, accepted, best_loglkl, stream=None):
+    _count()
     capi.check(capi.lib().pb200_schedule_update(C.byref(chains.c), C.byref(schedule), capi.ptr(accepted),
                                                 capi.ptr(best_loglkl), _stream_ptr(stream)))
 
@@ -139,6 +150,7 @@ def profile_reduce(records: Records, n_iter, n_points, reps, stream=None):
         'point_rep': torch.empty(n_points, dtype=torch.int32, device=dev),
         'point_avg': torch.empty(n_points, dtype=torch.float64, device=dev),
     }
+    _count()
     capi.check(capi.lib().pb200_profile_reduce(
         capi.ptr(records.best_loglkl), capi.ptr(records.accepted), int(n_iter), b, int(n_points), int(reps),
         capi.ptr(out['chain_best']), capi.ptr(out['chain_iter']), capi.ptr(out['point_best']),
@@ -151,6 +163,7 @@ def weighted_moments(x, n, weights=None, stream=None):
     -> (sum_w, sum_wx [n], sum_wxx [n, n]) device tensors."""
     x2 = x.reshape(-1, x.shape[-1])
     out = torch.empty(1 + n + n * n, dtype=torch.float64, device=x.device)
+    _count()
     capi.check(capi.lib().pb200_weighted_moments(capi.ptr(x2), capi.ptr(weights), x2.shape[0], x2.shape[1], int(n),
                                                  capi.ptr(out), _stream_ptr(stream)))
     return out[0], out[1:1 + n], out[1 + n:].reshape(n, n)
@@ -165,6 +178,7 @@ def covariance_from_moments(sum_w, sum_wx, sum_wxx):
 def rng_variates(device, seed, chain_id, step0, n_steps, n, stream=None):
     z = torch.empty((n_steps, n), dtype=torch.float32, device=device)
     e = torch.empty(n_steps, dtype=torch.float32, device=device)
+    _count()
     capi.check(capi.lib().pb200_rng_variates(C.c_uint64(seed), int(chain_id), int(step0), int(n_steps), int(n),
                                              capi.ptr(z), capi.ptr(e), _stream_ptr(stream)))
     return z, e

@@ -1,0 +1,211 @@
+"""Chain container, covariance estimator and the batched Metropolis-Hastings sampler.
+
+Mirrors prospect/mcmc.py: `Chain` (:25-82), `collapse_chains` (:84-91), `compute_covariance_matrix`
+(:93-97), `initialise_mcmc` (:13-18) and `MetropolisHastings` (:104-190) keep their names and meaning.
+What changes is the unit of work: one sampler object advances MANY independent chains per call -- one
+GPU warp each (pb200_mh_run) -- instead of one Python-loop chain per process.
+"""
+from collections import defaultdict
+
+import numpy as np
+
+from . import capi
+
+
+class Chain:
+    """Accepted points with multiplicities, -log L values and per-parameter positions (MontePython layout)."""
+
+    def __init__(self, initial_mults=None, initial_loglkls=None, initial_positions=None):
+        self.mults, self.loglkls, self.positions = [], [], defaultdict(list)
+        if initial_mults is not None and initial_loglkls is not None and initial_positions is not None:
+            self.mults += list(initial_mults)
+            self.loglkls += list(initial_loglkls)
+            for name, vec in initial_positions.items():
+                self.positions[name] += list(vec)
+
+    @classmethod
+    def from_arrays(cls, names, mults, loglkls, x):
+        ch = cls()
+        ch.mults = list(np.asarray(mults))
+        ch.loglkls = list(np.asarray(loglkls))
+        for i, name in enumerate(names):
+            ch.positions[name] = list(x[:, i])
+        return ch
+
+    def last_varying_position(self, names):
+        return {n: [self.positions[n][-1]] for n in names}
+
+    @property
+    def last_position(self):
+        return {n: [vec[-1]] for n, vec in self.positions.items()}
+
+    @property
+    def N(self):
+        lengths = {len(self.mults), len(self.loglkls)} | {len(v) for v in self.positions.values()}
+        if len(lengths) != 1:
+            raise ValueError('Invalid dimensions in Chain: Non-compatible length of mults, loglkls and positions.')
+        return len(self.mults)
+
+    @property
+    def data(self):
+        """[N_points, 2 + N_params] array: multiplicity, -log L, parameters."""
+        pos = np.array(list(self.positions.values()))
+        return np.concatenate([np.stack([self.mults, self.loglkls], axis=0), pos], axis=0).T
+
+    def __getitem__(self, idx):
+        return {n: [vec[idx]] for n, vec in self.positions.items()}
+
+    def push_position(self, new_loglkl, new_position):
+        self.mults.append(1)
+        self.loglkls.append(new_loglkl)
+        for n, vec in self.positions.items():
+            vec.append(new_position[n][0])
+
+    def from_indices(self, index_list):
+        pos = {n: np.take(vec, index_list) for n, vec in self.positions.items()}
+        return Chain(list(np.take(self.mults, index_list)), list(np.take(self.loglkls, index_list)), pos)
+
+
+def collapse_chains(chain_list):
+    total = Chain()
+    for ch in chain_list:
+        total.mults += list(ch.mults)
+        total.loglkls += list(ch.loglkls)
+        for n, vec in ch.positions.items():
+            total.positions[n] += list(vec)
+    return total
+
+
+def compute_covariance_matrix(chain_list, device='cuda:0'):
+    """np.cov(x, bias=True, fweights=mults) of the collapsed chains, reduced on the GPU in FP64
+    (pb200_weighted_moments)."""
+    import torch
+    from . import engine
+    total = collapse_chains(chain_list)
+    data = total.data
+    x = torch.as_tensor(np.ascontiguousarray(data[:, 2:]), device=device)
+    w = torch.as_tensor(np.asarray(total.mults).astype(np.int32), device=device)
+    cov = engine.covariance_from_moments(*engine.weighted_moments(x, x.shape[1], w))
+    return cov.cpu().numpy()
+
+
+def initialise_mcmc(config_mcmc, kernel, **mcmc_args):
+    if config_mcmc.algorithm in ('MetropolisHastings', 'Metropolis Hastings'):
+        return MetropolisHastings(config_mcmc, kernel, **mcmc_args)
+    raise ValueError('You have specified a non-existing MCMC type.')
+
+
+class MetropolisHastings:
+    """`n_chains` independent MH chains on one GPU.
+
+    config_mcmc: the `mcmc:` section (temperature, step_size, start_from_covmat, start_from_position,
+    steps_per_iteration).  mcmc_args: n_chains (default config_mcmc.N_chains), seed, chain_ids (global ids for
+    the Philox streams), chains (list[Chain] to continue), record ('accepted' | 'thinned' | None), thin."""
+
+    def __init__(self, config_mcmc, kernel, **mcmc_args):
+        from . import engine
+        self.config_mcmc = config_mcmc
+        self.kernel = kernel
+        self.seed = int(mcmc_args.get('seed', 0))
+        names = kernel.varying_param_names
+        n = len(names)
+        if config_mcmc.start_from_covmat is not None:
+            cm = config_mcmc.start_from_covmat
+            self.covmat = np.array(cm) if not isinstance(cm, str) else kernel.read_covmat(cm)
+        else:
+            self.covmat = kernel.get_default_covmat()
+        prior = mcmc_args.get('chains')
+        self.n_chains = len(prior) if prior is not None else int(mcmc_args.get('n_chains', config_mcmc.N_chains))
+        b = self.n_chains
+        if prior is not None:
+            x0 = np.array([[ch.positions[nm][-1] for nm in names] for ch in prior], dtype=np.float64)
+        elif config_mcmc.start_from_position is not None:
+            x0 = np.tile(np.asarray(kernel.read_initial_position(config_mcmc.start_from_position), dtype=float), (b, 1))
+        else:
+            start = kernel.get_default_initial_position()
+            x0 = np.tile(np.array([start[nm][0] for nm in names], dtype=np.float64), (b, 1))
+        self.problem = kernel.device_problem(proposal_covmats=np.asarray(self.covmat)[None])
+        ids = mcmc_args.get('chain_ids')
+        self.batch = engine.ChainBatch(self.problem, x0, 0, chain_id=ids, temperature=config_mcmc.temperature,
+                                       step_size=config_mcmc.step_size,
+                                       steps_done=mcmc_args.get('steps_done', 0))
+        self.record = mcmc_args.get('record', 'accepted')
+        self.thin = int(mcmc_args.get('thin', 1))
+        self._prior = prior
+        self._samples = None
+        self._names = names
+        self.accepted = np.zeros(b, dtype=np.int64)
+        self.steps = 0
+
+    def _ensure_samples(self, n_steps):
+        from . import engine
+        if self.record is None:
+            return None
+        mode = capi.RECORD_ACCEPTED if self.record == 'accepted' else capi.RECORD_THINNED
+        need = n_steps + 1 if mode == capi.RECORD_ACCEPTED else n_steps // self.thin + 1
+        if self._samples is None:
+            self._samples = engine.Samples(self.problem, self.n_chains, need, mode, self.thin)
+            self._used = 0
+        else:
+            # grow: copy the rows recorded so far into a larger buffer
+            import torch
+            old = self._samples
+            cap = old.capacity + need
+            new = engine.Samples(self.problem, self.n_chains, cap, mode, self.thin)
+            new.x[:, :old.capacity] = old.x
+            new.loglkl[:, :old.capacity] = old.loglkl
+            new.mult[:, :old.capacity] = old.mult
+            new.count.copy_(old.count)
+            self._samples = new
+        return self._samples
+
+    def step(self):
+        self.run_steps(1)
+
+    def run_steps(self, steps_per_iteration):
+        from . import engine
+        smp = self._ensure_samples(steps_per_iteration)
+        acc = engine.mh_run(self.problem, self.batch, steps_per_iteration, self.seed, smp)
+        self.accepted += acc.cpu().numpy()
+        self.steps += steps_per_iteration
+
+    def samples_numpy(self):
+        """(x [B, cap, n], loglkl [B, cap], mult [B, cap], count [B]) of everything recorded so far."""
+        s = self._samples
+        n = self.problem.n
+        cnt = s.count.cpu().numpy()
+        if np.any(cnt > s.capacity):
+            raise capi.Pb200Error('sample buffer overflow')
+        return s.x[:, :, :n].cpu().numpy(), s.loglkl.cpu().numpy(), s.mult.cpu().numpy(), cnt
+
+    @property
+    def chains(self):
+        """list[Chain]; continued chains are the earlier rows followed by the new ones (the open last row of
+        the earlier segment keeps accumulating multiplicity, exactly like Chain.mults[-1] += 1)."""
+        x, ll, mult, cnt = self.samples_numpy()
+        fixed = {nm: par['fixed_value'] for nm, par in self.kernel.param['fixed'].items()}
+        out = []
+        for c in range(self.n_chains):
+            r = cnt[c]
+            ch = Chain.from_arrays(self._names, mult[c, :r], ll[c, :r], x[c, :r])
+            for nm, val in fixed.items():
+                ch.positions[nm] = [val] * r
+            if self._prior is not None:
+                prev = self._prior[c]
+                merged = Chain(list(prev.mults), list(prev.loglkls), {k: list(v) for k, v in prev.positions.items()})
+                # row 0 of the new segment is the previous chain's last point: fold its multiplicity in
+                merged.mults[-1] += ch.mults[0] - 1
+                merged.mults += ch.mults[1:]
+                merged.loglkls += ch.loglkls[1:]
+                for k in merged.positions:
+                    merged.positions[k] += ch.positions[k][1:]
+                ch = merged
+            out.append(ch)
+        return out
+
+    @property
+    def chain(self):
+        return self.chains[0]
+
+    def finalize(self):
+        pass

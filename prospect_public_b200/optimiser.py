@@ -1,0 +1,198 @@
+"""Batched simulated annealing: every (profile point x repetition) chain of a job advances together.
+
+Mirrors prospect/optimiser.py (`initialise_optimiser` :6-11, `SimulatedAnnealing` :40-162) and the
+OptimiseTask loop around it (prospect/tasks/optimise_task.py:16-54).  The method names and the meaning of
+`settings` / `bestfit` are kept; values that were scalars per task are arrays over the chains of this rank
+(chain c = repetition * n_points + point, tasks/initialise_profile_task.py:16-26).  One call of
+`optimise()` is one annealing iteration of ALL chains (one kernel launch); `run_schedule()` runs many
+iterations per launch with set_bestfit / get_next_iteration_settings evaluated on the device.
+"""
+import math
+
+import numpy as np
+
+from . import capi
+from .distributed import RecordGatherer, dist_info, global_chain_index, shard_grid
+
+
+def initialise_optimiser(config, kernel, optimise_settings):
+    if config.profile.optimiser == 'simulated annealing':
+        return SimulatedAnnealing(config, kernel, optimise_settings)
+    raise ValueError('You have specified a non-existing optimizer type.')
+
+
+def get_temperature_change(config):
+    """(T_end / T_start) ** (1 / max_iterations)  (tasks/initialise_optimiser_task.py:133-141)."""
+    if config.profile.temperature_schedule != 'exponential':
+        raise ValueError('Invalid temperature schedule.')
+    tr = config.profile.temperature_range
+    return (tr[1] / tr[0]) ** (1 / config.profile.max_iterations)
+
+
+def get_initial_step_size_change(config):
+    """tasks/initialise_optimiser_task.py:143-156."""
+    prof = config.profile
+    if prof.step_size_schedule == 'exponential':
+        return (prof.step_size_range[1] / prof.step_size_range[0]) ** (1 / prof.max_iterations)
+    if prof.step_size_schedule == 'adaptive':
+        return {} if prof.step_size_adaptive_multiplier == 'adaptive' else None
+    raise ValueError('Invalid step size schedule.')
+
+
+def step_mode_of(profile_cfg):
+    if profile_cfg.step_size_schedule == 'exponential':
+        return capi.STEP_EXPONENTIAL
+    if profile_cfg.step_size_adaptive_multiplier == 'adaptive':
+        return capi.STEP_ADAPTIVE_SECANT
+    return capi.STEP_ADAPTIVE_FIXED
+
+
+class SimulatedAnnealing:
+    """optimise_settings (arrays over the P profile points; P = 1 for a global optimisation):
+        initial_position [P, n] (varying order), covmat [P, n, n], current_best_loglkl [P],
+        fixed_param_val [P] or None, repetitions R, temperature, temperature_change, step_size,
+        step_size_change, iteration_number (0), max_rows (record rows to allocate), seed."""
+
+    def __init__(self, config, kernel, optimise_settings, keep_positions=True):
+        from . import engine
+        self.config, self.kernel, self.settings = config, kernel, optimise_settings
+        prof = config.profile
+        if prof.steps_per_iteration is None:
+            raise ValueError("The GPU path needs 'steps_per_iteration' (time-boxed 'minutes_per_iteration' "
+                             'iterations would make results depend on the hardware).')
+        s = optimise_settings
+        if 'initial_position' not in s or len(s['initial_position']) == 0:
+            raise ValueError('No point to start the optimisation from.')
+        if 'covmat' not in s:
+            raise ValueError('No covmat to start the optimisation from.')
+        starts = np.atleast_2d(np.asarray(s['initial_position'], dtype=np.float64))
+        covs = np.asarray(s['covmat'], dtype=np.float64)
+        covs = covs[None] if covs.ndim == 2 else covs
+        self.covmat = covs
+        fixed = s.get('fixed_param_val')
+        self.n_points = starts.shape[0]
+        self.reps = int(s.get('repetitions', 1))
+        self.rank, self.world, _ = dist_info()
+        pt, rep = shard_grid(self.n_points, self.reps, self.rank, self.world)
+        self.point_global, self.rep = pt, rep
+        self.local_points = np.unique(pt)
+        local_of = {g: i for i, g in enumerate(self.local_points)}
+        point_local = np.array([local_of[g] for g in pt], dtype=np.int32)
+        fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
+        self.problem = kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covs[self.local_points])
+        cb = np.broadcast_to(np.asarray(s.get('current_best_loglkl', math.inf), dtype=np.float64), (self.n_points,))
+        self.batch = engine.ChainBatch(self.problem, starts[pt], point_local,
+                                       chain_id=global_chain_index(pt, rep, self.n_points),
+                                       temperature=s['temperature'], step_size=s['step_size'], current_best=cb[pt])
+        change = s.get('step_size_change')
+        interval = prof.step_size_adaptive_interval or (0.0, 1.0)
+        mult = prof.step_size_adaptive_multiplier
+        self.schedule = engine.make_schedule(
+            prof.steps_per_iteration, s['temperature_change'], step_mode_of(prof),
+            change if isinstance(change, float) else 1.0, interval, mult if not isinstance(mult, str) else 0.0,
+            prof.chi2_tolerance)
+        self.max_rows = int(s.get('max_rows', prof.max_iterations))
+        self.records = engine.Records(self.problem, self.batch.n_chains, self.max_rows, keep_positions)
+        self.seed = int(s.get('seed', 0))
+        self.iterations_done = int(s.get('iteration_number', 0))
+        self.bestfit = None
+        self._gatherer = None
+
+    @property
+    def n_chains(self):
+        return self.batch.n_chains
+
+    # --- the reference's three verbs -------------------------------------------------------------
+    def optimise(self, n_iterations=1, stream=None):
+        """Run `n_iterations` annealing iterations of every chain in one launch."""
+        from . import engine
+        engine.anneal_run(self.problem, self.batch, self.schedule, self.records, n_iterations, self.seed, stream)
+        self.iterations_done += n_iterations
+
+    def set_bestfit(self, iteration=None):
+        """Host view of one iteration's records: loglkl, acceptance_rate, accepted_steps, position per chain
+        (optimiser.py:74-85).  Chains that did not run that iteration have accepted_steps = 0 / loglkl = inf."""
+        k = self.iterations_done - 1 if iteration is None else iteration
+        r = self.records
+        acc = r.accepted[k].cpu().numpy()
+        ran = acc >= 0
+        names = self.kernel.varying_param_names
+        bx = r.best_x[k, :, :self.problem.n].cpu().numpy() if r.best_x is not None else None
+        steps = self.schedule.steps_per_iteration
+        self.bestfit = {
+            'loglkl': np.where(ran, r.best_loglkl[k].cpu().numpy(), np.inf),
+            'acceptance_rate': np.where(ran, (1 + acc) / (1.0 + steps), np.nan),
+            'accepted_steps': np.where(ran, 1 + acc, 0),
+            'iteration_number': k,
+            'position': {nm: bx[:, i] for i, nm in enumerate(names)} if bx is not None else {},
+        }
+        return self.bestfit
+
+    def get_next_iteration_settings(self):
+        """The settings the next iteration will run with (already computed on the device, optimiser.py:87-162)."""
+        b = self.batch
+        out = {
+            'current_best_loglkl': b.current_best.cpu().numpy(),
+            'initial_position': b.positions(),
+            'covmat': self.covmat,
+            'temperature': b.temperature.cpu().numpy(),
+            'temperature_change': self.schedule.temperature_change,
+            'step_size': b.step_size.cpu().numpy(),
+            'iteration_number': b.iteration.cpu().numpy(),
+            'status': b.status.cpu().numpy(),
+        }
+        if self.settings.get('fixed_param_val') is not None:
+            out['fixed_param_val'] = np.asarray(self.settings['fixed_param_val'])[self.point_global]
+        return out
+
+    # --- whole schedules ---------------------------------------------------------------------------
+    def run_schedule(self, n_iterations, iterations_per_launch=None, gather=True):
+        """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: one
+        launch per iteration and an all-gather of that iteration's records on a side stream, overlapping the
+        next iteration's compute (there is no dependency between them)."""
+        import torch
+        if self.world == 1 or not gather:
+            per = n_iterations if iterations_per_launch is None else iterations_per_launch
+            done = 0
+            while done < n_iterations:
+                k = min(per, n_iterations - done)
+                self.optimise(k)
+                done += k
+            return None
+        width = 4 + self.problem.npad
+        if self._gatherer is None:
+            self._gatherer = RecordGatherer(self.n_points, self.reps, width, self.problem.device)
+            self._comm_stream = torch.cuda.Stream(device=self.problem.device)
+            self.gathered = torch.zeros((self.max_rows, self.n_points * self.reps, width), dtype=torch.float64,
+                                        device=self.problem.device)
+        compute = torch.cuda.current_stream()
+        for _ in range(n_iterations):
+            k = self.iterations_done
+            self.optimise(1)
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(ev)
+                self.gathered[k].copy_(self._gatherer.gather(self.pack_row(k)))
+        compute.wait_stream(self._comm_stream)
+        return self.gathered
+
+    def pack_row(self, k):
+        """[B_local, 4 + npad] FP64: best_loglkl, last_loglkl, accepted, step_size, best_x."""
+        import torch
+        r = self.records
+        cols = torch.stack([r.best_loglkl[k], r.last_loglkl[k], r.accepted[k].to(torch.float64), r.step_size[k]], 1)
+        bx = r.best_x[k] if r.best_x is not None else torch.zeros(
+            (self.n_chains, self.problem.npad), dtype=torch.float64, device=cols.device)
+        return torch.cat([cols, bx], dim=1)
+
+    def reduce_over_iterations(self):
+        """Running-bestfit reduction on the device (analyse_profile_task.py:91-121) for this rank's chains when
+        it owns whole points (world == 1 or point sharding)."""
+        from . import engine
+        lp = len(self.local_points)
+        reps_local = self.n_chains // lp
+        return engine.profile_reduce(self.records, self.iterations_done, lp, reps_local)
+
+    def finalize(self):
+        pass

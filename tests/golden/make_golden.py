@@ -352,6 +352,38 @@ def main():
     with open(os.path.join(HERE, 'ref_debug_reanneal_initial_loglkl.json'), 'w') as f:
         json.dump({'source': 'test/debug_reanneal/profile/x2.txt (columns x2, initial_loglkl)', 'rows': rows}, f)
 
+    # ---- input schema: what Configuration makes of the shipped example yamls (C10/C11 defaults) ----
+    cfgs = {}
+    for name, path in (('example_toy', 'input/example_toy/example_toy.yaml'),
+                       ('example_global', 'input/example_toy/example_global_optimisation_toy.yaml')):
+        with open(os.path.join(REF, path)) as f:
+            y = yaml.full_load(f)
+        y['io']['dir'] = os.path.join(work, 'cfg_' + name)
+        with quiet():
+            c = Configuration(y)
+        cfgs[name] = {sec: {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in d_.items()}
+                      for sec, d_ in c.config_dict.items()}
+        cfgs[name]['io']['dir'] = '<dir>'
+    y = base_yaml('mcmc', os.path.join(work, 'cfg_mcmc'), 'input/example_toy/kernel_settings/kernel_random_gauss.yaml')
+    y['mcmc'] = {'algorithm': 'MetropolisHastings', 'N_chains': 4, 'steps_per_iteration': 2000,
+                 'convergence_Rm1': 0.01, 'unpack_at_dump': True}
+    with quiet():
+        c = Configuration(y)
+    cfgs['mcmc'] = {sec: dict(d_) for sec, d_ in c.config_dict.items()}
+    cfgs['mcmc']['io']['dir'] = '<dir>'
+    with open(os.path.join(HERE, 'config_defaults.json'), 'w') as f:
+        json.dump(cfgs, f, indent=1)
+
+    # ---- cold K1 run of the real reference: the "reference CPU run on identical inputs" for the GPU ----
+    kernel, chains = out[20]
+    cfg = profile_yaml(work, 'cold20', kpkl, root, temperature_range=[0.1, 1.0e-6], max_iterations=30)
+    config, sched = run_scheduler(cfg, max_iter=30)
+    rec = collect_tasks(config, sched)
+    keep = {'files': run_analysis(config, sched, 'profile', ['x2.txt']),
+            'final': [o for o in rec['optimise'] if o['iteration_number'] == 29]}
+    with open(os.path.join(HERE, 'toy20_cold_reference_run.json'), 'w') as f:
+        json.dump(keep, f)
+
     print(json.dumps(summary))
     shutil.rmtree(work, ignore_errors=True)
 

@@ -129,14 +129,15 @@ def test_chi2_tolerance_stop_matches_reference_port():
         assert (ch.status == 1) == expect
 
 
-@pytest.mark.parametrize('d', [20, 30])
-def test_cold_annealing_reaches_closed_form(d):
-    """Cold schedule (T 0.1 -> 1e-10 in 60 iterations): Delta chi^2 <= 1e-3, parameters <= 1e-4 relative."""
+@pytest.mark.parametrize('d,iters,steps', [(20, 80, 250), (30, 400, 500)])
+def test_cold_annealing_reaches_closed_form(d, iters, steps):
+    """Cold schedule (T 0.1 -> 1e-12): Delta chi^2 <= 1e-3, parameters <= 1e-4 relative (|x| floored at 1e-2).
+    The 30-D toy needs far more steps: its bin covariances come from 61 bootstrap rows, so the whitened
+    curvature spectrum spans 1.4e-2 .. 32 and the sloppy directions equilibrate slowly (same for the reference)."""
     pts = [0, len(golden(f'toy{d}_init.npz')['values']) // 2]
     hp, starts, init_ll, values, k = toy_profile_problem(d, points=pts)
     m = dm.Model(hp)
-    iters = 60
-    sched = dm.DmSchedule(250, 1, (1e-10 / 0.1) ** (1 / iters), 1.0, 0.19, 0.21, 0.3, 0.0)
+    sched = dm.DmSchedule(steps, 1, (1e-12 / 0.1) ** (1 / iters), 1.0, 0.19, 0.21, 0.3, 0.0)
     for p in range(len(pts)):
         ch = m.new_chain(starts[p], p, chain_id=p, temperature=0.1, step_size=0.1, current_best=init_ll[p])
         out = m.anneal_chain(ch, sched, iters, seed=2024)

@@ -1,0 +1,230 @@
+"""End-to-end GPU tests through the reference-facing host API (yaml -> run() -> PROSPECT output files).
+
+Tolerances are the north-star's: profiled chi^2 within Delta chi^2 <= 1e-3 of the analytic profile and of the
+reference CPU run on identical inputs (frozen in tests/golden/toy20_cold_reference_run.json); bestfit
+parameters within 1e-4 relative on the cold schedule; MH marginals by KS at p > 1e-3 / d (Bonferroni).
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+torch = pytest.importorskip('torch')
+pytestmark = pytest.mark.gpu
+
+from oracle import closed_form  # noqa: E402
+from prospect_public_b200 import capi  # noqa: E402
+from prospect_public_b200.config import Configuration  # noqa: E402
+from prospect_public_b200.io import load_profile  # noqa: E402
+from prospect_public_b200.run import analyse, run  # noqa: E402
+from prospect_public_b200.toy import annealing_yaml, mcmc_yaml, write_toy_inputs  # noqa: E402
+from tests.helpers import GOLDEN, golden, spd_target  # noqa: E402
+
+
+def _inputs(tmp_path, d):
+    k, m = golden(f'toy{d}_kernel.npz'), golden(f'toy{d}_mcmc.npz')
+    paths = write_toy_inputs(str(tmp_path / f'inp{d}'), k['means'], k['covmat'], [m[f'chain_{i}'] for i in range(4)])
+    return paths, k
+
+
+def test_example_toy_profile_writes_prospect_layout(tmp_path):
+    """K1: input/example_toy/example_toy.yaml as shipped (10 values x 1 rep x 20 it x 250 steps)."""
+    paths, k = _inputs(tmp_path, 20)
+    out_dir = str(tmp_path / 'out')
+    res = run(annealing_yaml(paths, out_dir))
+    for fn in ('log.yaml', 'config.pkl', 'state.pkl', 'status.txt', 'analytical/random_gauss.pkl', 'profile/x2.txt',
+               'profile/x2_status.txt', 'profile/x2_intervals.txt'):
+        assert os.path.isfile(os.path.join(out_dir, fn)), fn
+    assert res['chain_steps'] == 10 * 20 * 250
+    prof = load_profile(out_dir)                      # the reference's reader contract
+    assert np.allclose(prof['x2'], np.linspace(-1.0, 2.0, 10), atol=1e-10)
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, np.linspace(-1.0, 2.0, 10))
+    excess = prof['-loglkl'] - cf
+    # T_final = 1.26e-3: the reference itself ends 5e-3 .. 1.3e-2 above the minimum
+    assert np.all(excess > -1e-9) and np.all(excess < 5e-2)
+    ini = golden('toy20_init.npz')
+    assert np.allclose(prof['initial_loglkl'], ini['initial_loglkl'], rtol=1e-10)
+    # reported chi^2 is exact for the reported position
+    from oracle import reference_port as rp
+    t = rp.GaussianTarget(k['means'], k['covmat'])
+    names = [f'x{i}' for i in range(1, 21) if i != 2]
+    for row in (0, 5, 9):
+        x = np.array([prof[nm][row] for nm in names])
+        assert abs(t.fix(1, prof['x2'][row]).loglkl(x) - prof['-loglkl'][row]) < 1e-7
+    before = open(os.path.join(out_dir, 'profile/x2.txt')).read()
+    analyse(out_dir)                                   # prospect-analyse on the snapshot
+    assert open(os.path.join(out_dir, 'profile/x2.txt')).read() == before
+
+
+def test_initialisation_matches_reference_fixture(tmp_path):
+    """A14 through the product path: bin indices bit-exact, GPU bin covariance to 1e-9, start points exact."""
+    from prospect_public_b200.initialise import initialise_optimiser
+    from prospect_public_b200.kernels import initialise_kernel
+    for d, nvals in ((20, 10), (30, 32)):
+        paths, k = _inputs(tmp_path, d)
+        cfg = Configuration(annealing_yaml(paths, str(tmp_path / f'o{d}'), write=False,
+                                           values=f'np.linspace(-1.0, 2.0, {nvals})'))
+        kernel = initialise_kernel(cfg.kernel, None, 0)
+        sp, values = initialise_optimiser(cfg, kernel)
+        ini = golden(f'toy{d}_init.npz')
+        assert np.array_equal(values, ini['values'])
+        for p in range(nvals):
+            assert np.array_equal(sp.indices[p], ini['indices'][p])
+        assert np.array_equal(sp.positions, ini['position'][:, :-1])
+        assert np.allclose(sp.covmats, ini['covmat'], rtol=1e-9, atol=1e-14)
+        assert np.allclose(sp.initial_loglkl, ini['initial_loglkl'], rtol=1e-12)
+        assert kernel.varying_param_names == [f'x{i}' for i in range(1, d + 1) if i != 2]
+
+
+def test_kernel_plugin_interface(tmp_path):
+    """B1: CudaGaussianKernel.loglkl mutates prop, returns -log L; prior box; fixed-parameter bookkeeping."""
+    from oracle import reference_port as rp
+    from prospect_public_b200.kernels import initialise_kernel
+    paths, k = _inputs(tmp_path, 20)
+    cfg = Configuration(annealing_yaml(paths, str(tmp_path / 'o'), write=False))
+    kernel = initialise_kernel(cfg.kernel, None, 0)
+    t = rp.GaussianTarget(k['means'], k['covmat'])
+    rng = np.random.default_rng(0)
+    x = rng.uniform(-1, 1, 20)
+    pos = {f'x{i + 1}': [x[i]] for i in range(20)}
+    assert abs(kernel.loglkl(pos) - t.loglkl(x)) < 1e-12 * t.loglkl(x)
+    kernel.set_fixed_parameters({'x2': 0.75})
+    pos = {f'x{i + 1}': [x[i]] for i in range(20) if i != 1}
+    val = kernel.loglkl(pos)
+    assert pos['x2'] == [0.75]                                      # fixed parameter injected into prop
+    assert abs(val - t.fix(1, 0.75).loglkl(np.delete(x, 1))) < 1e-12 * val
+    assert kernel.logprior(pos) == 0.0
+    pos['x5'] = [2.6]
+    assert kernel.logprior(pos) == np.inf and kernel.logpost(pos) == np.inf
+    assert np.array_equal(kernel.get_default_covmat(), 0.005 * np.diag(np.full(19, 5.0)))
+    assert abs(kernel.get_analytic_profile('x2', -1.0) - 20.719044687) < 1e-8
+
+
+def test_cold_profile_matches_reference_run_and_analytic(tmp_path):
+    """The real reference's cold K1 run (T 0.1 -> 1e-6, 30 iterations, frozen) vs the GPU on identical inputs:
+    Delta chi^2 <= 1e-3 per point against the reference and against the analytic profile."""
+    with open(os.path.join(GOLDEN, 'toy20_cold_reference_run.json')) as f:
+        gold = json.load(f)
+    ref_rows = [[float(t) for t in ln.split('\t')[:3]] for ln in gold['files']['x2.txt'].strip().split('\n')[1:]]
+    ref_ll = np.array([r[2] for r in ref_rows])
+    paths, k = _inputs(tmp_path, 20)
+    res = run(annealing_yaml(paths, str(tmp_path / 'out'), temperature_range=[0.1, 1.0e-6], max_iterations=30,
+                             repetitions=4))
+    prof = res['profile']
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, np.linspace(-1.0, 2.0, 10))
+    assert np.max(2 * np.abs(prof['loglkls'] - ref_ll)) <= 1e-3
+    assert np.max(2 * np.abs(prof['loglkls'] - cf)) <= 1e-3
+    assert np.all(prof['loglkls'] - cf > -1e-9)
+    # Delta chi^2 column: same parabola construction as the reference
+    ref_dchi = np.array([r[1] for r in ref_rows])
+    assert np.max(np.abs(prof['Delta_chi2'] - ref_dchi)) <= 1e-3
+
+
+def test_30d_profile_32x256_cold_schedule_reaches_analytic(tmp_path):
+    """K3 at full size (32 values x 256 repetitions = 8192 chains) on a cold schedule:
+    Delta chi^2 <= 1e-3 and bestfit parameters <= 1e-4 relative (floor 1e-2 on |x|) for every point."""
+    paths, k = _inputs(tmp_path, 30)
+    vals = np.linspace(-1.0, 2.0, 32)
+    res = run(annealing_yaml(paths, str(tmp_path / 'out'), values='np.linspace(-1.0, 2.0, 32)', repetitions=256,
+                             temperature_range=[0.1, 1.0e-12], max_iterations=400, steps_per_iteration=500))
+    rec, srt, prof = res['record'], res['bestfits'], res['profile']
+    assert res['chain_steps'] == 32 * 256 * 400 * 500
+    p_idx = np.arange(32)
+    best = srt['chain_best'][srt['best_rep'], p_idx]
+    it = srt['chain_iter'][srt['best_rep'], p_idx]
+    pos = rec.best_x[it, srt['best_rep'] * 32 + p_idx]
+    for p, v in enumerate(vals):
+        cf, xcf = closed_form.profile_minimum(k['means'], k['covmat'], 1, v)
+        assert 0 <= 2 * (best[p] - cf) + 1e-9 and 2 * (best[p] - cf) <= 1e-3, (p, best[p] - cf)
+        rel = np.max(np.abs(pos[p] - xcf) / np.maximum(np.abs(xcf), 1e-2))
+        assert rel <= 1e-4, (p, rel)
+    lp = load_profile(str(tmp_path / 'out'))
+    assert len(lp['x2']) == 32
+    # chains of one point are independent (distinct Philox streams): repetitions do not coincide
+    assert len(np.unique(srt['chain_best'][:, 0])) > 250
+
+
+def test_global_optimisation_4096_chains(tmp_path):
+    """K2: example_global_optimisation_toy.yaml with repetitions = 4096 (20-D as shipped)."""
+    paths, k = _inputs(tmp_path, 20)
+    out_dir = str(tmp_path / 'out')
+    res = run(annealing_yaml(paths, out_dir, jobtype='global_optimisation', repetitions=4096,
+                             temperature_range=[0.1, 1.0e-6], max_iterations=30))
+    cb = res['bestfits']['chain_best'][:, 0]
+    assert res['chain_steps'] == 4096 * 30 * 250
+    assert cb.min() >= -1e-12 and 2 * cb.min() <= 1e-3            # global minimum of the Gaussian is 0 at mu
+    assert 2 * np.median(cb) <= 1e-3
+    lines = open(os.path.join(out_dir, 'global_optimisation', 'results.txt')).read().strip().split('\n')
+    assert len(lines) == 4097 and lines[0].startswith('Repetition number \t -loglkl \t initial_loglkl')
+    best_rep = res['bestfits']['best_rep']
+    x = np.array([float(t) for t in lines[1 + best_rep].split('\t')[3:]])
+    assert np.max(np.abs(x - k['means'])) < 5e-3
+
+
+def test_mcmc_job_65536_chains_ks(tmp_path):
+    """K5: 65 536 parallel MH chains on the 30-D toy at T = 1.  After burn-in the final states of the chains are
+    65 536 independent draws: KS per coordinate against N(mu_i, (S^-1)_ii), and the pooled covariance from the
+    GPU moment reduction against S^-1."""
+    from scipy import stats
+    from prospect_public_b200 import engine
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.mcmc import initialise_mcmc
+    paths, k = _inputs(tmp_path, 30)
+    d = 30
+    target_cov = closed_form.stationary_covariance(k['covmat'])
+    cfg = Configuration(mcmc_yaml(paths, str(tmp_path / 'o'), n_chains=65536, steps=2000, write=False,
+                                  start_from_covmat=target_cov.tolist(), step_size=2.4 / np.sqrt(d)))
+    kernel = initialise_kernel(cfg.kernel, None, 0)
+    sampler = initialise_mcmc(cfg.mcmc, kernel, seed=77, record='thinned', thin=2000)
+    sampler.run_steps(2000)            # burn-in from the reference's default start (zeros)
+    sampler.run_steps(2000)
+    x, ll, mult, cnt = sampler.samples_numpy()
+    assert np.all(cnt == 2)
+    final = x[:, 1, :]
+    ar = sampler.accepted.sum() / (65536 * 4000)
+    assert 0.15 < ar < 0.40
+    sig = np.sqrt(np.diag(target_cov))
+    for i in range(d):
+        p = stats.kstest((final[:, i] - k['means'][i]) / sig[i], 'norm').pvalue
+        assert p > 1e-3 / d, (i, p)
+    sw, swx, swxx = engine.weighted_moments(sampler._samples.x[:, 1, :].contiguous(), d)
+    cov = engine.covariance_from_moments(sw, swx, swxx).cpu().numpy()
+    assert np.max(np.abs(cov - target_cov) / np.sqrt(np.outer(np.diag(target_cov), np.diag(target_cov)))) < 0.02
+    assert np.max(np.abs((swx / sw).cpu().numpy() - k['means']) / sig) < 0.02
+
+
+def test_mcmc_job_writes_chain_files_like_reference(tmp_path):
+    """jobtype mcmc with the reference's defaults (4 chains, start 0, covmat 0.005*diag(widths)): chain files in
+    the MontePython layout that the profile initialiser can read back."""
+    from prospect_public_b200.initialise import load_mcmc
+    paths, k = _inputs(tmp_path, 20)
+    out_dir = str(tmp_path / 'mc')
+    res = run(mcmc_yaml(paths, out_dir, n_chains=4, steps=2000, rm1=1e9))
+    assert res['rounds'] == 1
+    chain = load_mcmc(os.path.join(out_dir, 'mcmc', 'test'))
+    assert np.sum(chain.mults) == 4 * 2001                      # every chain: sum(mults) = steps + 1
+    assert os.path.isfile(os.path.join(out_dir, 'mcmc', 'test.paramnames'))
+    ref = golden('toy20_mcmc.npz')
+    n_ref = sum(len(ref[f'chain_{i}']) for i in range(4)) / 4.0  # reference: 4 rounds
+    assert 0.5 < len(chain.mults) / n_ref * 4 < 2.0              # similar acceptance as the reference's chains
+
+
+def test_wide_kernel_profile_d256(tmp_path):
+    """K4-style 256-D synthetic SPD target through the CPL=8 path: 4 values x 8 reps, closed-form proposal covmat."""
+    from tests.helpers import conditional_covariance
+    d = 256
+    mu, cov = spd_target(d, seed=4)
+    paths = write_toy_inputs(str(tmp_path / 'inp'), mu, cov, None)
+    sig = np.sqrt(cov[1, 1])
+    vals = (mu[1] + sig * np.array([-2.0, -0.5, 0.5, 2.0])).tolist()
+    start = np.delete(mu, 1) + 0.01
+    y = annealing_yaml(paths, str(tmp_path / 'out'), values=vals, repetitions=8, start_from_mcmc=None,
+                       start_from_position=start.tolist(), start_from_covmat=conditional_covariance(cov, 1).tolist(),
+                       temperature_range=[0.1, 1.0e-8], max_iterations=120, steps_per_iteration=400,
+                       step_size_adaptive_initial=0.15)
+    res = run(y)
+    best = res['bestfits']['chain_best'][res['bestfits']['best_rep'], np.arange(4)]
+    for p, v in enumerate(vals):
+        cf, _ = closed_form.profile_minimum(mu, cov, 1, v)
+        assert 2 * abs(best[p] - cf) <= 1e-3, (p, best[p], cf)

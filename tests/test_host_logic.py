@@ -1,0 +1,247 @@
+"""CPU tests of the host-side mirror of the reference interfaces: yaml schema, analysis writers,
+bin/index bookkeeping, chain container, sharding + gather (gloo, world size 2)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from prospect_public_b200 import analysis
+from prospect_public_b200.config import ConfigError, Configuration
+from prospect_public_b200.distributed import global_chain_index, shard_grid
+from prospect_public_b200.initialise import get_fraction_of_points_in_bin, load_mcmc
+from prospect_public_b200.mcmc import Chain, collapse_chains
+from prospect_public_b200.toy import annealing_yaml, mcmc_yaml, write_toy_inputs
+from tests.helpers import GOLDEN, golden
+
+
+@pytest.fixture()
+def toy20(tmp_path):
+    k, m = golden('toy20_kernel.npz'), golden('toy20_mcmc.npz')
+    return write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], [m[f'chain_{i}'] for i in range(4)])
+
+
+def _plain(section):
+    return {k: (v.tolist() if isinstance(v, np.ndarray) else v) for k, v in section.items()}
+
+
+def test_schema_defaults_match_reference(toy20, tmp_path):
+    """Configuration resolves the shipped example yamls to the same dicts as prospect.input.Configuration."""
+    with open(os.path.join(GOLDEN, 'config_defaults.json')) as f:
+        gold = json.load(f)
+    shipped_profile = {'parameter': 'x2', 'values': 'np.linspace(-1.0, 2.0, 10)', 'plot_profile': True,
+                       'detailed_plot': False, 'plot_Delta_chi2': False, 'plot_schedule': True,
+                       'confidence_levels': [0.68, 0.95]}
+    y = annealing_yaml(toy20, str(tmp_path / 'o'), **shipped_profile)
+    c = Configuration(y)
+    g = gold['example_toy']
+    for key, val in g['profile'].items():
+        if key == 'start_from_mcmc':
+            continue
+        assert _plain(c.config_dict['profile'])[key] == val, key
+    assert set(c.config_dict['profile']) == set(g['profile'])
+    for sec in ('io', 'run', 'kernel'):
+        assert set(c.config_dict[sec]) == set(g[sec]), sec
+    assert c.config_dict['kernel']['ignore_prior'] is False and c.config_dict['io']['snapshot_interval'] == 10.0
+    # global optimisation: parameter None, values []
+    y = annealing_yaml(toy20, str(tmp_path / 'o2'), jobtype='global_optimisation', repetitions=3, plot_schedule=True)
+    del y['profile']['plot_profile'], y['profile']['start_bin_fraction']      # not in the shipped yaml -> defaults
+    c = Configuration(y)
+    for key, val in gold['example_global']['profile'].items():
+        if key != 'start_from_mcmc':
+            assert _plain(c.config_dict['profile'])[key] == val, key
+    c = Configuration(mcmc_yaml(toy20, str(tmp_path / 'o3')))
+    for key, val in gold['mcmc']['mcmc'].items():
+        assert c.config_dict['mcmc'][key] == val, key
+    assert c.mcmc.temperature == 1.0 and c.mcmc.step_size == 1.0
+
+
+def test_schema_rejections(toy20, tmp_path):
+    y = annealing_yaml(toy20, str(tmp_path / 'o'))
+    del y['profile']['max_iterations']
+    with pytest.raises(ConfigError):
+        Configuration(y)                                     # mandatory key
+    y = annealing_yaml(toy20, str(tmp_path / 'o'), bogus=1)
+    with pytest.raises(ConfigError):
+        Configuration(y)                                     # unknown key
+    y = annealing_yaml(toy20, str(tmp_path / 'o'), repetitions='3')
+    with pytest.raises(ConfigError):
+        Configuration(y)                                     # wrong type
+    y = annealing_yaml(toy20, str(tmp_path / 'o'), step_size_schedule='exponential')
+    with pytest.raises(ConfigError):
+        Configuration(y)                                     # exponential needs step_size_range
+    y = annealing_yaml(toy20, str(tmp_path / 'o'), values='__import__("os").getcwd()')
+    with pytest.raises(ConfigError):
+        Configuration(y)                                     # only numpy in evaluated strings
+    y = annealing_yaml(toy20, str(tmp_path / 'o'))
+    y['run']['jobtype'] = 'nope'
+    with pytest.raises(ConfigError):
+        Configuration(y)
+    y = annealing_yaml(toy20, str(tmp_path / 'o'))
+    y['kernel']['param'] = 'does/not/exist.yaml'
+    with pytest.raises(ConfigError):
+        Configuration(y)
+
+
+def test_output_dir_is_not_clobbered(toy20, tmp_path):
+    out = tmp_path / 'run'
+    out.mkdir()
+    y = annealing_yaml(toy20, str(out))
+    y['io']['overwrite_dir'] = False
+    assert Configuration(y).io.dir == str(out) + '_0'
+    (tmp_path / 'run_0').mkdir()
+    assert Configuration(y).io.dir == str(out) + '_1'
+
+
+def test_adaptive_initial_sets_step_size_range(toy20, tmp_path):
+    c = Configuration(annealing_yaml(toy20, str(tmp_path / 'o')))
+    assert c.profile.step_size_range == [0.1, None]
+    assert isinstance(c.profile.values, np.ndarray) and len(c.profile.values) == 10
+    assert c.profile.values[3] == np.linspace(-1.0, 2.0, 10)[3]        # exact float64 keys
+
+
+def _record_from_golden(gold, n_var, reps, values):
+    opt = gold['optimise']
+    iters = 1 + max(o['iteration_number'] for o in opt)
+    p_count = max(1, len(values))
+    b = p_count * reps
+    best = np.full((iters, b), np.inf)
+    acc = np.full((iters, b), -1, dtype=np.int32)
+    bx = np.zeros((iters, b, n_var))
+    for o in opt:
+        p = 0 if not len(values) else int(np.nonzero(values == o['fixed_param_val'])[0][0])
+        c = o['repetition_number'] * p_count + p
+        k = o['iteration_number']
+        best[k, c] = o['bestfit_loglkl']
+        acc[k, c] = o['accepted_steps'] - 1
+        bx[k, c] = o['bestfit_position'][:n_var]
+    ini = sorted(gold['initialise'], key=lambda t: t['id'])[:p_count]
+    names = opt[0]['position_names'][:n_var]
+    return analysis.RunRecord(values, reps, names, best, acc, bx, np.zeros(b, dtype=bool),
+                              np.array([t['initial_loglkl'] for t in ini]),
+                              np.array([t['initial_position'][:n_var] for t in ini]),
+                              np.array([t['initial_covmat'] for t in ini]))
+
+
+@pytest.mark.parametrize('d,nvals', [(20, 10), (30, 4)])
+def test_profile_files_identical_to_reference(tmp_path, d, nvals):
+    """A20: fed with the reference's own task results, the writers reproduce profile/x2.txt,
+    x2_status.txt and x2_intervals.txt byte for byte."""
+    with open(os.path.join(GOLDEN, f'toy{d}_profile_run.json')) as f:
+        gold = json.load(f)
+    rec = _record_from_golden(gold, d - 1, 1, np.linspace(-1.0, 2.0, nvals))
+    analysis.analyse_profile(rec, str(tmp_path), 'x2', [0.68, 0.95])
+    for fn in ('x2.txt', 'x2_status.txt', 'x2_intervals.txt'):
+        assert (tmp_path / fn).read_text() == gold['files'][fn], fn
+
+
+def test_global_results_file_identical_to_reference(tmp_path):
+    with open(os.path.join(GOLDEN, 'toy20_global_run.json')) as f:
+        gold = json.load(f)
+    rec = _record_from_golden(gold, 20, 3, np.zeros(0))
+    analysis.analyse_global_optimisation(rec, str(tmp_path))
+    assert (tmp_path / 'results.txt').read_text() == gold['files']['results.txt']
+
+
+def test_load_profile_round_trip(tmp_path):
+    from prospect_public_b200.io import load_profile
+    with open(os.path.join(GOLDEN, 'toy20_profile_run.json')) as f:
+        gold = json.load(f)
+    p = tmp_path / 'x2.txt'
+    p.write_text(gold['files']['x2.txt'])
+    prof = load_profile(str(p), direct_txt=True)
+    assert list(prof)[:5] == ['x2', 'Delta_chi2', '-loglkl', 'avg_best_loglkl', 'initial_loglkl']
+    assert len(prof['x2']) == 10 and prof['x2'][0] == -1.0 and len(prof) == 5 + 19
+
+
+def test_parabola_vertex():
+    x, f = analysis.bestfit_parabola([0.0, 1.0, 3.0], [2.0 + 1.5 * (t - 1.2) ** 2 for t in (0.0, 1.0, 3.0)])
+    assert abs(x - 1.2) < 1e-14 and abs(f - 2.0) < 1e-14
+
+
+def test_unfinished_points_and_ties():
+    """No finished optimisation -> initial_loglkl enters the profile and the row says so; ties -> first rep."""
+    vals = np.array([0.0, 1.0, 2.0])
+    best = np.array([[3.0, np.inf, 5.0, 3.0, np.inf, 4.0]])       # reps=2, P=3
+    acc = np.array([[4, -1, 2, 4, -1, 2]], dtype=np.int32)
+    rec = analysis.RunRecord(vals, 2, ['a'], best, acc, np.zeros((1, 6, 1)), np.zeros(6, dtype=bool),
+                             np.array([9.0, 2.5, 9.0]), np.zeros((3, 1)), np.zeros((3, 1, 1)))
+    srt = analysis.sort_bestfits(rec)
+    assert list(srt['best_rep']) == [0, 0, 1]
+    assert srt['avg_loglkl'][1] == np.inf and srt['avg_loglkl'][2] == 4.5
+    prof = analysis.compute_profile(rec, srt)
+    assert prof['loglkls'][1] == 2.5
+
+
+def test_bin_selection_bit_exact(toy20):
+    """A14: the rows picked for every profile value equal the reference's (golden indices)."""
+    chain = load_mcmc(toy20['mcmc_root'])
+    ini = golden('toy20_init.npz')
+    assert len(chain.mults) == 2477
+    for i, v in enumerate(ini['values']):
+        idx = get_fraction_of_points_in_bin(chain, v, 'x2', 0.1)
+        assert len(idx) == ini['N_points'][i] == 248
+        assert np.array_equal(idx, ini['indices'][i])
+        best = idx[int(np.argmin(np.take(chain.loglkls, idx)))]
+        assert np.array_equal(np.delete(np.array([chain.positions[f'x{j}'][best] for j in range(1, 21)]), 1),
+                              ini['position'][i][:-1])
+
+
+def test_chain_container_semantics():
+    ch = Chain([1], [5.0], {'a': [0.1], 'b': [0.2]})
+    ch.push_position(4.0, {'a': [0.3], 'b': [0.4]})
+    ch.mults[-1] += 2
+    assert ch.N == 2 and ch.last_position == {'a': [0.3], 'b': [0.4]}
+    assert np.array_equal(ch.data, np.array([[1, 5.0, 0.1, 0.2], [3, 4.0, 0.3, 0.4]]))
+    sub = ch.from_indices([1])
+    assert sub.mults == [3] and sub[0] == {'a': [0.3], 'b': [0.4]}
+    tot = collapse_chains([ch, sub])
+    assert tot.N == 3 and tot.mults == [1, 3, 3]
+
+
+def test_shard_grid_covers_every_chain_once():
+    for p, r, w in ((32, 256, 8), (10, 3, 4), (1, 4096, 8), (3, 5, 2), (7, 2, 8)):
+        seen = []
+        for rank in range(w):
+            pt, rep = shard_grid(p, r, rank, w)
+            seen.append(global_chain_index(pt, rep, p))
+            if p >= w:
+                assert len(np.unique(pt)) * r == len(pt)      # whole points stay on one rank
+        allc = np.concatenate(seen)
+        assert len(allc) == p * r and np.array_equal(np.sort(allc), np.arange(p * r))
+
+
+def _gloo_worker(rank, world, port, p, r, q):
+    import torch
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from prospect_public_b200.distributed import RecordGatherer
+    pt, rep = shard_grid(p, r, rank, world)
+    gid = global_chain_index(pt, rep, p)
+    g = RecordGatherer(p, r, 3, 'cpu')
+    local = torch.stack([torch.as_tensor(gid, dtype=torch.float64), torch.as_tensor(gid * 2.0),
+                         torch.full((len(gid),), float(rank), dtype=torch.float64)], dim=1)
+    out = g.gather(local)
+    q.put((rank, out.numpy()))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('p,r', [(5, 3), (1, 7)])
+def test_record_all_gather_world2_gloo(p, r):
+    """N > 1 path on CPU: two gloo ranks shard the grid and all-gather their records into global order."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29600 + (os.getpid() % 300) + p
+    procs = [ctx.Process(target=_gloo_worker, args=(rank, 2, port, p, r, q)) for rank in range(2)]
+    for pr in procs:
+        pr.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+    for rank in range(2):
+        assert np.array_equal(outs[rank][:, 0], np.arange(p * r))
+        assert np.array_equal(outs[rank][:, 1], 2.0 * np.arange(p * r))
+    owners = outs[0][:, 2]
+    assert set(owners) == {0.0, 1.0}
