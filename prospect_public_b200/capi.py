@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, '_lib', 'libpb200.so')
+LIB_PATH = os.environ.get('PB200_LIB') or os.path.join(_PKG, '_lib', 'libpb200.so')   # PB200_LIB: A/B builds
 
 ACTIVE, CONVERGED, FAILED = 0, 1, 2
 STEP_EXPONENTIAL, STEP_ADAPTIVE_FIXED, STEP_ADAPTIVE_SECANT = 0, 1, 2

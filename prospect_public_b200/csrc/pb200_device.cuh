@@ -48,7 +48,8 @@ __device__ __forceinline__ float u01(uint32_t w) {
 // Box-Muller on the MUFU pipe: r = sqrt(-2 ln u1), theta = 2 pi u2 - pi.
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
     const float u1 = u01(w0), u2 = u01(w1);
-    const float r = sqrtf(-1.3862943611198906f * __log2f(u1));       // -2 ln2 * log2(u1)
+    float r;                                                          // sqrt(-2 ln2 * log2(u1)), one MUFU.SQRT
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
     float s, c;
     __sincosf(__fmaf_rn(u2, 6.283185307179586f, -3.141592653589793f), &s, &c);
     z0 = r * c;

@@ -7,11 +7,19 @@
 //   mh_kernel<CPL, REC>       plain Metropolis-Hastings rounds with chain recording (jobtype mcmc).
 //   loglkl_kernel<CPL>        FP64 chi^2 quadratic form + prior box for a batch of positions.
 //   schedule_kernel           stand-alone adaptive step-size bookkeeping.
-//   profile_reduce_kernel     min over iterations / first-min repetition / mean (warp shuffles).
+//   chain_min_kernel + point_reduce_kernel   min over iterations / first-min repetition / mean (warp shuffles).
 //   moments_kernel            weighted first/second moments (covariance reduction), FP64.
 //   rng_kernel                test hook exposing the variates.
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
+
+#ifndef PB200_LT_REGS
+#define PB200_LT_REGS 0      // 1: keep this lane's column of the proposal factor in registers (n <= 32).
+                             // 0 (measured faster on B200): read it through L1 on accept, 72 registers, 28 warps/SM
+#endif
+#ifndef PB200_MIN_CTAS
+#define PB200_MIN_CTAS 7
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -61,6 +69,94 @@ __device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL]
 // The reference draws the uniform even for out-of-box proposals and never evaluates the likelihood
 // there; "inside AND likelihood-accept" is the same predicate evaluated in the cheaper order.
 // ----------------------------------------------------------------------------------------------
+// One MH step given this lane's normals zk[] and the accept variate ek.
+template <int CPL, bool LT_REGS, int REC>
+__device__ __forceinline__ void one_step(const float* __restrict__ lt_pt, int lane, uint32_t tk, float Tf, float sf,
+                                         const float (&zk)[CPL], float ek, const float (&ltrow)[LT_REGS ? 32 : 1],
+                                         const float (&hl)[CPL], float (&gf)[CPL], const double (&lo)[CPL],
+                                         const double (&hi)[CPL], double (&x)[CPL], double (&gt)[CPL], double& ll,
+                                         double& best_ll, double (&bx)[CPL], int32_t& nacc, float* zs, RecCursor& rc) {
+    constexpr int NPAD = 32 * CPL;
+    float tt = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) tt = __fmaf_rn(zk[r], __fmaf_rn(hl[r], zk[r], gf[r]), tt);
+    tt = warp_sum(tt);
+    const float delta = __fmul_rn(sf, tt);
+    bool accepted = false;
+    if (delta < __fmul_rn(Tf, ek)) {
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) zs[lane + 32 * r] = zk[r];
+        __syncwarp();
+        double xn[CPL];
+        bool outside = false;
+        const float4* __restrict__ z4 = reinterpret_cast<const float4*>(zs);
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            if (LT_REGS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float4 v = z4[j];
+                    a0 = __fmaf_rn(ltrow[4 * j + 0], v.x, a0);
+                    a1 = __fmaf_rn(ltrow[4 * j + 1], v.y, a1);
+                    a2 = __fmaf_rn(ltrow[4 * j + 2], v.z, a2);
+                    a3 = __fmaf_rn(ltrow[4 * j + 3], v.w, a3);
+                }
+            } else {
+                const float* __restrict__ col = lt_pt + lane + 32 * r;
+#pragma unroll 8
+                for (int j = 0; j < NPAD / 4; ++j) {
+                    const float4 v = z4[j];
+                    a0 = __fmaf_rn(__ldg(col + (4 * j + 0) * NPAD), v.x, a0);
+                    a1 = __fmaf_rn(__ldg(col + (4 * j + 1) * NPAD), v.y, a1);
+                    a2 = __fmaf_rn(__ldg(col + (4 * j + 2) * NPAD), v.z, a2);
+                    a3 = __fmaf_rn(__ldg(col + (4 * j + 3) * NPAD), v.w, a3);
+                }
+            }
+            const float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+            xn[r] = __dadd_rn(x[r], (double)__fmul_rn(sf, acc));
+            outside = outside || (xn[r] < lo[r]) || (xn[r] > hi[r]);
+        }
+        __syncwarp();
+        if (!__any_sync(kFull, outside)) {
+            accepted = true;
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                x[r] = xn[r];
+                gt[r] = __dadd_rn(gt[r], (double)__fmul_rn(2.0f, __fmul_rn(hl[r], zk[r])));
+                gf[r] = (float)gt[r];
+            }
+            ll = __dadd_rn(ll, (double)delta);
+            nacc += 1;
+            if (ll < best_ll) {
+                best_ll = ll;
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) bx[r] = x[r];
+            }
+        }
+    }
+    if (REC == PB200_RECORD_ACCEPTED) {
+        if (accepted) {
+            if (lane == 0 && rc.count - 1 < rc.capacity) rc.mult[rc.count - 1] = rc.cur_mult;
+            rc.cur_mult = 1;
+            record_row<CPL>(rc, x, ll, 1, lane);
+        } else {
+            rc.cur_mult += 1;
+        }
+    } else if (REC == PB200_RECORD_THINNED) {
+        if ((tk + 1) % (uint32_t)rc.thin == 0) record_row<CPL>(rc, x, ll, 1, lane);
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// MH steps [t_begin, t_end) of one chain (prospect/mcmc.py:163-190, batched and re-ordered):
+//   Delta   = step * sum_i z_i (gt_i + 1/2 step lam_i z_i)        O(n), FP32, every step
+//   accept  = Delta < T * e   and   x + step * Lt z inside the box  (matvec only if the first holds)
+// The reference draws the uniform even for out-of-box proposals and never evaluates the likelihood
+// there; "inside AND likelihood-accept" is the same predicate evaluated in the cheaper order.
+// Philox blocks cover 4 consecutive steps: whole blocks run a branch-free unrolled body, the ragged
+// head / tail of the range goes through one generic copy.
+// ----------------------------------------------------------------------------------------------
 template <int CPL, bool LT_REGS, int REC>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, const float* __restrict__ lt_pt, int lane,
                                           uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
@@ -68,7 +164,6 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, const float* _
                                           const float (&lam)[CPL], const double (&lo)[CPL], const double (&hi)[CPL],
                                           double (&x)[CPL], double (&gt)[CPL], double& ll, double& best_ll,
                                           double (&bx)[CPL], int32_t& nacc, float* zs, RecCursor& rc) {
-    constexpr int NPAD = 32 * CPL;
     float gf[CPL], hl[CPL];
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
@@ -76,87 +171,34 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, const float* _
         gf[r] = (float)gt[r];
         hl[r] = __fmul_rn(half_s, lam[r]);
     }
-    for (uint32_t blk = t_begin >> 2; (blk << 2) < t_end; ++blk) {
-        float z4s[CPL][4], e4[4];
-        draw_block<CPL>(k0, k1, chain_id, blk, p.n, lane, z4s, e4);
+    uint32_t t = t_begin;
+    while (t < t_end) {
+        const uint32_t blk = t >> 2, base = blk << 2;
+        float z[CPL][4], e[4];
+        draw_block<CPL>(k0, k1, chain_id, blk, p.n, lane, z, e);
+        if (t == base && t_end - base >= 4u) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                float zk[CPL];
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
+                one_step<CPL, LT_REGS, REC>(lt_pt, lane, base + k, Tf, sf, zk, e[k], ltrow, hl, gf, lo, hi, x, gt, ll,
+                                            best_ll, bx, nacc, zs, rc);
+            }
+            t = base + 4;
+        } else {
+            const uint32_t stop = min(base + 4u, t_end);
 #pragma unroll 1
-        for (int k = 0; k < 4; ++k) {           // not unrolled: one copy of the step body (I-cache, registers)
-            const uint32_t tk = (blk << 2) + k;
-            if (tk < t_begin || tk >= t_end) continue;      // warp-uniform
-            float zk[CPL];
+            for (uint32_t tk = t; tk < stop; ++tk) {
+                const int k = (int)(tk - base);
+                float zk[CPL];
 #pragma unroll
-            for (int r = 0; r < CPL; ++r)
-                zk[r] = k == 0 ? z4s[r][0] : (k == 1 ? z4s[r][1] : (k == 2 ? z4s[r][2] : z4s[r][3]));
-            const float ek = k == 0 ? e4[0] : (k == 1 ? e4[1] : (k == 2 ? e4[2] : e4[3]));
-            float tt = 0.0f;
-#pragma unroll
-            for (int r = 0; r < CPL; ++r) tt = __fmaf_rn(zk[r], __fmaf_rn(hl[r], zk[r], gf[r]), tt);
-            tt = warp_sum(tt);
-            const float delta = __fmul_rn(sf, tt);
-            bool accepted = false;
-            if (delta < __fmul_rn(Tf, ek)) {
-#pragma unroll
-                for (int r = 0; r < CPL; ++r) zs[lane + 32 * r] = zk[r];
-                __syncwarp();
-                double xn[CPL];
-                bool outside = false;
-                const float4* __restrict__ z4 = reinterpret_cast<const float4*>(zs);
-#pragma unroll
-                for (int r = 0; r < CPL; ++r) {
-                    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-                    if (LT_REGS) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 v = z4[j];
-                            a0 = __fmaf_rn(ltrow[4 * j + 0], v.x, a0);
-                            a1 = __fmaf_rn(ltrow[4 * j + 1], v.y, a1);
-                            a2 = __fmaf_rn(ltrow[4 * j + 2], v.z, a2);
-                            a3 = __fmaf_rn(ltrow[4 * j + 3], v.w, a3);
-                        }
-                    } else {
-                        const float* __restrict__ col = lt_pt + lane + 32 * r;
-#pragma unroll 4
-                        for (int j = 0; j < NPAD / 4; ++j) {
-                            const float4 v = z4[j];
-                            a0 = __fmaf_rn(__ldg(col + (4 * j + 0) * NPAD), v.x, a0);
-                            a1 = __fmaf_rn(__ldg(col + (4 * j + 1) * NPAD), v.y, a1);
-                            a2 = __fmaf_rn(__ldg(col + (4 * j + 2) * NPAD), v.z, a2);
-                            a3 = __fmaf_rn(__ldg(col + (4 * j + 3) * NPAD), v.w, a3);
-                        }
-                    }
-                    const float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
-                    xn[r] = __dadd_rn(x[r], (double)__fmul_rn(sf, acc));
-                    outside = outside || (xn[r] < lo[r]) || (xn[r] > hi[r]);
-                }
-                __syncwarp();
-                if (!__any_sync(kFull, outside)) {
-                    accepted = true;
-#pragma unroll
-                    for (int r = 0; r < CPL; ++r) {
-                        x[r] = xn[r];
-                        gt[r] = __dadd_rn(gt[r], (double)__fmul_rn(2.0f, __fmul_rn(hl[r], zk[r])));
-                        gf[r] = (float)gt[r];
-                    }
-                    ll = __dadd_rn(ll, (double)delta);
-                    nacc += 1;
-                    if (ll < best_ll) {
-                        best_ll = ll;
-#pragma unroll
-                        for (int r = 0; r < CPL; ++r) bx[r] = x[r];
-                    }
-                }
+                for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
+                const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
+                one_step<CPL, LT_REGS, REC>(lt_pt, lane, tk, Tf, sf, zk, ek, ltrow, hl, gf, lo, hi, x, gt, ll, best_ll,
+                                            bx, nacc, zs, rc);
             }
-            if (REC == PB200_RECORD_ACCEPTED) {
-                if (accepted) {
-                    if (lane == 0 && rc.count - 1 < rc.capacity) rc.mult[rc.count - 1] = rc.cur_mult;
-                    rc.cur_mult = 1;
-                    record_row<CPL>(rc, x, ll, 1, lane);
-                } else {
-                    rc.cur_mult += 1;
-                }
-            } else if (REC == PB200_RECORD_THINNED) {
-                if ((tk + 1) % (uint32_t)rc.thin == 0) record_row<CPL>(rc, x, ll, 1, lane);
-            }
+            t = stop;
         }
     }
 }
@@ -189,11 +231,11 @@ __device__ __forceinline__ void load_lane_const(const pb200_problem& p, int pt, 
 // Fused annealing kernel: n_iter iterations x S steps per launch, one warp per chain.
 // ----------------------------------------------------------------------------------------------
 template <int CPL>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (CPL == 1) ? PB200_MIN_CTAS : 1)
 anneal_kernel(pb200_problem p, pb200_chains c, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
               uint32_t k1) {
     constexpr int NPAD = 32 * CPL;
-    constexpr bool LT_REGS = (CPL == 1);
+    constexpr bool LT_REGS = (CPL == 1) && PB200_LT_REGS;
     __shared__ __align__(16) double stage[kWarpsPerCta][NPAD];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int chain = blockIdx.x * kWarpsPerCta + wib;
@@ -281,11 +323,11 @@ anneal_kernel(pb200_problem p, pb200_chains c, pb200_schedule s, pb200_records r
 constexpr uint32_t kResync = 256;
 
 template <int CPL, int REC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta)
+__global__ void __launch_bounds__(32 * kWarpsPerCta, (CPL == 1) ? PB200_MIN_CTAS : 1)
 mh_kernel(pb200_problem p, pb200_chains c, int n_steps, uint32_t k0, uint32_t k1, pb200_samples smp,
           int32_t* accepted_out) {
     constexpr int NPAD = 32 * CPL;
-    constexpr bool LT_REGS = (CPL == 1);
+    constexpr bool LT_REGS = (CPL == 1) && PB200_LT_REGS;
     __shared__ __align__(16) double stage[kWarpsPerCta][NPAD];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int chain = blockIdx.x * kWarpsPerCta + wib;
@@ -393,42 +435,66 @@ __global__ void schedule_kernel(pb200_chains c, pb200_schedule s, const int32_t*
     c.iteration[i] = st.iteration;
 }
 
-// One warp per profile point: per-chain first minimum over iterations, then first-minimum repetition
-// and the mean over repetitions that finished at least one iteration (analyse_profile_task.py:91-121).
-__global__ void profile_reduce_kernel(const double* __restrict__ best, const int32_t* __restrict__ accepted,
-                                      int n_iter, int b, int n_points, int reps, double* __restrict__ chain_best,
-                                      int32_t* __restrict__ chain_iter, double* __restrict__ point_best,
-                                      int32_t* __restrict__ point_rep, double* __restrict__ point_avg) {
-    const int lane = threadIdx.x & 31;
-    const int pt = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (pt >= n_points) return;
+// Running-bestfit reductions (analyse_profile_task.py:91-121) in two coalesced passes:
+//   chain_min_kernel   one thread per chain: first minimum over the iterations that ran;
+//   point_reduce_kernel one CTA per profile point: first-minimum repetition and the mean over the
+//                       repetitions that finished, block-wide via warp shuffles + one smem hop.
+__global__ void chain_min_kernel(const double* __restrict__ best, const int32_t* __restrict__ accepted, int n_iter,
+                                 int b, double* __restrict__ chain_best, int32_t* __restrict__ chain_iter) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= b) return;
+    double cb = INFINITY;
+    int ci = -1;
+    for (int k = 0; k < n_iter; ++k) {
+        const size_t o = (size_t)k * b + ch;
+        const double v = best[o];
+        if (accepted[o] >= 0 && v < cb) { cb = v; ci = k; }
+    }
+    chain_best[ch] = cb;
+    chain_iter[ch] = ci;
+}
+
+constexpr int kPointThreads = 256;
+
+__global__ void __launch_bounds__(kPointThreads)
+point_reduce_kernel(const double* __restrict__ chain_best, int n_points, int reps, double* __restrict__ point_best,
+                    int32_t* __restrict__ point_rep, double* __restrict__ point_avg) {
+    __shared__ double s_best[kPointThreads / 32], s_sum[kPointThreads / 32];
+    __shared__ int s_rep[kPointThreads / 32], s_cnt[kPointThreads / 32];
+    const int pt = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double my_best = INFINITY, my_sum = 0.0;
     int my_rep = 0x7fffffff, my_cnt = 0;
-    for (int rep = lane; rep < reps; rep += 32) {
-        const int ch = rep * n_points + pt;
-        double cb = INFINITY;
-        int ci = -1;
-        for (int k = 0; k < n_iter; ++k) {
-            const size_t o = (size_t)k * b + ch;
-            if (accepted[o] >= 0 && best[o] < cb) { cb = best[o]; ci = k; }
-        }
-        chain_best[ch] = cb;
-        chain_iter[ch] = ci;
+    for (int rep = threadIdx.x; rep < reps; rep += kPointThreads) {
+        const double cb = chain_best[(size_t)rep * n_points + pt];
         if (cb < my_best) { my_best = cb; my_rep = rep; }      // ascending reps: first minimum kept
         if (cb < INFINITY) { my_sum += cb; my_cnt += 1; }
     }
-#pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        const double ob = __shfl_xor_sync(kFull, my_best, m);
-        const int orp = __shfl_xor_sync(kFull, my_rep, m);
+    auto combine = [&](double ob, int orp, double os, int oc) {
         if (ob < my_best || (ob == my_best && orp < my_rep)) { my_best = ob; my_rep = orp; }
-        my_sum += __shfl_xor_sync(kFull, my_sum, m);
-        my_cnt += __shfl_xor_sync(kFull, my_cnt, m);
-    }
-    if (lane == 0) {
-        point_best[pt] = my_best;
-        point_rep[pt] = (my_best < INFINITY) ? my_rep : 0;     // np.argmin of all-inf is 0
-        point_avg[pt] = my_cnt > 0 ? my_sum / my_cnt : INFINITY;
+        my_sum += os;
+        my_cnt += oc;
+    };
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1)
+        combine(__shfl_xor_sync(kFull, my_best, m), __shfl_xor_sync(kFull, my_rep, m),
+                __shfl_xor_sync(kFull, my_sum, m), __shfl_xor_sync(kFull, my_cnt, m));
+    if (lane == 0) { s_best[warp] = my_best; s_rep[warp] = my_rep; s_sum[warp] = my_sum; s_cnt[warp] = my_cnt; }
+    __syncthreads();
+    if (warp == 0) {
+        const bool have = lane < kPointThreads / 32;
+        my_best = have ? s_best[lane] : INFINITY;
+        my_rep = have ? s_rep[lane] : 0x7fffffff;
+        my_sum = have ? s_sum[lane] : 0.0;
+        my_cnt = have ? s_cnt[lane] : 0;
+#pragma unroll
+        for (int m = 4; m >= 1; m >>= 1)
+            combine(__shfl_xor_sync(kFull, my_best, m), __shfl_xor_sync(kFull, my_rep, m),
+                    __shfl_xor_sync(kFull, my_sum, m), __shfl_xor_sync(kFull, my_cnt, m));
+        if (lane == 0) {
+            point_best[pt] = my_best;
+            point_rep[pt] = (my_best < INFINITY) ? my_rep : 0;     // np.argmin of all-inf is 0
+            point_avg[pt] = my_cnt > 0 ? my_sum / my_cnt : INFINITY;
+        }
     }
 }
 
@@ -615,10 +681,12 @@ int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int
         return fail("profile_reduce: NULL argument");
     if (b != n_points * reps) return fail("profile_reduce: b must equal n_points * reps");
     if (n_points <= 0) return 0;
-    profile_reduce_kernel<<<(n_points + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        best_loglkl, accepted, n_iter, b, n_points, reps, out_chain_best, out_chain_iter, out_point_best,
-        out_point_rep, out_point_avg);
-    return check_cuda(cudaGetLastError(), "profile_reduce_kernel launch");
+    chain_min_kernel<<<(b + 255) / 256, 256, 0, (cudaStream_t)stream>>>(best_loglkl, accepted, n_iter, b,
+                                                                       out_chain_best, out_chain_iter);
+    point_reduce_kernel<<<n_points, kPointThreads, 0, (cudaStream_t)stream>>>(out_chain_best, n_points, reps,
+                                                                              out_point_best, out_point_rep,
+                                                                              out_point_avg);
+    return check_cuda(cudaGetLastError(), "profile_reduce launch");
 }
 
 int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, int32_t ld, int32_t n, double* out,

@@ -150,7 +150,7 @@ def profile_reduce(records: Records, n_iter, n_points, reps, stream=None):
         'point_rep': torch.empty(n_points, dtype=torch.int32, device=dev),
         'point_avg': torch.empty(n_points, dtype=torch.float64, device=dev),
     }
-    _count()
+    _count(2)
     capi.check(capi.lib().pb200_profile_reduce(
         capi.ptr(records.best_loglkl), capi.ptr(records.accepted), int(n_iter), b, int(n_points), int(reps),
         capi.ptr(out['chain_best']), capi.ptr(out['chain_iter']), capi.ptr(out['point_best']),

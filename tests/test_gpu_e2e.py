@@ -142,7 +142,9 @@ def test_30d_profile_32x256_cold_schedule_reaches_analytic(tmp_path):
     lp = load_profile(str(tmp_path / 'out'))
     assert len(lp['x2']) == 32
     # chains of one point are independent (distinct Philox streams): repetitions do not coincide
-    assert len(np.unique(srt['chain_best'][:, 0])) > 250
+    # (checked on the first, hot iteration; at T = 1e-12 all of them agree to the last bits of the minimum)
+    assert len(np.unique(rec.best_loglkl[0].reshape(256, 32)[:, 0])) == 256
+    assert np.max(srt['chain_best'][:, 0]) - np.min(srt['chain_best'][:, 0]) < 1e-8
 
 
 def test_global_optimisation_4096_chains(tmp_path):
@@ -174,7 +176,7 @@ def test_mcmc_job_65536_chains_ks(tmp_path):
     d = 30
     target_cov = closed_form.stationary_covariance(k['covmat'])
     cfg = Configuration(mcmc_yaml(paths, str(tmp_path / 'o'), n_chains=65536, steps=2000, write=False,
-                                  start_from_covmat=target_cov.tolist(), step_size=2.4 / np.sqrt(d)))
+                                  start_from_covmat=target_cov.tolist(), step_size=float(2.4 / np.sqrt(d))))
     kernel = initialise_kernel(cfg.kernel, None, 0)
     sampler = initialise_mcmc(cfg.mcmc, kernel, seed=77, record='thinned', thin=2000)
     sampler.run_steps(2000)            # burn-in from the reference's default start (zeros)
@@ -206,8 +208,8 @@ def test_mcmc_job_writes_chain_files_like_reference(tmp_path):
     assert np.sum(chain.mults) == 4 * 2001                      # every chain: sum(mults) = steps + 1
     assert os.path.isfile(os.path.join(out_dir, 'mcmc', 'test.paramnames'))
     ref = golden('toy20_mcmc.npz')
-    n_ref = sum(len(ref[f'chain_{i}']) for i in range(4)) / 4.0  # reference: 4 rounds
-    assert 0.5 < len(chain.mults) / n_ref * 4 < 2.0              # similar acceptance as the reference's chains
+    rows_per_round = sum(len(ref[f'chain_{i}']) for i in range(4)) / 4.0     # the reference ran 4 rounds
+    assert 0.7 < len(chain.mults) / rows_per_round < 1.4          # same acceptance as the reference's chains
 
 
 def test_wide_kernel_profile_d256(tmp_path):
