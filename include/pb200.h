@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 1
+#define PB200_ABI_VERSION 2
 
 /* chain status (pb200_chains.status) */
 #define PB200_ACTIVE     0
@@ -70,6 +70,8 @@ typedef struct pb200_problem {
     const double* c0;     /* device [P] */
     const float*  lt_t;   /* device [P][npad*npad]  lt_t[j*npad+i] = Lt[i][j]  (FP32) */
     const float*  lam;    /* device [P][npad]       eigenvalues (FP32) */
+    const float*  lt_norm;/* device [P][npad]       Euclidean norm of row i of Lt, rounded up (0 for pads): bounds
+                             |x_i - xref_i| <= lt_norm_i * |w| for a whitened displacement w (deferred box test) */
     const double* g_t;    /* device [P][npad*npad]  g_t[j*npad+i] = G[i][j] */
     const double* h;      /* device [P][npad] */
 } pb200_problem;
@@ -113,9 +115,13 @@ typedef struct pb200_schedule {
  * One record per (iteration, chain): what SimulatedAnnealing.set_bestfit produces
  * (prospect/optimiser.py:74-85) plus the settings the task ran with.  Row k = iteration_number.
  * accepted = -1 marks "chain did not run this iteration" (converged / failed earlier).
+ * All arrays of one iteration may live in one contiguous block (that block is what ranks all-gather at an
+ * iteration boundary): element (k, c) of an f64 array is at [k * iter_stride + c], of `accepted` at
+ * [k * 2 * iter_stride + c], coordinate i of best_x / last_x at [k * iter_stride + c * npad + i].
  */
 typedef struct pb200_records {
     int32_t  max_iterations;    /* rows allocated */
+    int64_t  iter_stride;       /* distance between consecutive iterations, in doubles */
     double*  best_loglkl;       /* device [K][B]  exact FP64 loglkl of best_x */
     double*  last_loglkl;       /* device [K][B] */
     double*  temperature;       /* device [K][B] */
@@ -161,7 +167,7 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
  * (prospect/optimiser.py:40-162) and MetropolisHastings.step/get_proposal (prospect/mcmc.py:163-190).
  */
 int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
-                     const pb200_records* rec, int32_t n_iter, uint64_t seed, void* stream);
+                     const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream);
 
 /*
  * n_steps Metropolis-Hastings steps per chain at the chain's temperature / step size, optionally
@@ -169,7 +175,14 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
  * (prospect/tasks/mcmc_task.py:17-23, prospect/mcmc.py:131-138).  accepted_out [B] device (may be NULL).
  */
 int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,
-                 const pb200_samples* samples, int32_t* accepted_out, void* stream);
+                 const pb200_samples* samples, int32_t* accepted_out, int32_t lanes_per_chain, void* stream);
+
+/*
+ * lanes_per_chain (both samplers): how many lanes of a warp cooperate on one chain -- 32, 16 or 8 (16 / 8 only
+ * for npad <= 64 / 32); 0 lets the library choose from the batch size.  A chain's random stream does not depend
+ * on it; the floating-point summation order inside a step does (pb200_choose_lanes tells what 0 resolves to).
+ */
+int pb200_choose_lanes(int32_t npad, int32_t n_chains);
 
 /*
  * Stand-alone adaptive step-size / temperature bookkeeping for B chains (the same device function the
@@ -184,11 +197,12 @@ int pb200_schedule_update(const pb200_chains* chains, const pb200_schedule* sche
  * Running-bestfit reductions of the analysis side.  Replaces AnalyseProfileTask.sort_tasks
  * (prospect/tasks/analyse_profile_task.py:91-121): per chain the first minimum over iterations,
  * per point the first-minimum repetition and the mean over repetitions with a finite bestfit.
- *   best_loglkl [K][B] + accepted [K][B] (records); n_iter rows used; B = R * P (rep-major).
+ *   best_loglkl / accepted: element (k, c) at best_loglkl[k * stride_best + c] / accepted[k * stride_accepted + c]
+ *   (records: iter_stride and 2 * iter_stride; dense [K][B] arrays: b and b); n_iter rows; B = R * P (rep-major).
  *   out_chain_best [B], out_chain_iter [B], out_point_best [P], out_point_rep [P], out_point_avg [P].
  */
-int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int32_t n_iter, int32_t b,
-                         int32_t n_points, int32_t reps,
+int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int64_t stride_best,
+                         int64_t stride_accepted, int32_t n_iter, int32_t b, int32_t n_points, int32_t reps,
                          double* out_chain_best, int32_t* out_chain_iter,
                          double* out_point_best, int32_t* out_point_rep, double* out_point_avg, void* stream);
 

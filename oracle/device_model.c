@@ -16,6 +16,10 @@
  *   prospect/kernels/analytical_kernel.py:59-66 + base_kernel.py:89-102  Gaussian -log L, prior box
  * Parity of those semantics with the reference itself is pinned through oracle/reference_port.py
  * (tests/test_oracle_golden.py) and compared with this model in tests/test_device_model.py.
+ *
+ * Device specifics that are mirrored: a chain is spread over `lpc` lanes (coordinate c lives on lane
+ * c % lpc), sums are butterfly reductions over those lanes, and the prior-box test is deferred: the
+ * chain keeps position = xref + Lt*w and only materialises it when |w|^2 leaves a provably safe radius.
  */
 #include <math.h>
 #include <stdint.h>
@@ -23,11 +27,12 @@
 #include <string.h>
 
 #define ACCEPT_SLOT 0xffffffffu
+#define MAXN 256
 
 typedef struct {
     int32_t d, n, npad, n_points;
     const double *saa, *sab, *mu, *lo, *hi, *f, *c0;
-    const float *lt_t, *lam;
+    const float *lt_t, *lam, *lt_norm;
     const double *g_t, *h;
 } dm_problem;
 
@@ -43,6 +48,14 @@ typedef struct {          /* one chain */
     int32_t point, iteration, status, stage;
     uint32_t chain_id, steps_done;
 } dm_chain;
+
+typedef struct {          /* in-flight state of a chain (device registers) */
+    double xref[MAXN], gt[MAXN], bref[MAXN];
+    float w[MAXN], bw[MAXN];
+    double ll, best_ll;
+    float m2;
+    int32_t nacc;
+} dm_state;
 
 void dm_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3], k0 = key[0], k1 = key[1];
@@ -74,7 +87,7 @@ void dm_variates(uint64_t seed, uint32_t chain_id, uint32_t step0, int32_t n_ste
     for (uint32_t blk = step0 >> 2; (blk << 2) < t_end; ++blk) {
         for (int c = 0; c <= n; ++c) {
             uint32_t ctr[4] = {blk, c == n ? ACCEPT_SLOT : (uint32_t)c, chain_id, 0u}, w[4];
-            float zz[4];
+            float zz[4] = {0.f, 0.f, 0.f, 0.f};
             dm_philox4x32_10(ctr, key, w);
             if (c < n) {
                 box_muller(w[0], w[1], &zz[0], &zz[1]);
@@ -90,33 +103,34 @@ void dm_variates(uint64_t seed, uint32_t chain_id, uint32_t step0, int32_t n_ste
     }
 }
 
-static float warp_sum_f(float v[32]) {
+/* butterfly reductions over the lpc lanes of a group; every lane ends with the same value */
+static float group_sum_f(float *v, int lpc) {
     float t[32];
-    for (int m = 16; m >= 1; m >>= 1) {
-        for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ m];
-        memcpy(v, t, sizeof(t));
+    for (int m = lpc / 2; m >= 1; m >>= 1) {
+        for (int i = 0; i < lpc; ++i) t[i] = v[i] + v[i ^ m];
+        memcpy(v, t, sizeof(float) * lpc);
     }
     return v[0];
 }
-static double warp_sum_d(double v[32]) {
+static double group_sum_d(double *v, int lpc) {
     double t[32];
-    for (int m = 16; m >= 1; m >>= 1) {
-        for (int i = 0; i < 32; ++i) t[i] = v[i] + v[i ^ m];
-        memcpy(v, t, sizeof(t));
+    for (int m = lpc / 2; m >= 1; m >>= 1) {
+        for (int i = 0; i < lpc; ++i) t[i] = v[i] + v[i ^ m];
+        memcpy(v, t, sizeof(double) * lpc);
     }
     return v[0];
 }
 
 /* exact FP64 -log L at x (and gt = G q + h when gt != NULL), device operation order */
-double dm_exact_eval(const dm_problem *p, int pt, const double *x, double *gt) {
-    const int np = p->npad, cpl = np / 32;
-    double q[256], part[32];
+double dm_exact_eval(const dm_problem *p, int pt, const double *x, double *gt, int lpc) {
+    const int np = p->npad, cpl = np / lpc;
+    double q[MAXN], part[32];
     for (int c = 0; c < np; ++c) q[c] = x[c] - p->mu[c];
     const double f = p->f[pt];
-    for (int lane = 0; lane < 32; ++lane) {
+    for (int gl = 0; gl < lpc; ++gl) {
         double acc = 0.0;
         for (int r = 0; r < cpl; ++r) {
-            const int c = lane + 32 * r;
+            const int c = gl + lpc * r;
             double v = 0.0, g = 0.0;
             for (int j = 0; j < p->n; ++j) {
                 v = fma(p->saa[(size_t)j * np + c], q[j], v);
@@ -125,71 +139,147 @@ double dm_exact_eval(const dm_problem *p, int pt, const double *x, double *gt) {
             acc = fma(q[c], fma(0.5, v, f * p->sab[c]), acc);
             if (gt) gt[c] = g + p->h[(size_t)pt * np + c];
         }
-        part[lane] = acc;
+        part[gl] = acc;
     }
-    return warp_sum_d(part) + p->c0[pt];
+    return group_sum_d(part, lpc) + p->c0[pt];
+}
+
+/* out = base + Lt w: FP32 matvec, four interleaved partial sums over j, one FP64 add */
+static void materialise(const dm_problem *p, int pt, const double *base, const float *w, double *out) {
+    const int np = p->npad;
+    const float *lt = p->lt_t + (size_t)pt * np * np;
+    for (int c = 0; c < np; ++c) {
+        float a[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int j = 0; j < np; ++j) a[j & 3] = fmaf(lt[(size_t)j * np + c], w[j], a[j & 3]);
+        out[c] = base[c] + (double)((a[0] + a[1]) + (a[2] + a[3]));
+    }
+}
+
+/* squared whitened radius around base inside which base + Lt w provably stays in the prior box */
+static float safe_radius2(const dm_problem *p, int pt, const double *base) {
+    const int np = p->npad;
+    double m = INFINITY;
+    for (int c = 0; c < np; ++c) {
+        const double nrm = (double)p->lt_norm[(size_t)pt * np + c];
+        const double dist = fmin(p->hi[c] - base[c], base[c] - p->lo[c]);
+        if (nrm > 0.0) m = fmin(m, dist / nrm);
+    }
+    m = fmax(m, 0.0) * 0.999;
+    return (float)(m * m);
+}
+
+static void anchor(const dm_problem *p, int pt, const double *x, dm_state *s, int lpc) {
+    s->ll = dm_exact_eval(p, pt, x, s->gt, lpc);
+    memcpy(s->xref, x, sizeof(double) * p->npad);
+    memset(s->w, 0, sizeof(float) * p->npad);
+    s->m2 = safe_radius2(p, pt, s->xref);
 }
 
 /*
- * MH steps [t_begin, t_end).  z_replay/e_replay (may be NULL) are indexed by (step - replay_step0).
- * on_row (may be NULL) is called for chain recording: kind 0 = accepted point, 1 = rejected, 2 = any step.
+ * MH steps [t_begin, t_begin + n_steps).  z_replay/e_replay (may be NULL) are indexed by (step - replay_step0).
+ * rec_mode: 0 none, 1 accepted points (every accepted move is materialised), 2 thinned.
  */
-typedef void (*dm_row_cb)(void *user, int kind, uint32_t step, const double *x, double ll);
+typedef struct {
+    int mode, thin, capacity, np, count, cur_mult;
+    double *x, *ll;
+    int32_t *mult;
+} dm_recorder;
 
-static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain_id, uint32_t t_begin, uint32_t t_end,
-                      float Tf, float sf, double *x, double *gt, double *ll, double *best_ll, double *bx,
-                      int32_t *nacc, const float *z_replay, const float *e_replay, uint32_t replay_step0,
-                      dm_row_cb cb, void *user) {
-    const int np = p->npad, n = p->n, cpl = np / 32;
-    const float *lt = p->lt_t + (size_t)pt * np * np;
+static void rec_push(dm_recorder *r, const double *x, double ll, int mult) {
+    if (r->count < r->capacity) {
+        memcpy(r->x + (size_t)r->count * r->np, x, sizeof(double) * r->np);
+        r->ll[r->count] = ll;
+        r->mult[r->count] = mult;
+    }
+    r->count += 1;
+}
+
+static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain_id, uint32_t t_begin,
+                      uint32_t n_steps, float Tf, float sf, int lpc, dm_state *s, const float *z_replay,
+                      const float *e_replay, uint32_t replay_step0, dm_recorder *rec) {
+    const int np = p->npad, n = p->n, cpl = np / lpc;
     const float *lam = p->lam + (size_t)pt * np;
-    float gf[256], hl[256], z[256];
-    double xn[256];
+    float gf[MAXN], hl[MAXN], z[MAXN], wt[MAXN];
+    double xt[MAXN];
     const float half_s = 0.5f * sf;
-    for (int c = 0; c < np; ++c) { gf[c] = (float)gt[c]; hl[c] = half_s * lam[c]; }
+    for (int c = 0; c < np; ++c) { gf[c] = (float)s->gt[c]; hl[c] = half_s * lam[c]; }
     float *zbuf = NULL, *ebuf = NULL;
     if (!z_replay) {
-        zbuf = (float *)malloc(sizeof(float) * (size_t)(t_end - t_begin) * n);
-        ebuf = (float *)malloc(sizeof(float) * (size_t)(t_end - t_begin));
-        dm_variates(seed, chain_id, t_begin, (int32_t)(t_end - t_begin), n, zbuf, ebuf);
+        zbuf = (float *)malloc(sizeof(float) * (size_t)n_steps * n);
+        ebuf = (float *)malloc(sizeof(float) * (size_t)n_steps);
+        dm_variates(seed, chain_id, t_begin, (int32_t)n_steps, n, zbuf, ebuf);
     }
-    for (uint32_t t = t_begin; t < t_end; ++t) {
-        const float *zt = z_replay ? z_replay + (size_t)(t - replay_step0) * n : zbuf + (size_t)(t - t_begin) * n;
-        const float ek = e_replay ? e_replay[t - replay_step0] : ebuf[t - t_begin];
+    const int always_exact = rec && rec->mode == 1;
+    for (uint32_t i = 0; i < n_steps; ++i) {
+        const uint32_t t = t_begin + i;
+        const float *zt = z_replay ? z_replay + (size_t)(t - replay_step0) * n : zbuf + (size_t)i * n;
+        const float ek = e_replay ? e_replay[t - replay_step0] : ebuf[i];
         for (int c = 0; c < np; ++c) z[c] = c < n ? zt[c] : 0.0f;
         float lanes[32];
-        for (int lane = 0; lane < 32; ++lane) {
+        for (int gl = 0; gl < lpc; ++gl) {
             float tt = 0.0f;
             for (int r = 0; r < cpl; ++r) {
-                const int c = lane + 32 * r;
+                const int c = gl + lpc * r;
                 tt = fmaf(z[c], fmaf(hl[c], z[c], gf[c]), tt);
             }
-            lanes[lane] = tt;
+            lanes[gl] = tt;
         }
-        const float delta = sf * warp_sum_f(lanes);
-        int accepted = 0;
+        const float delta = sf * group_sum_f(lanes, lpc);
+        int acc = 0;
         if (delta < Tf * ek) {
-            int outside = 0;
-            for (int c = 0; c < np; ++c) {
-                float a[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int j = 0; j < np; ++j) a[j & 3] = fmaf(lt[(size_t)j * np + c], z[j], a[j & 3]);
-                const float acc = (a[0] + a[1]) + (a[2] + a[3]);
-                xn[c] = x[c] + (double)(sf * acc);
-                if (xn[c] < p->lo[c] || xn[c] > p->hi[c]) outside = 1;
-            }
-            if (!outside) {
-                accepted = 1;
-                for (int c = 0; c < np; ++c) {
-                    x[c] = xn[c];
-                    gt[c] = gt[c] + (double)(2.0f * (hl[c] * z[c]));
-                    gf[c] = (float)gt[c];
+            for (int gl = 0; gl < lpc; ++gl) {
+                float rr = 0.0f;
+                for (int r = 0; r < cpl; ++r) {
+                    const int c = gl + lpc * r;
+                    wt[c] = fmaf(sf, z[c], s->w[c]);
+                    rr = fmaf(wt[c], wt[c], rr);
                 }
-                *ll = *ll + (double)delta;
-                *nacc += 1;
-                if (*ll < *best_ll) { *best_ll = *ll; memcpy(bx, x, sizeof(double) * np); }
+                lanes[gl] = rr;
+            }
+            const float rr = group_sum_f(lanes, lpc);
+            acc = 1;
+            if (always_exact || !(rr <= s->m2)) {
+                materialise(p, pt, s->xref, wt, xt);
+                int outside = 0;
+                for (int c = 0; c < np; ++c)
+                    if (xt[c] < p->lo[c] || xt[c] > p->hi[c]) outside = 1;
+                if (outside) {
+                    acc = 0;
+                } else {
+                    memcpy(s->xref, xt, sizeof(double) * np);
+                    memset(wt, 0, sizeof(float) * np);
+                    s->m2 = safe_radius2(p, pt, s->xref);
+                }
+            }
+            if (acc) {
+                for (int c = 0; c < np; ++c) {
+                    s->w[c] = wt[c];
+                    s->gt[c] = s->gt[c] + (double)(2.0f * (hl[c] * z[c]));
+                    gf[c] = (float)s->gt[c];
+                }
+                s->ll = s->ll + (double)delta;
+                s->nacc += 1;
+                if (s->ll < s->best_ll) {
+                    s->best_ll = s->ll;
+                    memcpy(s->bw, s->w, sizeof(float) * np);
+                    memcpy(s->bref, s->xref, sizeof(double) * np);
+                }
             }
         }
-        if (cb) { cb(user, accepted ? 0 : 1, t, x, *ll); cb(user, 2, t, x, *ll); }
+        if (rec && rec->mode == 1) {
+            if (acc) {
+                if (rec->count - 1 < rec->capacity) rec->mult[rec->count - 1] = rec->cur_mult;
+                rec->cur_mult = 1;
+                rec_push(rec, s->xref, s->ll, 1);
+            } else {
+                rec->cur_mult += 1;
+            }
+        } else if (rec && rec->mode == 2) {
+            if ((t + 1) % (uint32_t)rec->thin == 0) {
+                materialise(p, pt, s->xref, s->w, xt);
+                rec_push(rec, xt, s->ll, 1);
+            }
+        }
     }
     free(zbuf); free(ebuf);
 }
@@ -234,95 +324,70 @@ void dm_schedule_next(const dm_schedule *s, dm_chain *st, int32_t accepted, doub
 }
 
 /*
- * n_iter annealing iterations of one chain.  Per-iteration outputs are rows [row0 + k] of the rec_* arrays
- * (row0 = the chain's iteration number at entry): best/last loglkl, T, step, accepted, best_x/last_x [npad].
+ * n_iter annealing iterations of one chain.  Per-iteration outputs are rows [k] of the rec_* arrays
+ * (k counted from the chain's iteration number at entry): best/last loglkl, T, step, accepted, best_x/last_x.
  */
-void dm_anneal_chain(const dm_problem *p, const dm_schedule *s, dm_chain *c, int32_t n_iter, uint64_t seed,
+void dm_anneal_chain(const dm_problem *p, const dm_schedule *s, dm_chain *c, int32_t n_iter, uint64_t seed, int lpc,
                      const float *z_replay, const float *e_replay, double *rec_best, double *rec_last,
                      double *rec_T, double *rec_step, int32_t *rec_acc, double *rec_best_x, double *rec_last_x) {
     const int np = p->npad;
-    double gt[256], bx[256], tmp[256];
+    double bx[MAXN];
+    dm_state st;
     if (c->status != 0) return;
     const uint32_t replay0 = c->steps_done;
-    double ll = dm_exact_eval(p, c->point, c->x, gt);
+    anchor(p, c->point, c->x, &st, lpc);
     int row = 0;
     for (int it = 0; it < n_iter && c->status == 0; ++it, ++row) {
-        double best_ll = ll;
-        int32_t nacc = 0;
-        memcpy(bx, c->x, sizeof(double) * np);
-        run_steps(p, c->point, seed, c->chain_id, c->steps_done, c->steps_done + s->steps_per_iteration,
-                  (float)c->temperature, (float)c->step_size, c->x, gt, &ll, &best_ll, bx, &nacc, z_replay, e_replay,
-                  replay0, NULL, NULL);
+        st.best_ll = st.ll;
+        st.nacc = 0;
+        memcpy(st.bref, st.xref, sizeof(double) * np);
+        memset(st.bw, 0, sizeof(float) * np);
+        run_steps(p, c->point, seed, c->chain_id, c->steps_done, (uint32_t)s->steps_per_iteration,
+                  (float)c->temperature, (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, NULL);
         c->steps_done += s->steps_per_iteration;
-        const double best_exact = dm_exact_eval(p, c->point, bx, NULL);
-        ll = dm_exact_eval(p, c->point, c->x, gt);
-        (void)tmp;
-        rec_best[row] = best_exact; rec_last[row] = ll; rec_T[row] = c->temperature; rec_step[row] = c->step_size;
+        materialise(p, c->point, st.bref, st.bw, bx);
+        materialise(p, c->point, st.xref, st.w, c->x);
+        const double best_exact = dm_exact_eval(p, c->point, bx, NULL, lpc);
+        const int32_t nacc = st.nacc;
+        anchor(p, c->point, c->x, &st, lpc);
+        rec_best[row] = best_exact; rec_last[row] = st.ll; rec_T[row] = c->temperature; rec_step[row] = c->step_size;
         rec_acc[row] = nacc;
         if (rec_best_x) memcpy(rec_best_x + (size_t)row * np, bx, sizeof(double) * np);
         if (rec_last_x) memcpy(rec_last_x + (size_t)row * np, c->x, sizeof(double) * np);
         dm_schedule_next(s, c, nacc, best_exact);
     }
-    c->loglkl = ll;
-}
-
-/* chain recording for dm_mh_chain */
-typedef struct {
-    int mode, thin, capacity, np, count, cur_mult;
-    double *x, *ll;
-    int32_t *mult;
-} dm_recorder;
-
-static void rec_push(dm_recorder *r, const double *x, double ll, int mult) {
-    if (r->count < r->capacity) {
-        memcpy(r->x + (size_t)r->count * r->np, x, sizeof(double) * r->np);
-        r->ll[r->count] = ll;
-        r->mult[r->count] = mult;
-    }
-    r->count += 1;
-}
-static void rec_cb(void *user, int kind, uint32_t step, const double *x, double ll) {
-    dm_recorder *r = (dm_recorder *)user;
-    if (r->mode == 1) {
-        if (kind == 0) {
-            if (r->count - 1 < r->capacity) r->mult[r->count - 1] = r->cur_mult;
-            r->cur_mult = 1;
-            rec_push(r, x, ll, 1);
-        } else if (kind == 1) {
-            r->cur_mult += 1;
-        }
-    } else if (r->mode == 2 && kind == 2) {
-        if ((step + 1) % (uint32_t)r->thin == 0) rec_push(r, x, ll, 1);
-    }
+    c->loglkl = st.ll;
 }
 
 /* n_steps MH steps with the device's 256-step re-anchoring; returns accepted count; *count in/out */
-int32_t dm_mh_chain(const dm_problem *p, dm_chain *c, int32_t n_steps, uint64_t seed, const float *z_replay,
+int32_t dm_mh_chain(const dm_problem *p, dm_chain *c, int32_t n_steps, uint64_t seed, int lpc, const float *z_replay,
                     const float *e_replay, int mode, int thin, int capacity, double *sx, double *sll, int32_t *smult,
                     int32_t *count) {
     const int np = p->npad;
-    double gt[256], bx[256];
+    dm_state st;
     const uint32_t replay0 = c->steps_done;
-    double ll = dm_exact_eval(p, c->point, c->x, gt);
+    anchor(p, c->point, c->x, &st, lpc);
+    st.best_ll = st.ll;
+    st.nacc = 0;
+    memcpy(st.bref, st.xref, sizeof(double) * np);
+    memset(st.bw, 0, sizeof(float) * np);
     dm_recorder r = {mode, thin > 0 ? thin : 1, capacity, np, count ? *count : 0, 1, sx, sll, smult};
     if (mode == 1) {
-        if (r.count == 0) rec_push(&r, c->x, ll, 1);
+        if (r.count == 0) rec_push(&r, c->x, st.ll, 1);
         else r.cur_mult = r.count - 1 < capacity ? smult[r.count - 1] : 1;
     }
-    double best_ll = ll;
-    int32_t nacc = 0;
-    uint32_t t = c->steps_done;
-    const uint32_t t_end = t + (uint32_t)n_steps;
-    while (t < t_end) {
-        const uint32_t t_next = t_end < t + 256u ? t_end : t + 256u;
-        run_steps(p, c->point, seed, c->chain_id, t, t_next, (float)c->temperature, (float)c->step_size, c->x, gt, &ll,
-                  &best_ll, bx, &nacc, z_replay, e_replay, replay0, mode ? rec_cb : NULL, &r);
-        t = t_next;
-        ll = dm_exact_eval(p, c->point, c->x, gt);
+    uint32_t done = 0;
+    while (done < (uint32_t)n_steps) {
+        const uint32_t chunk = (uint32_t)n_steps - done < 256u ? (uint32_t)n_steps - done : 256u;
+        run_steps(p, c->point, seed, c->chain_id, c->steps_done + done, chunk, (float)c->temperature,
+                  (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, mode ? &r : NULL);
+        done += chunk;
+        materialise(p, c->point, st.xref, st.w, c->x);
+        anchor(p, c->point, c->x, &st, lpc);
     }
     if (mode == 1 && r.count - 1 < capacity) smult[r.count - 1] = r.cur_mult;
     if (count) *count = r.count;
-    c->steps_done = t;
-    c->loglkl = ll;
-    return nacc;
+    c->steps_done += (uint32_t)n_steps;
+    c->loglkl = st.ll;
+    return st.nacc;
 }

@@ -22,7 +22,7 @@ _ip = C.POINTER(C.c_int32)
 class DmProblem(C.Structure):
     _fields_ = [('d', C.c_int32), ('n', C.c_int32), ('npad', C.c_int32), ('n_points', C.c_int32),
                 ('saa', _dp), ('sab', _dp), ('mu', _dp), ('lo', _dp), ('hi', _dp), ('f', _dp), ('c0', _dp),
-                ('lt_t', _fp), ('lam', _fp), ('g_t', _dp), ('h', _dp)]
+                ('lt_t', _fp), ('lam', _fp), ('lt_norm', _fp), ('g_t', _dp), ('h', _dp)]
 
 
 class DmSchedule(C.Structure):
@@ -53,7 +53,7 @@ def lib():
     if _lib is None:
         h = C.CDLL(build())
         h.dm_exact_eval.restype = C.c_double
-        h.dm_exact_eval.argtypes = [C.POINTER(DmProblem), C.c_int, _dp, _dp]
+        h.dm_exact_eval.argtypes = [C.POINTER(DmProblem), C.c_int, _dp, _dp, C.c_int]
         h.dm_mh_chain.restype = C.c_int32
         h.dm_variates.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _fp, _fp]
         _lib = h
@@ -71,22 +71,24 @@ def _f(a):
 class Model:
     """Holds contiguous copies of the problem arrays and exposes the C entry points."""
 
-    def __init__(self, hp):
+    def __init__(self, hp, lanes=32):
+        """lanes: lanes per chain of the device geometry being mirrored (32, 16 or 8)."""
         self.hp = hp
+        self.lanes = int(lanes)
         self.np_ = hp.npad
         self.arr = {k: np.ascontiguousarray(getattr(hp, k), dtype=np.float64)
                     for k in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'g_t', 'h')}
-        self.arr32 = {k: np.ascontiguousarray(getattr(hp, k), dtype=np.float32) for k in ('lt_t', 'lam')}
+        self.arr32 = {k: np.ascontiguousarray(getattr(hp, k), dtype=np.float32) for k in ('lt_t', 'lam', 'lt_norm')}
         a, b = self.arr, self.arr32
         self.c = DmProblem(hp.d, hp.n, hp.npad, hp.n_points, _d(a['saa']), _d(a['sab']), _d(a['mu']), _d(a['lo']),
-                           _d(a['hi']), _d(a['f']), _d(a['c0']), _f(b['lt_t']), _f(b['lam']), _d(a['g_t']),
+                           _d(a['hi']), _d(a['f']), _d(a['c0']), _f(b['lt_t']), _f(b['lam']), _f(b['lt_norm']), _d(a['g_t']),
                            _d(a['h']))
 
     def exact_eval(self, x, point=0, with_grad=False):
         xp = np.zeros(self.np_)
         xp[:len(x)] = x
         gt = np.zeros(self.np_) if with_grad else None
-        ll = lib().dm_exact_eval(C.byref(self.c), int(point), _d(xp), _d(gt) if with_grad else None)
+        ll = lib().dm_exact_eval(C.byref(self.c), int(point), _d(xp), _d(gt) if with_grad else None, self.lanes)
         return (ll, gt) if with_grad else ll
 
     def new_chain(self, x0, point=0, chain_id=0, temperature=1.0, step_size=1.0, current_best=np.inf, steps_done=0):
@@ -106,6 +108,7 @@ class Model:
             z = np.ascontiguousarray(z, dtype=np.float32)
             e = np.ascontiguousarray(e, dtype=np.float32)
         lib().dm_anneal_chain(C.byref(self.c), C.byref(sched), C.byref(chain), C.c_int32(n_iter), C.c_uint64(seed),
+                              C.c_int(self.lanes),
                               _f(z) if z is not None else None, _f(e) if e is not None else None,
                               _d(out['best_loglkl']), _d(out['last_loglkl']), _d(out['temperature']),
                               _d(out['step_size']), out['accepted'].ctypes.data_as(_ip), _d(out['best_x']),
@@ -120,7 +123,7 @@ class Model:
             samples = {'x': np.zeros((capacity, self.np_)), 'loglkl': np.zeros(capacity),
                        'mult': np.zeros(capacity, dtype=np.int32), 'count': np.zeros(1, dtype=np.int32)}
         nacc = lib().dm_mh_chain(
-            C.byref(self.c), C.byref(chain), C.c_int32(n_steps), C.c_uint64(seed),
+            C.byref(self.c), C.byref(chain), C.c_int32(n_steps), C.c_uint64(seed), C.c_int(self.lanes),
             _f(z) if z is not None else None, _f(e) if e is not None else None, C.c_int(mode), C.c_int(thin),
             C.c_int(capacity), _d(samples['x']) if mode else None, _d(samples['loglkl']) if mode else None,
             samples['mult'].ctypes.data_as(_ip) if mode else None,

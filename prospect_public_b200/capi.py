@@ -13,7 +13,7 @@ LIB_PATH = os.environ.get('PB200_LIB') or os.path.join(_PKG, '_lib', 'libpb200.s
 ACTIVE, CONVERGED, FAILED = 0, 1, 2
 STEP_EXPONENTIAL, STEP_ADAPTIVE_FIXED, STEP_ADAPTIVE_SECANT = 0, 1, 2
 RECORD_NONE, RECORD_ACCEPTED, RECORD_THINNED = 0, 1, 2
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 _vp = C.c_void_p
 
@@ -21,7 +21,7 @@ _vp = C.c_void_p
 class Problem(C.Structure):
     _fields_ = [('d', C.c_int32), ('n', C.c_int32), ('npad', C.c_int32), ('n_points', C.c_int32),
                 ('saa', _vp), ('sab', _vp), ('mu', _vp), ('lo', _vp), ('hi', _vp), ('f', _vp), ('c0', _vp),
-                ('lt_t', _vp), ('lam', _vp), ('g_t', _vp), ('h', _vp)]
+                ('lt_t', _vp), ('lam', _vp), ('lt_norm', _vp), ('g_t', _vp), ('h', _vp)]
 
 
 class Chains(C.Structure):
@@ -38,7 +38,7 @@ class Schedule(C.Structure):
 
 
 class Records(C.Structure):
-    _fields_ = [('max_iterations', C.c_int32), ('best_loglkl', _vp), ('last_loglkl', _vp), ('temperature', _vp),
+    _fields_ = [('max_iterations', C.c_int32), ('iter_stride', C.c_int64), ('best_loglkl', _vp), ('last_loglkl', _vp), ('temperature', _vp),
                 ('step_size', _vp), ('accepted', _vp), ('best_x', _vp), ('last_x', _vp)]
 
 
@@ -54,12 +54,13 @@ SIGNATURES = {
     'pb200_device_info': (C.c_int, [C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'pb200_loglkl_batch': (C.c_int, [C.POINTER(Problem), _vp, _vp, C.c_int32, _vp, _vp, _vp]),
     'pb200_anneal_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule), C.POINTER(Records),
-                                   C.c_int32, C.c_uint64, _vp]),
+                                   C.c_int32, C.c_uint64, C.c_int32, _vp]),
     'pb200_mh_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_int32, C.c_uint64, C.POINTER(Samples),
-                               _vp, _vp]),
+                               _vp, C.c_int32, _vp]),
+    'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),
     'pb200_schedule_update': (C.c_int, [C.POINTER(Chains), C.POINTER(Schedule), _vp, _vp, _vp]),
-    'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp,
-                                       _vp, _vp]),
+    'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                       _vp, _vp, _vp, _vp, _vp, _vp]),
     'pb200_weighted_moments': (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
     'pb200_rng_variates': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     'pb200_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),

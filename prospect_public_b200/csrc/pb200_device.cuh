@@ -1,10 +1,11 @@
 // pb200_device.cuh -- device building blocks shared by the sampler kernels (sm_100a).
 //
-// Mapping: ONE WARP PER CHAIN.  Lane l owns coordinates l, l+32, ... (CPL = npad/32 per lane).
-// A chain is strictly sequential in steps, so the parallelism inside a step is what fills the SM:
-// the n normals, the O(n) whitened quadratic form and (on accept) the n x n proposal matvec are
-// spread over the 32 lanes and reduced with xor-shuffles.  The accept decision is warp-uniform,
-// so the expensive matvec only runs for steps whose likelihood test passed (no divergence).
+// Mapping: a GROUP of LPC lanes (32, 16 or 8) per chain, G = 32/LPC chains per warp.  Lane l of a group
+// owns coordinates l, l+LPC, ... (CPL per lane, npad = LPC*CPL).  A chain is strictly sequential in steps,
+// so the parallelism inside a step is what fills the SM: the n normals and the O(n) whitened quadratic
+// form are spread over the group's lanes and reduced with xor-shuffles that never leave the group.
+// Small groups make every warp instruction serve several chains (fewer instructions per chain-step);
+// large groups give more warps for a small batch.  pb200_choose_lanes picks LPC from the batch size.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -61,37 +62,52 @@ __device__ __forceinline__ float exp_variate(uint32_t w) {
     return -0.6931471805599453f * __log2f(u01(w));
 }
 
-__device__ __forceinline__ float warp_sum(float v) {
+// Reductions over the LPC lanes of a group (xor distances < LPC stay inside the group).
+template <int LPC>
+__device__ __forceinline__ float group_sum(float v) {
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, m));
+    for (int m = LPC / 2; m >= 1; m >>= 1) v = __fadd_rn(v, __shfl_xor_sync(kFull, v, m));
     return v;
 }
-__device__ __forceinline__ double warp_sum(double v) {
+template <int LPC>
+__device__ __forceinline__ double group_sum(double v) {
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, m));
+    for (int m = LPC / 2; m >= 1; m >>= 1) v = __dadd_rn(v, __shfl_xor_sync(kFull, v, m));
     return v;
+}
+template <int LPC>
+__device__ __forceinline__ double group_min(double v) {
+#pragma unroll
+    for (int m = LPC / 2; m >= 1; m >>= 1) v = fmin(v, __shfl_xor_sync(kFull, v, m));
+    return v;
+}
+template <int LPC>
+__device__ __forceinline__ bool group_any(bool pred, int gi) {
+    const unsigned b = __ballot_sync(kFull, pred);
+    if (LPC == 32) return b != 0u;
+    return ((b >> (gi * LPC)) & ((1u << (LPC & 31)) - 1u)) != 0u;
 }
 
 // Variates of the 4 steps of Philox block `blk` for this lane's CPL coordinates.
-//   z[r][k]: N(0,1) for coordinate lane+32r at step 4*blk+k (0 for pads);  e[k]: Exp(1) accept variate.
+//   z[r][k]: N(0,1) for coordinate gl+LPC*r at step 4*blk+k (0 for pads);  e[k]: Exp(1) accept variate.
 // When n < npad the spare coordinate n carries the accept slot, otherwise every lane makes one
 // extra (identical) call -- both give the same numbers.
-template <int CPL>
+template <int LPC, int CPL>
 __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t blk, int n,
-                                           int lane, float (&z)[CPL][4], float (&e)[4]) {
-    constexpr int NPAD = 32 * CPL;
-    const int acc_r = n >> 5, acc_lane = n & 31;
+                                           int gl, float (&z)[CPL][4], float (&e)[4]) {
+    constexpr int NPAD = LPC * CPL;
+    const int acc_r = n / LPC, acc_lane = n % LPC;
     uint32_t w[4];
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
-        const int coord = lane + 32 * r;
+        const int coord = gl + LPC * r;
         philox4x32_10(blk, coord == n ? kAcceptSlot : (uint32_t)coord, chain_id, 0u, k0, k1, w);
         box_muller(w[0], w[1], z[r][0], z[r][1]);
         box_muller(w[2], w[3], z[r][2], z[r][3]);
         if (coord >= n) { z[r][0] = z[r][1] = z[r][2] = z[r][3] = 0.0f; }
         if (r == acc_r) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = __shfl_sync(kFull, exp_variate(w[k]), acc_lane);
+            for (int k = 0; k < 4; ++k) e[k] = __shfl_sync(kFull, exp_variate(w[k]), acc_lane, LPC);
         }
     }
     if (n >= NPAD) {
@@ -103,30 +119,30 @@ __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t ch
 
 // ----------------------------------------------------------------------------------------------
 // Exact FP64 evaluation at a position: loglkl = sum_i q_i (1/2 (S_aa q)_i + f s_ab_i) + c0 and,
-// optionally, the whitened gradient gt = G q + h.  `qs` is this warp's [npad] double staging row.
+// optionally, the whitened gradient gt = G q + h.  `qs` is this group's [npad] double staging row.
 // ----------------------------------------------------------------------------------------------
-template <int CPL, bool WITH_GRAD>
-__device__ __forceinline__ double exact_eval(const pb200_problem& p, int pt, const double (&x)[CPL], int lane,
+template <int LPC, int CPL, bool WITH_GRAD>
+__device__ __forceinline__ double exact_eval(const pb200_problem& p, int pt, const double (&x)[CPL], int gl,
                                              double* qs, double (&gt)[CPL]) {
-    constexpr int NPAD = 32 * CPL;
+    constexpr int NPAD = LPC * CPL;
     double q[CPL], v[CPL], g[CPL];
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
-        const int c = lane + 32 * r;
+        const int c = gl + LPC * r;
         q[r] = x[r] - __ldg(p.mu + c);
         qs[c] = q[r];
         v[r] = 0.0;
         g[r] = 0.0;
     }
     __syncwarp();
-    const double* __restrict__ saa = p.saa + lane;
-    const double* __restrict__ gtm = p.g_t + (size_t)pt * NPAD * NPAD + lane;
+    const double* __restrict__ saa = p.saa + gl;
+    const double* __restrict__ gtm = p.g_t + (size_t)pt * NPAD * NPAD + gl;
     for (int j = 0; j < p.n; ++j) {
         const double qj = qs[j];
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
-            v[r] = fma(__ldg(saa + j * NPAD + 32 * r), qj, v[r]);
-            if (WITH_GRAD) g[r] = fma(__ldg(gtm + j * NPAD + 32 * r), qj, g[r]);
+            v[r] = fma(__ldg(saa + j * NPAD + LPC * r), qj, v[r]);
+            if (WITH_GRAD) g[r] = fma(__ldg(gtm + j * NPAD + LPC * r), qj, g[r]);
         }
     }
     __syncwarp();
@@ -134,11 +150,61 @@ __device__ __forceinline__ double exact_eval(const pb200_problem& p, int pt, con
     double part = 0.0;
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
-        const int c = lane + 32 * r;
+        const int c = gl + LPC * r;
         part = fma(q[r], fma(0.5, v[r], f * __ldg(p.sab + c)), part);
         if (WITH_GRAD) gt[r] = g[r] + __ldg(p.h + (size_t)pt * NPAD + c);
     }
-    return warp_sum(part) + __ldg(p.c0 + pt);
+    return group_sum<LPC>(part) + __ldg(p.c0 + pt);
+}
+
+// x_out = base + Lt * w for this group: w staged through `ws` (float [npad]), FP32 matvec with four
+// interleaved partial sums, one FP64 add.  Used whenever a position must be materialised (see run_steps).
+template <int LPC, int CPL>
+__device__ __forceinline__ void materialise(const float* __restrict__ lt_pt, int gl, const double (&base)[CPL],
+                                            const float (&w)[CPL], float* ws, double (&x_out)[CPL]) {
+    constexpr int NPAD = LPC * CPL;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) ws[gl + LPC * r] = w[r];
+    __syncwarp();
+    const float4* __restrict__ w4 = reinterpret_cast<const float4*>(ws);
+    float a[CPL][4];
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) a[r][0] = a[r][1] = a[r][2] = a[r][3] = 0.0f;
+    const float* __restrict__ col = lt_pt + gl;
+#pragma unroll 4
+    for (int j = 0; j < NPAD / 4; ++j) {
+        const float4 v = w4[j];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            a[r][0] = __fmaf_rn(__ldg(col + (4 * j + 0) * NPAD + LPC * r), v.x, a[r][0]);
+            a[r][1] = __fmaf_rn(__ldg(col + (4 * j + 1) * NPAD + LPC * r), v.y, a[r][1]);
+            a[r][2] = __fmaf_rn(__ldg(col + (4 * j + 2) * NPAD + LPC * r), v.z, a[r][2]);
+            a[r][3] = __fmaf_rn(__ldg(col + (4 * j + 3) * NPAD + LPC * r), v.w, a[r][3]);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < CPL; ++r)
+        x_out[r] = __dadd_rn(base[r], (double)__fadd_rn(__fadd_rn(a[r][0], a[r][1]), __fadd_rn(a[r][2], a[r][3])));
+}
+
+// Squared whitened radius inside which base + Lt*w provably stays in the prior box:
+//   |x_i - base_i| <= lt_norm_i * |w|  (Cauchy-Schwarz)  =>  safe while |w| < min_i dist_i / lt_norm_i.
+// 0.999 absorbs FP32 rounding of |w|^2 and of the later materialisation.  +inf without a box.
+template <int LPC, int CPL>
+__device__ __forceinline__ float safe_radius2(const pb200_problem& p, int pt, int gl, const double (&base)[CPL]) {
+    constexpr int NPAD = LPC * CPL;
+    double m = INFINITY;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int c = gl + LPC * r;
+        const double nrm = (double)__ldg(p.lt_norm + (size_t)pt * NPAD + c);
+        const double dist = fmin(__ldg(p.hi + c) - base[r], base[r] - __ldg(p.lo + c));
+        if (nrm > 0.0) m = fmin(m, dist / nrm);
+    }
+    m = group_min<LPC>(m);
+    m = fmax(m, 0.0) * 0.999;
+    return (float)(m * m);
 }
 
 // ----------------------------------------------------------------------------------------------

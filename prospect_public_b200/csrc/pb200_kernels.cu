@@ -1,10 +1,10 @@
 // pb200_kernels.cu -- sm_100a kernels + the C ABI of include/pb200.h.
 //
 // Kernels (DESIGN.md has the roofline of each):
-//   anneal_kernel<CPL>        fused annealing iterations: Philox normals -> whitened quadratic form ->
+//   anneal_kernel<LPC,CPL>    fused annealing iterations: Philox normals -> whitened quadratic form ->
 //                             accept/reject at the chain temperature -> (on accept) proposal matvec, box
 //                             test, state update, running bestfit -> set_bestfit + next settings.
-//   mh_kernel<CPL, REC>       plain Metropolis-Hastings rounds with chain recording (jobtype mcmc).
+//   mh_kernel<LPC,CPL,REC>    plain Metropolis-Hastings rounds with chain recording (jobtype mcmc).
 //   loglkl_kernel<CPL>        FP64 chi^2 quadratic form + prior box for a batch of positions.
 //   schedule_kernel           stand-alone adaptive step-size bookkeeping.
 //   chain_min_kernel + point_reduce_kernel   min over iterations / first-min repetition / mean (warp shuffles).
@@ -13,16 +13,13 @@
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
 
-#ifndef PB200_LT_REGS
-#define PB200_LT_REGS 0      // 1: keep this lane's column of the proposal factor in registers (n <= 32).
-                             // 0 (measured faster on B200): read it through L1 on accept, 72 registers, 28 warps/SM
-#endif
 #ifndef PB200_MIN_CTAS
-#define PB200_MIN_CTAS 7
+#define PB200_MIN_CTAS 7     // npad = 32 kernels: <= 72 registers -> 7 CTAs (28 warps) per SM, measured best on B200
 #endif
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -39,7 +36,7 @@ static int check_cuda(cudaError_t e, const char* what) {
     return fail(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
-// Per-warp recording cursor of mh_kernel.
+// Per-group recording cursor of mh_kernel.
 struct RecCursor {
     double* x;        // this chain's [capacity][npad]
     double* ll;       // [capacity]
@@ -47,14 +44,14 @@ struct RecCursor {
     int32_t capacity, thin, count, cur_mult;
 };
 
-template <int CPL>
-__device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL], double ll, int32_t mult, int lane) {
-    constexpr int NPAD = 32 * CPL;
+template <int LPC, int CPL>
+__device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL], double ll, int32_t mult, int gl) {
+    constexpr int NPAD = LPC * CPL;
     if (rc.count < rc.capacity) {
         double* row = rc.x + (size_t)rc.count * NPAD;
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) row[lane + 32 * r] = x[r];
-        if (lane == 0) {
+        for (int r = 0; r < CPL; ++r) row[gl + LPC * r] = x[r];
+        if (gl == 0) {
             rc.ll[rc.count] = ll;
             rc.mult[rc.count] = mult;
         }
@@ -62,257 +59,277 @@ __device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL]
     rc.count += 1;   // count > capacity tells the host that rows were dropped
 }
 
+// Registers of one chain, spread over the LPC lanes of its group.
+//   position = xref + Lt * w   (w: whitened displacement accumulated since xref was last materialised)
+//   best     = bref + Lt * bw
+template <int CPL>
+struct ChainState {
+    double xref[CPL], gt[CPL], bref[CPL];
+    float w[CPL], bw[CPL], gf[CPL], hl[CPL];
+    double ll, best_ll;
+    float m2;             // squared whitened radius around xref that provably stays inside the prior box
+    int32_t nacc;
+};
+
 // ----------------------------------------------------------------------------------------------
-// MH steps [t_begin, t_end) of one chain (prospect/mcmc.py:163-190, batched and re-ordered):
-//   Delta   = step * sum_i z_i (gt_i + 1/2 step lam_i z_i)        O(n), FP32, every step
-//   accept  = Delta < T * e   and   x + step * Lt z inside the box  (matvec only if the first holds)
-// The reference draws the uniform even for out-of-box proposals and never evaluates the likelihood
-// there; "inside AND likelihood-accept" is the same predicate evaluated in the cheaper order.
+// One MH step of every chain of the warp (prospect/mcmc.py:163-190, batched and re-ordered):
+//   Delta  = step * sum_i z_i (gt_i + 1/2 step lam_i z_i)            O(n), FP32, every step
+//   accept = Delta < T * e  and  proposal inside the prior box
+// The reference draws the uniform even for out-of-box proposals and never evaluates the likelihood there;
+// "likelihood-accept AND inside" is the same predicate evaluated in the cheaper order.  The box test is
+// DEFERRED: a likelihood-accepted move only updates the whitened displacement w (O(n)); as long as
+// |w|^2 <= m2 the position provably lies inside the box (safe_radius2), otherwise the position is
+// materialised (n x n matvec), tested exactly and becomes the new reference point.
+// Predicates are per group; everything containing a shuffle or __syncwarp runs under warp-uniform control.
 // ----------------------------------------------------------------------------------------------
-// One MH step given this lane's normals zk[] and the accept variate ek.
-template <int CPL, bool LT_REGS, int REC>
-__device__ __forceinline__ void one_step(const float* __restrict__ lt_pt, int lane, uint32_t tk, float Tf, float sf,
-                                         const float (&zk)[CPL], float ek, const float (&ltrow)[LT_REGS ? 32 : 1],
-                                         const float (&hl)[CPL], float (&gf)[CPL], const double (&lo)[CPL],
-                                         const double (&hi)[CPL], double (&x)[CPL], double (&gt)[CPL], double& ll,
-                                         double& best_ll, double (&bx)[CPL], int32_t& nacc, float* zs, RecCursor& rc) {
-    constexpr int NPAD = 32 * CPL;
+template <int LPC, int CPL, int REC>
+__device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
+                                         bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
+                                         ChainState<CPL>& c, float* ws, RecCursor& rc) {
     float tt = 0.0f;
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) tt = __fmaf_rn(zk[r], __fmaf_rn(hl[r], zk[r], gf[r]), tt);
-    tt = warp_sum(tt);
+    for (int r = 0; r < CPL; ++r) tt = __fmaf_rn(zk[r], __fmaf_rn(c.hl[r], zk[r], c.gf[r]), tt);
+    tt = group_sum<LPC>(tt);
     const float delta = __fmul_rn(sf, tt);
-    bool accepted = false;
-    if (delta < __fmul_rn(Tf, ek)) {
-#pragma unroll
-        for (int r = 0; r < CPL; ++r) zs[lane + 32 * r] = zk[r];
-        __syncwarp();
-        double xn[CPL];
-        bool outside = false;
-        const float4* __restrict__ z4 = reinterpret_cast<const float4*>(zs);
+    const bool lik = live && (delta < __fmul_rn(Tf, ek));
+    bool acc = false;
+    if (__any_sync(kFull, lik)) {
+        float wt[CPL], rr = 0.0f;
 #pragma unroll
         for (int r = 0; r < CPL; ++r) {
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            if (LT_REGS) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const float4 v = z4[j];
-                    a0 = __fmaf_rn(ltrow[4 * j + 0], v.x, a0);
-                    a1 = __fmaf_rn(ltrow[4 * j + 1], v.y, a1);
-                    a2 = __fmaf_rn(ltrow[4 * j + 2], v.z, a2);
-                    a3 = __fmaf_rn(ltrow[4 * j + 3], v.w, a3);
-                }
-            } else {
-                const float* __restrict__ col = lt_pt + lane + 32 * r;
-#pragma unroll 8
-                for (int j = 0; j < NPAD / 4; ++j) {
-                    const float4 v = z4[j];
-                    a0 = __fmaf_rn(__ldg(col + (4 * j + 0) * NPAD), v.x, a0);
-                    a1 = __fmaf_rn(__ldg(col + (4 * j + 1) * NPAD), v.y, a1);
-                    a2 = __fmaf_rn(__ldg(col + (4 * j + 2) * NPAD), v.z, a2);
-                    a3 = __fmaf_rn(__ldg(col + (4 * j + 3) * NPAD), v.w, a3);
-                }
-            }
-            const float acc = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
-            xn[r] = __dadd_rn(x[r], (double)__fmul_rn(sf, acc));
-            outside = outside || (xn[r] < lo[r]) || (xn[r] > hi[r]);
+            wt[r] = __fmaf_rn(sf, zk[r], c.w[r]);
+            rr = __fmaf_rn(wt[r], wt[r], rr);
         }
-        __syncwarp();
-        if (!__any_sync(kFull, outside)) {
-            accepted = true;
+        rr = group_sum<LPC>(rr);
+        const bool exact = lik && (REC == PB200_RECORD_ACCEPTED || !(rr <= c.m2));
+        acc = lik;
+        if (__any_sync(kFull, exact)) {
+            double xt[CPL];
+            materialise<LPC, CPL>(lt_pt, gl, c.xref, wt, ws, xt);
+            bool outside = false;
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
-                x[r] = xn[r];
-                gt[r] = __dadd_rn(gt[r], (double)__fmul_rn(2.0f, __fmul_rn(hl[r], zk[r])));
-                gf[r] = (float)gt[r];
+                const int col = gl + LPC * r;
+                outside = outside || (xt[r] < __ldg(p.lo + col)) || (xt[r] > __ldg(p.hi + col));
             }
-            ll = __dadd_rn(ll, (double)delta);
-            nacc += 1;
-            if (ll < best_ll) {
-                best_ll = ll;
+            outside = group_any<LPC>(outside, gi);
+            const bool reref = exact && !outside;
+            acc = lik && !(exact && outside);
+            if (reref) {
 #pragma unroll
-                for (int r = 0; r < CPL; ++r) bx[r] = x[r];
+                for (int r = 0; r < CPL; ++r) { c.xref[r] = xt[r]; wt[r] = 0.0f; }
+            }
+            const float m2n = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
+            if (reref) c.m2 = m2n;
+        }
+        if (acc) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                c.w[r] = wt[r];
+                c.gt[r] = __dadd_rn(c.gt[r], (double)__fmul_rn(2.0f, __fmul_rn(c.hl[r], zk[r])));
+                c.gf[r] = (float)c.gt[r];
+            }
+            c.ll = __dadd_rn(c.ll, (double)delta);
+            c.nacc += 1;
+            if (c.ll < c.best_ll) {
+                c.best_ll = c.ll;
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) { c.bw[r] = c.w[r]; c.bref[r] = c.xref[r]; }
             }
         }
     }
     if (REC == PB200_RECORD_ACCEPTED) {
-        if (accepted) {
-            if (lane == 0 && rc.count - 1 < rc.capacity) rc.mult[rc.count - 1] = rc.cur_mult;
-            rc.cur_mult = 1;
-            record_row<CPL>(rc, x, ll, 1, lane);
-        } else {
-            rc.cur_mult += 1;
+        if (live) {
+            if (acc) {       // exact path always re-references: the new point is xref itself
+                if (gl == 0 && rc.count - 1 < rc.capacity) rc.mult[rc.count - 1] = rc.cur_mult;
+                rc.cur_mult = 1;
+                record_row<LPC, CPL>(rc, c.xref, c.ll, 1, gl);
+            } else {
+                rc.cur_mult += 1;
+            }
         }
     } else if (REC == PB200_RECORD_THINNED) {
-        if ((tk + 1) % (uint32_t)rc.thin == 0) record_row<CPL>(rc, x, ll, 1, lane);
+        const bool now = live && ((tk + 1) % (uint32_t)rc.thin == 0);
+        if (__any_sync(kFull, now)) {
+            double xn[CPL];
+            materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, xn);
+            if (now) record_row<LPC, CPL>(rc, xn, c.ll, 1, gl);
+        }
     }
 }
 
-// ----------------------------------------------------------------------------------------------
-// MH steps [t_begin, t_end) of one chain (prospect/mcmc.py:163-190, batched and re-ordered):
-//   Delta   = step * sum_i z_i (gt_i + 1/2 step lam_i z_i)        O(n), FP32, every step
-//   accept  = Delta < T * e   and   x + step * Lt z inside the box  (matvec only if the first holds)
-// The reference draws the uniform even for out-of-box proposals and never evaluates the likelihood
-// there; "inside AND likelihood-accept" is the same predicate evaluated in the cheaper order.
-// Philox blocks cover 4 consecutive steps: whole blocks run a branch-free unrolled body, the ragged
-// head / tail of the range goes through one generic copy.
-// ----------------------------------------------------------------------------------------------
-template <int CPL, bool LT_REGS, int REC>
-__device__ __forceinline__ void run_steps(const pb200_problem& p, const float* __restrict__ lt_pt, int lane,
-                                          uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
-                                          uint32_t t_end, float Tf, float sf, const float (&ltrow)[LT_REGS ? 32 : 1],
-                                          const float (&lam)[CPL], const double (&lo)[CPL], const double (&hi)[CPL],
-                                          double (&x)[CPL], double (&gt)[CPL], double& ll, double& best_ll,
-                                          double (&bx)[CPL], int32_t& nacc, float* zs, RecCursor& rc) {
-    float gf[CPL], hl[CPL];
+// MH steps [t_begin, t_begin + n_steps) of the warp's chains.  Philox blocks cover 4 consecutive steps: when
+// all chains of the warp share the block alignment (always, unless the caller mixed chains with different
+// histories) whole blocks run a branch-free unrolled body and the ragged head / tail one generic copy;
+// otherwise every step redraws its block (correct, 4x the RNG work).
+template <int LPC, int CPL, int REC>
+__device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
+                                          bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
+                                          uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
+                                          ChainState<CPL>& c, float* ws, RecCursor& rc) {
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
-        gf[r] = (float)gt[r];
-        hl[r] = __fmul_rn(half_s, lam[r]);
+        c.gf[r] = (float)c.gt[r];
+        c.hl[r] = __fmul_rn(half_s, lam[r]);
     }
-    uint32_t t = t_begin;
-    while (t < t_end) {
-        const uint32_t blk = t >> 2, base = blk << 2;
-        float z[CPL][4], e[4];
-        draw_block<CPL>(k0, k1, chain_id, blk, p.n, lane, z, e);
-        if (t == base && t_end - base >= 4u) {
+    const uint32_t lead = __shfl_sync(kFull, t_begin, 0);
+    const bool aligned = __all_sync(kFull, (t_begin & 3u) == (lead & 3u));
+    float z[CPL][4], e[4], zk[CPL];
+    if (aligned) {
+        uint32_t i = 0;                         // steps done (warp-uniform); this group's step index is t_begin + i
+        while (i < n_steps) {
+            const uint32_t t = t_begin + i, off = (lead + i) & 3u;
+            draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+            if (off == 0u && n_steps - i >= 4u) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                float zk[CPL];
+                for (int k = 0; k < 4; ++k) {
 #pragma unroll
-                for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
-                one_step<CPL, LT_REGS, REC>(lt_pt, lane, base + k, Tf, sf, zk, e[k], ltrow, hl, gf, lo, hi, x, gt, ll,
-                                            best_ll, bx, nacc, zs, rc);
-            }
-            t = base + 4;
-        } else {
-            const uint32_t stop = min(base + 4u, t_end);
+                    for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
+                    one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t + k, Tf, sf, zk, e[k], c, ws, rc);
+                }
+                i += 4;
+            } else {
+                const uint32_t cnt = min(4u - off, n_steps - i);
 #pragma unroll 1
-            for (uint32_t tk = t; tk < stop; ++tk) {
-                const int k = (int)(tk - base);
-                float zk[CPL];
+                for (uint32_t q = 0; q < cnt; ++q) {
+                    const uint32_t k = off + q;
 #pragma unroll
-                for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
-                const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
-                one_step<CPL, LT_REGS, REC>(lt_pt, lane, tk, Tf, sf, zk, ek, ltrow, hl, gf, lo, hi, x, gt, ll, best_ll,
-                                            bx, nacc, zs, rc);
+                    for (int r = 0; r < CPL; ++r)
+                        zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
+                    const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
+                    one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t + q, Tf, sf, zk, ek, c, ws, rc);
+                }
+                i += cnt;
             }
-            t = stop;
+        }
+    } else {
+#pragma unroll 1
+        for (uint32_t i = 0; i < n_steps; ++i) {
+            const uint32_t t = t_begin + i, k = t & 3u;
+            draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
+            const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
+            one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t, Tf, sf, zk, ek, c, ws, rc);
         }
     }
 }
 
-template <int CPL>
-struct LaneConst {
-    float lam[CPL];
-    double lo[CPL], hi[CPL];
+// Make x the new reference point of the chain: exact loglkl + whitened gradient, w = 0, fresh safe radius.
+template <int LPC, int CPL>
+__device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, const double (&x)[CPL],
+                                       ChainState<CPL>& c, double* qs) {
+    c.ll = exact_eval<LPC, CPL, true>(p, pt, x, gl, qs, c.gt);
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) { c.xref[r] = x[r]; c.w[r] = 0.0f; }
+    c.m2 = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
+}
+
+template <int LPC, int CPL>
+struct Geometry {
+    static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
+    static constexpr int kMinCtas = NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? 5 : 4));
 };
 
-template <int CPL, bool LT_REGS>
-__device__ __forceinline__ void load_lane_const(const pb200_problem& p, int pt, int lane, LaneConst<CPL>& lc,
-                                                float (&ltrow)[LT_REGS ? 32 : 1]) {
-    constexpr int NPAD = 32 * CPL;
+// ----------------------------------------------------------------------------------------------
+// Fused annealing kernel: n_iter iterations x S steps per launch, one lane group per chain.
+// ----------------------------------------------------------------------------------------------
+template <int LPC, int CPL>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
+anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
+              uint32_t k1) {
+    constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane / LPC, gl = lane % LPC;
+    const int slot = (blockIdx.x * kWarpsPerCta + wib) * G + gi;
+    if ((blockIdx.x * kWarpsPerCta + wib) * G >= ch.n_chains) return;         // whole warp idle
+    const bool alive = slot < ch.n_chains;
+    const int chain = alive ? slot : ch.n_chains - 1;
+    SchedState st;
+    st.status = ch.status[chain];
+    st.temperature = ch.temperature[chain];
+    st.step_size = ch.step_size[chain];
+    st.current_best = ch.current_best[chain];
+    st.prev_mult = ch.secant_prev_mult[chain];
+    st.cur_mult = ch.secant_cur_mult[chain];
+    st.prev_ar = ch.secant_prev_ar[chain];
+    st.stage = ch.secant_stage[chain];
+    st.iteration = ch.iteration[chain];
+    bool live = alive && st.status == PB200_ACTIVE;
+    const bool was_live = live;
+    const int pt = ch.point[chain];
+    const uint32_t chain_id = ch.chain_id[chain];
+    uint32_t t = ch.steps_done[chain];
+    const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
+    double* qs = stage[wib][gi];
+    float* ws = reinterpret_cast<float*>(qs);
+
+    float lam[CPL];
+    double x[CPL], bx[CPL];
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
-        const int c = lane + 32 * r;
-        lc.lam[r] = __ldg(p.lam + (size_t)pt * NPAD + c);
-        lc.lo[r] = __ldg(p.lo + c);
-        lc.hi[r] = __ldg(p.hi + c);
+        lam[r] = __ldg(p.lam + (size_t)pt * NPAD + gl + LPC * r);
+        x[r] = ch.x[(size_t)chain * NPAD + gl + LPC * r];
     }
-    if (LT_REGS) {
-        const float* lt = p.lt_t + (size_t)pt * NPAD * NPAD + lane;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) ltrow[j] = __ldg(lt + j * NPAD);
-    }
-}
-
-// ----------------------------------------------------------------------------------------------
-// Fused annealing kernel: n_iter iterations x S steps per launch, one warp per chain.
-// ----------------------------------------------------------------------------------------------
-template <int CPL>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (CPL == 1) ? PB200_MIN_CTAS : 1)
-anneal_kernel(pb200_problem p, pb200_chains c, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1) {
-    constexpr int NPAD = 32 * CPL;
-    constexpr bool LT_REGS = (CPL == 1) && PB200_LT_REGS;
-    __shared__ __align__(16) double stage[kWarpsPerCta][NPAD];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int chain = blockIdx.x * kWarpsPerCta + wib;
-    if (chain >= c.n_chains) return;
-    SchedState st;
-    st.status = c.status[chain];
-    if (st.status != PB200_ACTIVE) return;
-    st.temperature = c.temperature[chain];
-    st.step_size = c.step_size[chain];
-    st.current_best = c.current_best[chain];
-    st.prev_mult = c.secant_prev_mult[chain];
-    st.cur_mult = c.secant_cur_mult[chain];
-    st.prev_ar = c.secant_prev_ar[chain];
-    st.stage = c.secant_stage[chain];
-    st.iteration = c.iteration[chain];
-    const int pt = c.point[chain];
-    const uint32_t chain_id = c.chain_id[chain];
-    uint32_t t = c.steps_done[chain];
-
-    LaneConst<CPL> lc;
-    float ltrow[LT_REGS ? 32 : 1];
-    load_lane_const<CPL, LT_REGS>(p, pt, lane, lc, ltrow);
-    const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
-
-    double x[CPL], gt[CPL], bx[CPL];
-#pragma unroll
-    for (int r = 0; r < CPL; ++r) x[r] = c.x[(size_t)chain * NPAD + lane + 32 * r];
-    double* qs = stage[wib];
-    float* zs = reinterpret_cast<float*>(stage[wib]);
-    double ll = exact_eval<CPL, true>(p, pt, x, lane, qs, gt);   // loglkl of the start point (optimiser.py:55)
+    ChainState<CPL> c;
+    anchor<LPC, CPL>(p, pt, gl, x, c, qs);                 // loglkl of the start point (optimiser.py:55)
     RecCursor rc{};
 
-    for (int it = 0; it < n_iter && st.status == PB200_ACTIVE; ++it) {
-        double best_ll = ll;
-        int32_t nacc = 0;
+    for (int it = 0; it < n_iter && __any_sync(kFull, live); ++it) {
+        c.best_ll = c.ll;
+        c.nacc = 0;
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) bx[r] = x[r];
-        run_steps<CPL, LT_REGS, PB200_RECORD_NONE>(p, lt_pt, lane, k0, k1, chain_id, t, t + s.steps_per_iteration,
-                                                   (float)st.temperature, (float)st.step_size, ltrow, lc.lam, lc.lo,
-                                                   lc.hi, x, gt, ll, best_ll, bx, nacc, zs, rc);
-        t += s.steps_per_iteration;
-        // set_bestfit: the reported chi^2 is re-evaluated in FP64 at the reported position
+        for (int r = 0; r < CPL; ++r) { c.bref[r] = c.xref[r]; c.bw[r] = 0.0f; }
+        run_steps<LPC, CPL, PB200_RECORD_NONE>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
+                                               (uint32_t)s.steps_per_iteration, (float)st.temperature,
+                                               (float)st.step_size, lam, c, ws, rc);
+        // set_bestfit: positions are materialised, the reported chi^2 is re-evaluated in FP64 at them
+        materialise<LPC, CPL>(lt_pt, gl, c.bref, c.bw, ws, bx);
+        materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
         double unused[CPL];
-        const double best_exact = exact_eval<CPL, false>(p, pt, bx, lane, qs, unused);
-        ll = exact_eval<CPL, true>(p, pt, x, lane, qs, gt);       // re-anchor the incremental state
-        const int row = st.iteration;
-        if (row < rec.max_iterations) {
-            const size_t o = (size_t)row * c.n_chains + chain;
-            if (lane == 0) {
-                rec.best_loglkl[o] = best_exact;
-                rec.last_loglkl[o] = ll;
-                rec.temperature[o] = st.temperature;
-                rec.step_size[o] = st.step_size;
-                rec.accepted[o] = nacc;
-            }
+        const double best_exact = exact_eval<LPC, CPL, false>(p, pt, bx, gl, qs, unused);
+        const int32_t nacc = c.nacc;
+        anchor<LPC, CPL>(p, pt, gl, x, c, qs);             // re-anchor the incremental state at x
+        if (live) {
+            t += s.steps_per_iteration;
+            const int row = st.iteration;
+            if (row < rec.max_iterations) {
+                const size_t o = (size_t)row * rec.iter_stride;
+                if (gl == 0) {
+                    rec.best_loglkl[o + chain] = best_exact;
+                    rec.last_loglkl[o + chain] = c.ll;
+                    rec.temperature[o + chain] = st.temperature;
+                    rec.step_size[o + chain] = st.step_size;
+                    rec.accepted[2 * o + chain] = nacc;
+                }
 #pragma unroll
-            for (int r = 0; r < CPL; ++r) {
-                if (rec.best_x) rec.best_x[o * NPAD + lane + 32 * r] = bx[r];
-                if (rec.last_x) rec.last_x[o * NPAD + lane + 32 * r] = x[r];
+                for (int r = 0; r < CPL; ++r) {
+                    if (rec.best_x) rec.best_x[o + (size_t)chain * NPAD + gl + LPC * r] = bx[r];
+                    if (rec.last_x) rec.last_x[o + (size_t)chain * NPAD + gl + LPC * r] = x[r];
+                }
             }
+            schedule_next(s, st, nacc, best_exact);
+            live = st.status == PB200_ACTIVE;
         }
-        schedule_next(s, st, nacc, best_exact);
     }
+    if (was_live) {
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) c.x[(size_t)chain * NPAD + lane + 32 * r] = x[r];
-    if (lane == 0) {
-        c.loglkl[chain] = ll;
-        c.temperature[chain] = st.temperature;
-        c.step_size[chain] = st.step_size;
-        c.current_best[chain] = st.current_best;
-        c.secant_prev_mult[chain] = st.prev_mult;
-        c.secant_cur_mult[chain] = st.cur_mult;
-        c.secant_prev_ar[chain] = st.prev_ar;
-        c.secant_stage[chain] = st.stage;
-        c.iteration[chain] = st.iteration;
-        c.status[chain] = st.status;
-        c.steps_done[chain] = t;
+        for (int r = 0; r < CPL; ++r) ch.x[(size_t)chain * NPAD + gl + LPC * r] = x[r];
+        if (gl == 0) {
+            ch.loglkl[chain] = c.ll;
+            ch.temperature[chain] = st.temperature;
+            ch.step_size[chain] = st.step_size;
+            ch.current_best[chain] = st.current_best;
+            ch.secant_prev_mult[chain] = st.prev_mult;
+            ch.secant_cur_mult[chain] = st.cur_mult;
+            ch.secant_prev_ar[chain] = st.prev_ar;
+            ch.secant_stage[chain] = st.stage;
+            ch.iteration[chain] = st.iteration;
+            ch.status[chain] = st.status;
+            ch.steps_done[chain] = t;
+        }
     }
 }
 
@@ -322,32 +339,38 @@ anneal_kernel(pb200_problem p, pb200_chains c, pb200_schedule s, pb200_records r
 // ----------------------------------------------------------------------------------------------
 constexpr uint32_t kResync = 256;
 
-template <int CPL, int REC>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, (CPL == 1) ? PB200_MIN_CTAS : 1)
-mh_kernel(pb200_problem p, pb200_chains c, int n_steps, uint32_t k0, uint32_t k1, pb200_samples smp,
+template <int LPC, int CPL, int REC>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
+mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k1, pb200_samples smp,
           int32_t* accepted_out) {
-    constexpr int NPAD = 32 * CPL;
-    constexpr bool LT_REGS = (CPL == 1) && PB200_LT_REGS;
-    __shared__ __align__(16) double stage[kWarpsPerCta][NPAD];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int chain = blockIdx.x * kWarpsPerCta + wib;
-    if (chain >= c.n_chains) return;
-    const int pt = c.point[chain];
-    const uint32_t chain_id = c.chain_id[chain];
-    uint32_t t = c.steps_done[chain];
-    const float Tf = (float)c.temperature[chain], sf = (float)c.step_size[chain];
-
-    LaneConst<CPL> lc;
-    float ltrow[LT_REGS ? 32 : 1];
-    load_lane_const<CPL, LT_REGS>(p, pt, lane, lc, ltrow);
+    constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane / LPC, gl = lane % LPC;
+    const int slot = (blockIdx.x * kWarpsPerCta + wib) * G + gi;
+    if ((blockIdx.x * kWarpsPerCta + wib) * G >= ch.n_chains) return;
+    const bool live = slot < ch.n_chains;
+    const int chain = live ? slot : ch.n_chains - 1;
+    const int pt = ch.point[chain];
+    const uint32_t chain_id = ch.chain_id[chain];
+    uint32_t t = ch.steps_done[chain];
+    const float Tf = (float)ch.temperature[chain], sf = (float)ch.step_size[chain];
     const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
+    double* qs = stage[wib][gi];
+    float* ws = reinterpret_cast<float*>(qs);
 
-    double x[CPL], gt[CPL], bx[CPL];
+    float lam[CPL];
+    double x[CPL];
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) x[r] = c.x[(size_t)chain * NPAD + lane + 32 * r];
-    double* qs = stage[wib];
-    float* zs = reinterpret_cast<float*>(stage[wib]);
-    double ll = exact_eval<CPL, true>(p, pt, x, lane, qs, gt);
+    for (int r = 0; r < CPL; ++r) {
+        lam[r] = __ldg(p.lam + (size_t)pt * NPAD + gl + LPC * r);
+        x[r] = ch.x[(size_t)chain * NPAD + gl + LPC * r];
+    }
+    ChainState<CPL> c;
+    anchor<LPC, CPL>(p, pt, gl, x, c, qs);
+    c.best_ll = c.ll;
+    c.nacc = 0;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) { c.bref[r] = c.xref[r]; c.bw[r] = 0.0f; }
 
     RecCursor rc{};
     if (REC != PB200_RECORD_NONE) {
@@ -357,35 +380,34 @@ mh_kernel(pb200_problem p, pb200_chains c, int n_steps, uint32_t k0, uint32_t k1
         rc.ll = smp.loglkl + (size_t)chain * smp.capacity;
         rc.mult = smp.mult + (size_t)chain * smp.capacity;
         rc.count = smp.count[chain];
-        if (REC == PB200_RECORD_ACCEPTED) {
+        if (REC == PB200_RECORD_ACCEPTED && live) {
             if (rc.count == 0) {
-                record_row<CPL>(rc, x, ll, 1, lane);   // Chain([1], [loglkl(x0)], x0), mcmc.py:125
+                record_row<LPC, CPL>(rc, x, c.ll, 1, gl);   // Chain([1], [loglkl(x0)], x0), mcmc.py:125
                 rc.cur_mult = 1;
             } else {
                 rc.cur_mult = rc.count - 1 < rc.capacity ? rc.mult[rc.count - 1] : 1;
             }
         }
     }
-    double best_ll = ll;
-    int32_t nacc = 0;
-    const uint32_t t_end = t + (uint32_t)n_steps;
-    while (t < t_end) {
-        const uint32_t t_next = min(t_end, t + kResync);
-        run_steps<CPL, LT_REGS, REC>(p, lt_pt, lane, k0, k1, chain_id, t, t_next, Tf, sf, ltrow, lc.lam, lc.lo, lc.hi,
-                                     x, gt, ll, best_ll, bx, nacc, zs, rc);
-        t = t_next;
-        ll = exact_eval<CPL, true>(p, pt, x, lane, qs, gt);
+    uint32_t done = 0;
+    while (done < (uint32_t)n_steps) {
+        const uint32_t chunk = min((uint32_t)n_steps - done, kResync);
+        run_steps<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc);
+        done += chunk;
+        materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
+        anchor<LPC, CPL>(p, pt, gl, x, c, qs);
     }
-    if (REC != PB200_RECORD_NONE && lane == 0) {
+    if (!live) return;
+    if (REC != PB200_RECORD_NONE && gl == 0) {
         if (REC == PB200_RECORD_ACCEPTED && rc.count - 1 < rc.capacity) rc.mult[rc.count - 1] = rc.cur_mult;
         smp.count[chain] = rc.count;
     }
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) c.x[(size_t)chain * NPAD + lane + 32 * r] = x[r];
-    if (lane == 0) {
-        c.loglkl[chain] = ll;
-        c.steps_done[chain] = t;
-        if (accepted_out) accepted_out[chain] = nacc;
+    for (int r = 0; r < CPL; ++r) ch.x[(size_t)chain * NPAD + gl + LPC * r] = x[r];
+    if (gl == 0) {
+        ch.loglkl[chain] = c.ll;
+        ch.steps_done[chain] = t + (uint32_t)n_steps;
+        if (accepted_out) accepted_out[chain] = c.nacc;
     }
 }
 
@@ -408,7 +430,7 @@ loglkl_kernel(pb200_problem p, const double* __restrict__ xs, const int32_t* __r
             x[r] = xs[(size_t)row * NPAD + c];
             out_of_box = out_of_box || (x[r] < __ldg(p.lo + c)) || (x[r] > __ldg(p.hi + c));
         }
-        const double ll = exact_eval<CPL, false>(p, pt, x, lane, stage[wib], unused);
+        const double ll = exact_eval<32, CPL, false>(p, pt, x, lane, stage[wib], unused);
         const bool any_out = __any_sync(kFull, out_of_box);
         if (lane == 0) {
             out[row] = ll;
@@ -439,16 +461,16 @@ __global__ void schedule_kernel(pb200_chains c, pb200_schedule s, const int32_t*
 //   chain_min_kernel   one thread per chain: first minimum over the iterations that ran;
 //   point_reduce_kernel one CTA per profile point: first-minimum repetition and the mean over the
 //                       repetitions that finished, block-wide via warp shuffles + one smem hop.
-__global__ void chain_min_kernel(const double* __restrict__ best, const int32_t* __restrict__ accepted, int n_iter,
-                                 int b, double* __restrict__ chain_best, int32_t* __restrict__ chain_iter) {
+__global__ void chain_min_kernel(const double* __restrict__ best, const int32_t* __restrict__ accepted,
+                                 long long stride_best, long long stride_acc, int n_iter, int b,
+                                 double* __restrict__ chain_best, int32_t* __restrict__ chain_iter) {
     const int ch = blockIdx.x * blockDim.x + threadIdx.x;
     if (ch >= b) return;
     double cb = INFINITY;
     int ci = -1;
     for (int k = 0; k < n_iter; ++k) {
-        const size_t o = (size_t)k * b + ch;
-        const double v = best[o];
-        if (accepted[o] >= 0 && v < cb) { cb = v; ci = k; }
+        const double v = best[(size_t)k * stride_best + ch];
+        if (accepted[(size_t)k * stride_acc + ch] >= 0 && v < cb) { cb = v; ci = k; }
     }
     chain_best[ch] = cb;
     chain_iter[ch] = ci;
@@ -555,7 +577,7 @@ __global__ void rng_kernel(uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t
     const uint32_t t_end = step0 + (uint32_t)n_steps;
     for (uint32_t blk = step0 >> 2; (blk << 2) < t_end; ++blk) {
         float z[8][4], e[4];
-        draw_block<8>(k0, k1, chain_id, blk, n, lane, z, e);
+        draw_block<32, 8>(k0, k1, chain_id, blk, n, lane, z, e);
         for (int k = 0; k < 4; ++k) {
             const uint32_t tk = (blk << 2) + k;
             if (tk < step0 || tk >= t_end) continue;
@@ -574,7 +596,7 @@ static int validate(const pb200_problem* p) {
         return fail("npad must be 32, 64, 128 or 256 (n <= 256)");
     if (p->n < 1 || p->n > p->npad) return fail("need 1 <= n <= npad");
     if (p->n_points < 1) return fail("n_points must be >= 1");
-    if (!p->saa || !p->sab || !p->mu || !p->lo || !p->hi || !p->f || !p->c0 || !p->lt_t || !p->lam || !p->g_t || !p->h)
+    if (!p->saa || !p->sab || !p->mu || !p->lo || !p->hi || !p->f || !p->c0 || !p->lt_t || !p->lam || !p->lt_norm || !p->g_t || !p->h)
         return fail("problem has NULL device pointers");
     return 0;
 }
@@ -621,8 +643,42 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
     return check_cuda(cudaGetLastError(), "loglkl_kernel launch");
 }
 
+// lanes per chain: small groups serve several chains per warp instruction, large groups give more warps.
+static int choose_lanes(int npad, int n_chains) {
+    if (npad > 64) return 32;
+    const long long warps32 = n_chains;                    // warps with one chain each
+    const long long want = 148LL * 4 * 6;                  // ~6 warps per SM sub-partition keep the issue slots busy
+    if (npad == 32 && warps32 / 4 >= want) return 8;
+    if (warps32 / 2 >= want) return 16;
+    return 32;
+}
+
+static int resolve_lanes(int requested, int npad, int n_chains, int* out) {
+    int l = requested == 0 ? choose_lanes(npad, n_chains) : requested;
+    if (const char* env = std::getenv("PB200_LANES_PER_CHAIN")) {
+        if (requested == 0 && std::atoi(env) > 0) l = std::atoi(env);
+    }
+    const bool ok = (l == 32) || (l == 16 && npad <= 64) || (l == 8 && npad == 32);
+    if (!ok) return fail("lanes_per_chain must be 32, 16 (npad <= 64) or 8 (npad == 32)");
+    *out = l;
+    return 0;
+}
+
+#define PB200_DISPATCH_GEOMETRY(npad, lanes, CALL)                                   \
+    switch ((npad) * 64 + (lanes)) {                                                 \
+        case 32 * 64 + 32:  { constexpr int LPC = 32, CPL = 1; CALL; } break;        \
+        case 32 * 64 + 16:  { constexpr int LPC = 16, CPL = 2; CALL; } break;        \
+        case 32 * 64 + 8:   { constexpr int LPC = 8,  CPL = 4; CALL; } break;        \
+        case 64 * 64 + 32:  { constexpr int LPC = 32, CPL = 2; CALL; } break;        \
+        case 64 * 64 + 16:  { constexpr int LPC = 16, CPL = 4; CALL; } break;        \
+        case 128 * 64 + 32: { constexpr int LPC = 32, CPL = 4; CALL; } break;        \
+        default:            { constexpr int LPC = 32, CPL = 8; CALL; } break;        \
+    }
+
+int pb200_choose_lanes(int32_t npad, int32_t n_chains) { return choose_lanes(npad, n_chains); }
+
 int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
-                     const pb200_records* rec, int32_t n_iter, uint64_t seed, void* stream) {
+                     const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream) {
     if (validate(prob)) return 1;
     if (!chains || !sched || !rec) return fail("anneal_run: NULL argument");
     if (chains->n_chains <= 0 || n_iter <= 0) return 0;
@@ -630,16 +686,20 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
     if (sched->step_mode < 0 || sched->step_mode > 2) return fail("anneal_run: unknown step_mode");
     if (!rec->best_loglkl || !rec->last_loglkl || !rec->temperature || !rec->step_size || !rec->accepted)
         return fail("anneal_run: records have NULL device pointers");
+    if (rec->iter_stride < chains->n_chains) return fail("anneal_run: records iter_stride < n_chains");
+    int lanes;
+    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = (chains->n_chains + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int per_cta = kWarpsPerCta * (32 / lanes);
+    const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    PB200_DISPATCH_CPL(prob->npad, (anneal_kernel<CPL><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
-                                        *prob, *chains, *sched, *rec, n_iter, k0, k1)));
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
+                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");
 }
 
 int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,
-                 const pb200_samples* samples, int32_t* accepted_out, void* stream) {
+                 const pb200_samples* samples, int32_t* accepted_out, int32_t lanes_per_chain, void* stream) {
     if (validate(prob)) return 1;
     if (!chains) return fail("mh_run: NULL chains");
     if (chains->n_chains <= 0 || n_steps <= 0) return 0;
@@ -650,12 +710,15 @@ int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t 
             return fail("mh_run: sample buffers missing");
         if (smp.mode == PB200_RECORD_THINNED && smp.thin <= 0) return fail("mh_run: thin must be > 0");
     }
+    int lanes;
+    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    const int blocks = (chains->n_chains + kWarpsPerCta - 1) / kWarpsPerCta;
+    const int per_cta = kWarpsPerCta * (32 / lanes);
+    const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#define PB200_MH(REC)                                                                                          \
-    PB200_DISPATCH_CPL(prob->npad, (mh_kernel<CPL, REC><<<blocks, 32 * kWarpsPerCta, 0, st>>>(                 \
-                                        *prob, *chains, n_steps, k0, k1, smp, accepted_out)))
+#define PB200_MH(REC)                                                                                                  \
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (mh_kernel<LPC, CPL, REC><<<blocks, 32 * kWarpsPerCta, 0, st>>>(      \
+                                                    *prob, *chains, n_steps, k0, k1, smp, accepted_out)))
     if (smp.mode == PB200_RECORD_NONE) { PB200_MH(PB200_RECORD_NONE); }
     else if (smp.mode == PB200_RECORD_ACCEPTED) { PB200_MH(PB200_RECORD_ACCEPTED); }
     else if (smp.mode == PB200_RECORD_THINNED) { PB200_MH(PB200_RECORD_THINNED); }
@@ -673,16 +736,18 @@ int pb200_schedule_update(const pb200_chains* chains, const pb200_schedule* sche
     return check_cuda(cudaGetLastError(), "schedule_kernel launch");
 }
 
-int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int32_t n_iter, int32_t b,
-                         int32_t n_points, int32_t reps, double* out_chain_best, int32_t* out_chain_iter,
-                         double* out_point_best, int32_t* out_point_rep, double* out_point_avg, void* stream) {
+int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int64_t stride_best,
+                         int64_t stride_accepted, int32_t n_iter, int32_t b, int32_t n_points, int32_t reps,
+                         double* out_chain_best, int32_t* out_chain_iter, double* out_point_best,
+                         int32_t* out_point_rep, double* out_point_avg, void* stream) {
     if (!best_loglkl || !accepted || !out_chain_best || !out_chain_iter || !out_point_best || !out_point_rep ||
         !out_point_avg)
         return fail("profile_reduce: NULL argument");
     if (b != n_points * reps) return fail("profile_reduce: b must equal n_points * reps");
     if (n_points <= 0) return 0;
-    chain_min_kernel<<<(b + 255) / 256, 256, 0, (cudaStream_t)stream>>>(best_loglkl, accepted, n_iter, b,
-                                                                       out_chain_best, out_chain_iter);
+    chain_min_kernel<<<(b + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+        best_loglkl, accepted, (long long)stride_best, (long long)stride_accepted, n_iter, b, out_chain_best,
+        out_chain_iter);
     point_reduce_kernel<<<n_points, kPointThreads, 0, (cudaStream_t)stream>>>(out_chain_best, n_points, reps,
                                                                               out_point_best, out_point_rep,
                                                                               out_point_avg);

@@ -4,7 +4,8 @@ the path needs: an NCCL all-gather of per-chain bestfits at iteration boundaries
 Replaces the MPI / process-pool task farm of prospect/communication.py:50-157 and prospect/run.py:27-44:
 chains never interact, so every rank owns a fixed block of chains for the whole run and there is no
 data-path collective; the all-gather only makes every rank's records complete (status files, snapshots,
-min over repetitions).  One process per GPU (torchrun), backend nccl on GPUs / gloo in the CPU tests.
+min over repetitions).  The gathered unit is the contiguous per-iteration record block the annealing kernel
+writes (engine.Records), so no packing kernel sits between compute and the collective.  One process per GPU (torchrun), backend nccl on GPUs / gloo in the CPU tests.
 """
 import os
 
@@ -59,35 +60,3 @@ def shard_grid(n_points, reps, rank, world):
 def global_chain_index(point, rep, n_points):
     """c = rep * P + point: the reference's task enumeration (tasks/initialise_profile_task.py:16-26)."""
     return rep * n_points + point
-
-
-class RecordGatherer:
-    """All-gathers one packed [B_local, width] FP64 row block per iteration into global chain order."""
-
-    def __init__(self, n_points, reps, width, device):
-        import torch
-        self.rank, self.world, self.active = dist_info()
-        self.n_points, self.reps, self.width = n_points, reps, width
-        shards = [shard_grid(n_points, reps, r, self.world) for r in range(self.world)]
-        self.sizes = [len(p) for p, _ in shards]
-        self.b_max = max(self.sizes)
-        self.global_ids = [global_chain_index(p, r, n_points) for p, r in shards]
-        self.device = torch.device(device)
-        self.local_pad = torch.zeros((self.b_max, width), dtype=torch.float64, device=self.device)
-        self.gathered = torch.zeros((self.world, self.b_max, width), dtype=torch.float64, device=self.device)
-        order = np.concatenate([r * self.b_max + np.arange(s) for r, s in enumerate(self.sizes)])
-        dest = np.concatenate(self.global_ids)
-        inv = np.empty(n_points * reps, dtype=np.int64)
-        inv[dest] = order
-        self.take = torch.as_tensor(inv, device=self.device)
-
-    def gather(self, local_block):
-        """local_block [B_local, width] -> [P*R, width] in global chain order (on every rank)."""
-        import torch.distributed as dist
-        b = local_block.shape[0]
-        self.local_pad[:b].copy_(local_block)
-        if self.world > 1:
-            dist.all_gather_into_tensor(self.gathered.view(-1, self.width), self.local_pad)
-        else:
-            self.gathered[0].copy_(self.local_pad)
-        return self.gathered.view(-1, self.width).index_select(0, self.take)

@@ -67,21 +67,53 @@ class ChainBatch:
 
 
 class Records:
-    """Per-(iteration, chain) bestfit records (struct pb200_records)."""
+    """Per-(iteration, chain) bestfit records (struct pb200_records).
 
-    def __init__(self, problem: DeviceProblem, n_chains, max_iterations, keep_positions=True):
+    One contiguous FP64 block per iteration -- [best_loglkl | last_loglkl | temperature | step_size | accepted
+    (int32) | best_x | last_x] -- so a rank can all-gather `buf[k]` at an iteration boundary without packing.
+    `n_alloc` >= n_chains pads the block to a rank-independent size."""
+
+    def __init__(self, problem: DeviceProblem, n_chains, max_iterations, keep_positions=True, n_alloc=None):
         dev = problem.device
-        k, b = max_iterations, n_chains
-        self.max_iterations = k
-        self.best_loglkl = torch.full((k, b), math.inf, dtype=torch.float64, device=dev)
-        self.last_loglkl = torch.full((k, b), math.inf, dtype=torch.float64, device=dev)
-        self.temperature = torch.zeros((k, b), dtype=torch.float64, device=dev)
-        self.step_size = torch.zeros((k, b), dtype=torch.float64, device=dev)
-        self.accepted = torch.full((k, b), -1, dtype=torch.int32, device=dev)
-        self.best_x = torch.zeros((k, b, problem.npad), dtype=torch.float64, device=dev) if keep_positions else None
-        self.last_x = torch.zeros((k, b, problem.npad), dtype=torch.float64, device=dev) if keep_positions else None
-        self.c = capi.Records(k, *(capi.ptr(getattr(self, n)) for n in (
-            'best_loglkl', 'last_loglkl', 'temperature', 'step_size', 'accepted', 'best_x', 'last_x')))
+        k, b, npad = max_iterations, int(n_alloc or n_chains), problem.npad
+        self.max_iterations, self.n_chains, self.n_alloc, self.npad = k, n_chains, b, npad
+        acc_d = (b + 1) // 2
+        self.offsets = {'best_loglkl': 0, 'last_loglkl': b, 'temperature': 2 * b, 'step_size': 3 * b,
+                        'accepted': 4 * b, 'best_x': 4 * b + acc_d, 'last_x': 4 * b + acc_d + b * npad}
+        self.stride = 4 * b + acc_d + (2 * b * npad if keep_positions else 0)
+        self.buf = torch.zeros((k, self.stride), dtype=torch.float64, device=dev)
+        o = self.offsets
+        self.best_loglkl = self.buf[:, o['best_loglkl']:o['best_loglkl'] + n_chains]
+        self.last_loglkl = self.buf[:, o['last_loglkl']:o['last_loglkl'] + n_chains]
+        self.temperature = self.buf[:, o['temperature']:o['temperature'] + n_chains]
+        self.step_size = self.buf[:, o['step_size']:o['step_size'] + n_chains]
+        self.accepted = self.buf[:, o['accepted']:o['accepted'] + acc_d].view(torch.int32)[:, :n_chains]
+        self.best_x = self.last_x = None
+        if keep_positions:
+            self.best_x = self.buf[:, o['best_x']:o['best_x'] + b * npad].unflatten(1, (b, npad))[:, :n_chains]
+            self.last_x = self.buf[:, o['last_x']:o['last_x'] + b * npad].unflatten(1, (b, npad))[:, :n_chains]
+        self.best_loglkl.fill_(math.inf)
+        self.last_loglkl.fill_(math.inf)
+        self.accepted.fill_(-1)
+        base = self.buf.data_ptr()
+        addr = lambda name: C.c_void_p(base + 8 * o[name])
+        self.c = capi.Records(k, self.stride, addr('best_loglkl'), addr('last_loglkl'), addr('temperature'),
+                              addr('step_size'), addr('accepted'), addr('best_x') if keep_positions else None,
+                              addr('last_x') if keep_positions else None)
+
+    @staticmethod
+    def decode(block, n_chains, n_alloc, npad, keep_positions=True):
+        """Split gathered blocks [..., stride] (numpy) back into named arrays of the first n_chains chains."""
+        b, acc_d = n_alloc, (n_alloc + 1) // 2
+        out = {'best_loglkl': block[..., 0:n_chains], 'last_loglkl': block[..., b:b + n_chains],
+               'temperature': block[..., 2 * b:2 * b + n_chains], 'step_size': block[..., 3 * b:3 * b + n_chains]}
+        acc = np.ascontiguousarray(block[..., 4 * b:4 * b + acc_d]).view(np.int32)
+        out['accepted'] = acc[..., :n_chains]
+        if keep_positions:
+            o = 4 * b + acc_d
+            bx = block[..., o:o + b * npad]
+            out['best_x'] = bx.reshape(bx.shape[:-1] + (b, npad))[..., :n_chains, :]
+        return out
 
 
 class Samples:
@@ -118,18 +150,24 @@ def loglkl_batch(problem: DeviceProblem, x, point=None, stream=None):
     return out, outside
 
 
-def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, stream=None):
+def choose_lanes(npad, n_chains):
+    """Lanes per chain the library picks for this batch (see pb200_choose_lanes)."""
+    return int(capi.lib().pb200_choose_lanes(int(npad), int(n_chains)))
+
+
+def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, stream=None, lanes=0):
     _count()
     capi.check(capi.lib().pb200_anneal_run(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
-                                           C.byref(records.c), int(n_iter), C.c_uint64(seed), _stream_ptr(stream)))
+                                           C.byref(records.c), int(n_iter), C.c_uint64(seed), int(lanes),
+                                           _stream_ptr(stream)))
 
 
-def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None):
+def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None, lanes=0):
     accepted = torch.zeros(chains.n_chains, dtype=torch.int32, device=problem.device)
     _count()
     capi.check(capi.lib().pb200_mh_run(C.byref(problem.c), C.byref(chains.c), int(n_steps), C.c_uint64(seed),
                                        C.byref(samples.c) if samples is not None else None, capi.ptr(accepted),
-                                       _stream_ptr(stream)))
+                                       int(lanes), _stream_ptr(stream)))
     return accepted
 
 
@@ -152,7 +190,8 @@ def profile_reduce(records: Records, n_iter, n_points, reps, stream=None):
     }
     _count(2)
     capi.check(capi.lib().pb200_profile_reduce(
-        capi.ptr(records.best_loglkl), capi.ptr(records.accepted), int(n_iter), b, int(n_points), int(reps),
+        capi.ptr(records.best_loglkl), capi.ptr(records.accepted), int(records.stride), 2 * int(records.stride),
+        int(n_iter), b, int(n_points), int(reps),
         capi.ptr(out['chain_best']), capi.ptr(out['chain_iter']), capi.ptr(out['point_best']),
         capi.ptr(out['point_rep']), capi.ptr(out['point_avg']), _stream_ptr(stream)))
     return out

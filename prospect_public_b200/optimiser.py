@@ -12,7 +12,7 @@ import math
 import numpy as np
 
 from . import capi
-from .distributed import RecordGatherer, dist_info, global_chain_index, shard_grid
+from .distributed import dist_info, global_chain_index, shard_grid
 
 
 def initialise_optimiser(config, kernel, optimise_settings):
@@ -92,7 +92,12 @@ class SimulatedAnnealing:
             change if isinstance(change, float) else 1.0, interval, mult if not isinstance(mult, str) else 0.0,
             prof.chi2_tolerance)
         self.max_rows = int(s.get('max_rows', prof.max_iterations))
-        self.records = engine.Records(self.problem, self.batch.n_chains, self.max_rows, keep_positions)
+        # every rank allocates record blocks of the same size so that one all-gather per iteration moves them
+        self.b_alloc = max(len(shard_grid(self.n_points, self.reps, r, self.world)[0]) for r in range(self.world))
+        self.keep_positions = keep_positions
+        self.records = engine.Records(self.problem, self.batch.n_chains, self.max_rows, keep_positions,
+                                      n_alloc=self.b_alloc)
+        self.lanes = int(s.get('lanes_per_chain', 0))
         self.seed = int(s.get('seed', 0))
         self.iterations_done = int(s.get('iteration_number', 0))
         self.bestfit = None
@@ -106,7 +111,8 @@ class SimulatedAnnealing:
     def optimise(self, n_iterations=1, stream=None):
         """Run `n_iterations` annealing iterations of every chain in one launch."""
         from . import engine
-        engine.anneal_run(self.problem, self.batch, self.schedule, self.records, n_iterations, self.seed, stream)
+        engine.anneal_run(self.problem, self.batch, self.schedule, self.records, n_iterations, self.seed, stream,
+                          self.lanes)
         self.iterations_done += n_iterations
 
     def set_bestfit(self, iteration=None):
@@ -159,11 +165,11 @@ class SimulatedAnnealing:
                 self.optimise(k)
                 done += k
             return None
-        width = 4 + self.problem.npad
+        import torch.distributed as dist
         if self._gatherer is None:
-            self._gatherer = RecordGatherer(self.n_points, self.reps, width, self.problem.device)
+            self._gatherer = True
             self._comm_stream = torch.cuda.Stream(device=self.problem.device)
-            self.gathered = torch.zeros((self.max_rows, self.n_points * self.reps, width), dtype=torch.float64,
+            self.gathered = torch.zeros((self.max_rows, self.world, self.records.stride), dtype=torch.float64,
                                         device=self.problem.device)
         compute = torch.cuda.current_stream()
         for _ in range(n_iterations):
@@ -173,18 +179,52 @@ class SimulatedAnnealing:
             ev.record(compute)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
-                self.gathered[k].copy_(self._gatherer.gather(self.pack_row(k)))
+                dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k])
         compute.wait_stream(self._comm_stream)
         return self.gathered
 
-    def pack_row(self, k):
-        """[B_local, 4 + npad] FP64: best_loglkl, last_loglkl, accepted, step_size, best_x."""
+    def global_records(self):
+        """Host arrays over ALL chains of the job in global order c = rep * P + point:
+        best_loglkl [K, B], accepted [K, B], step_size [K, B], temperature [K, B], best_x [K, B, n] or None."""
+        from . import engine
+        n, k = self.problem.n, self.max_rows
+        if self.world == 1:
+            r = self.records
+            out = {name: getattr(r, name).cpu().numpy() for name in ('best_loglkl', 'accepted', 'step_size',
+                                                                      'temperature')}
+            out['best_x'] = r.best_x[:, :, :n].cpu().numpy() if r.best_x is not None else None
+            return out
+        g = self.gathered.cpu().numpy()                       # [K, world, stride]
+        b_glob = self.n_points * self.reps
+        out = {'best_loglkl': np.full((k, b_glob), np.inf), 'accepted': np.full((k, b_glob), -1, dtype=np.int32),
+               'step_size': np.zeros((k, b_glob)), 'temperature': np.zeros((k, b_glob)),
+               'best_x': np.zeros((k, b_glob, n)) if self.keep_positions else None}
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            ids = global_chain_index(pt, rep, self.n_points)
+            dec = engine.Records.decode(g[:, rank], len(ids), self.b_alloc, self.problem.npad, self.keep_positions)
+            for name in ('best_loglkl', 'accepted', 'step_size', 'temperature'):
+                out[name][:, ids] = dec[name]
+            if self.keep_positions:
+                out['best_x'][:, ids] = dec['best_x'][..., :n]
+        return out
+
+    def global_status(self):
+        """status of every chain of the job in global order (one small all-gather)."""
         import torch
-        r = self.records
-        cols = torch.stack([r.best_loglkl[k], r.last_loglkl[k], r.accepted[k].to(torch.float64), r.step_size[k]], 1)
-        bx = r.best_x[k] if r.best_x is not None else torch.zeros(
-            (self.n_chains, self.problem.npad), dtype=torch.float64, device=cols.device)
-        return torch.cat([cols, bx], dim=1)
+        if self.world == 1:
+            return self.batch.status.cpu().numpy()
+        import torch.distributed as dist
+        pad = torch.full((self.b_alloc,), -1, dtype=torch.int32, device=self.problem.device)
+        pad[:self.n_chains] = self.batch.status
+        allst = torch.empty((self.world, self.b_alloc), dtype=torch.int32, device=self.problem.device)
+        dist.all_gather_into_tensor(allst.view(-1), pad)
+        allst = allst.cpu().numpy()
+        out = np.zeros(self.n_points * self.reps, dtype=np.int32)
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            out[global_chain_index(pt, rep, self.n_points)] = allst[rank, :len(pt)]
+        return out
 
     def reduce_over_iterations(self):
         """Running-bestfit reduction on the device (analyse_profile_task.py:91-121) for this rank's chains when

@@ -62,6 +62,7 @@ class HostProblem:
     c0: np.ndarray       # [P]
     lt_t: np.ndarray     # [P, npad, npad] f32, lt_t[p, j, i] = Lt[i, j]
     lam: np.ndarray      # [P, npad] f32
+    lt_norm: np.ndarray  # [P, npad] f32, Euclidean row norms of the FP32 Lt, rounded up
     g_t: np.ndarray      # [P, npad, npad] f64, g_t[p, j, i] = G[i, j]
     h: np.ndarray        # [P, npad]
     varying: list        # indices of the varying parameters in x1..xd
@@ -116,6 +117,7 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
         raise ValueError(f'proposal covmats must have shape {(n_points, n, n)}, got {proposal_covmats.shape}')
     lt_t = np.zeros((n_points, npad, npad), dtype=np.float32)
     lam = np.zeros((n_points, npad), dtype=np.float32)
+    lt_norm = np.zeros((n_points, npad), dtype=np.float32)
     g_t = np.zeros((n_points, npad, npad))
     h = np.zeros((n_points, npad))
     s_aa = saa[:n, :n]
@@ -127,9 +129,12 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
         g = lt.T @ s_aa
         lt_t[p, :n, :n] = lt.T
         lam[p, :n] = w
+        # bound used by the deferred prior-box test: norms of the rows of the FP32 factor, nudged upwards
+        rows = np.linalg.norm(lt_t[p, :n, :n].astype(np.float64), axis=0) * (1.0 + 1e-6)
+        lt_norm[p, :n] = np.nextafter(rows.astype(np.float32), np.float32(np.inf))
         g_t[p, :n, :n] = g.T
         h[p, :n] = lt.T @ sab[:n] * f[p]
-    return HostProblem(d, n, npad, n_points, saa, sab, sbb, mu, lo_p, hi_p, f, c0, lt_t, lam, g_t, h, varying,
+    return HostProblem(d, n, npad, n_points, saa, sab, sbb, mu, lo_p, hi_p, f, c0, lt_t, lam, lt_norm, g_t, h, varying,
                        fixed_index, fixed_values)
 
 
@@ -144,10 +149,10 @@ class DeviceProblem:
         if self.device.type != 'cuda':
             raise capi.Pb200Error('prospect_public_b200 runs on CUDA devices only (no CPU fallback)')
         self.t = {name: torch.as_tensor(np.ascontiguousarray(getattr(host, name)), device=self.device)
-                  for name in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t', 'lam', 'g_t', 'h')}
+                  for name in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t', 'lam', 'lt_norm', 'g_t', 'h')}
         self.c = capi.Problem(host.d, host.n, host.npad, host.n_points,
                               *(capi.ptr(self.t[k]) for k in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t',
-                                                              'lam', 'g_t', 'h')))
+                                                              'lam', 'lt_norm', 'g_t', 'h')))
 
     @property
     def n(self):

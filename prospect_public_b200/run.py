@@ -101,19 +101,9 @@ def run_annealing(config, keep_positions=True):
     gathered = sa.run_schedule(n_iter)
     torch.cuda.synchronize()
     loop_s = time.perf_counter() - t0
-    n = sa.problem.n
-    if world == 1:
-        r = sa.records
-        best_ll, acc = r.best_loglkl.cpu().numpy(), r.accepted.cpu().numpy()
-        best_x = r.best_x[:, :, :n].cpu().numpy() if r.best_x is not None else None
-        status = sa.batch.status.cpu().numpy()
-        temperature, step = r.temperature.cpu().numpy(), r.step_size.cpu().numpy()
-    else:
-        g = gathered.cpu().numpy()
-        best_ll, acc, step = g[:, :, 0], g[:, :, 2].astype(np.int32), g[:, :, 3]
-        best_x = g[:, :, 4:4 + n]
-        temperature = None
-        status = _gather_status(sa)
+    g = sa.global_records()
+    best_ll, acc, step, temperature, best_x = g['best_loglkl'], g['accepted'], g['step_size'], g['temperature'], g['best_x']
+    status = sa.global_status()
     ran = acc >= 0
     chain_steps = int(ran.sum()) * int(prof.steps_per_iteration) * 1       # global (records are gathered)
     rec = analysis.RunRecord(values, reps, starts.names, best_ll, acc, best_x, status == capi.CONVERGED,
@@ -145,16 +135,6 @@ def run_annealing(config, keep_positions=True):
             dump_snapshot(config, rec)
     _barrier()
     return result
-
-
-def _gather_status(sa):
-    import torch
-    import torch.distributed as dist
-    g = sa._gatherer
-    pad = torch.zeros((g.b_max, g.width), dtype=torch.float64, device=sa.problem.device)
-    pad[:sa.n_chains, 0] = sa.batch.status.to(torch.float64)
-    out = g.gather(pad[:sa.n_chains])
-    return out[:, 0].cpu().numpy().astype(np.int32)
 
 
 def dump_snapshot(config, rec):

@@ -92,7 +92,7 @@ def test_loglkl_batch_matches_reference(d):
     assert np.allclose(ll0.cpu().numpy(), init_ll, rtol=1e-12, atol=0)
 
 
-def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED):
+def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED, lanes=32):
     """Run B = reps * P chains on the GPU and through the scalar model with the GPU's variates."""
     prob = DeviceProblem(hp, DEV)
     p_count = hp.n_points
@@ -108,11 +108,11 @@ def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode
     recs = engine.Records(prob, b, n_iter)
     done = 0
     for chunk in launches:
-        engine.anneal_run(prob, chains, sched, recs, chunk, SEED)
+        engine.anneal_run(prob, chains, sched, recs, chunk, SEED, lanes=lanes)
         done += chunk
     assert done == n_iter
     torch.cuda.synchronize()
-    model = dm.Model(hp)
+    model = dm.Model(hp, lanes)
     msched = dm.DmSchedule(s['S'], mode, s['tc'], s.get('sc', 1.0), s['interval'][0], s['interval'][1],
                            s.get('mult', 0.0), s.get('tol') or 0.0)
     out = {k: getattr(recs, k).cpu().numpy() for k in ('best_loglkl', 'last_loglkl', 'temperature', 'step_size',
@@ -145,11 +145,13 @@ def _toy_sched(**kw):
     return base
 
 
+@pytest.mark.parametrize('lanes', [32, 16, 8])
 @pytest.mark.parametrize('d', [20, 30])
-def test_anneal_bit_exact_vs_model_replay(d):
-    """K1-style schedule, all profile points x 3 repetitions, 4 iterations in one launch."""
+def test_anneal_bit_exact_vs_model_replay(d, lanes):
+    """K1-style schedule, all profile points x 3 repetitions, 4 iterations in one launch, for every lane-group
+    geometry (32 / 16 / 8 lanes per chain; 30 chains do not fill the last warp of the 16- and 8-lane grids)."""
     hp, starts, init_ll, values, k = toy_profile_problem(d, points=None if d == 20 else list(range(0, 32, 4)))
-    out, _ = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 4, [4])
+    out, _ = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 4, [4], lanes=lanes)
     ar = (1 + out['accepted']) / 251.0
     assert 0.02 < ar.mean() < 0.8
 
@@ -157,8 +159,8 @@ def test_anneal_bit_exact_vs_model_replay(d):
 def test_anneal_launch_partitioning_is_invisible():
     """1 launch of 4 iterations == 1+2+1 launches (state round-trips through HBM losslessly)."""
     hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0, 4, 9])
-    a, fa = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [4])
-    b, fb = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [1, 2, 1])
+    a, fa = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [4], lanes=16)
+    b, fb = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(S=101), 4, [1, 2, 1], lanes=16)
     for key in a:
         assert np.array_equal(a[key], b[key]), key
     for key in fa:
@@ -170,9 +172,12 @@ def test_anneal_exponential_secant_and_tolerance_modes():
     _replay_anneal(hp, starts, init_ll, 2, _toy_sched(s0=0.5, sc=(0.05 / 0.5) ** (1 / 20)), 5, [5],
                    mode=capi.STEP_EXPONENTIAL)
     out, fin = _replay_anneal(hp, starts, init_ll, 4, _toy_sched(s0=0.3, interval=(0.24, 0.26), S=400), 8, [8],
-                              mode=capi.STEP_ADAPTIVE_SECANT)
-    _, fin = _replay_anneal(hp, starts, init_ll, 4, _toy_sched(tol=2.5, t0=0.01), 10, [10])
-    assert (fin['status'] == capi.CONVERGED).any()      # the chi2_tolerance stop fires for some chains
+                              mode=capi.STEP_ADAPTIVE_SECANT, lanes=8)
+    # chains of one warp stop at different iterations (chi2_tolerance): the others must be unaffected
+    _, fin = _replay_anneal(hp, starts, init_ll, 6, _toy_sched(tol=0.02, t0=0.01), 12, [12], lanes=8)
+    assert (fin['status'] == capi.CONVERGED).any() and len(np.unique(fin['iteration'])) > 1
+    _, fin = _replay_anneal(hp, starts, init_ll, 4, _toy_sched(tol=2.5, t0=0.01), 10, [4, 6], lanes=16)
+    assert (fin['status'] == capi.CONVERGED).any()
 
 
 def test_anneal_wide_path_bit_exact_npad64_and_256():
@@ -185,16 +190,33 @@ def test_anneal_wide_path_bit_exact_npad64_and_256():
         starts = np.stack([np.delete(mu, 1) + 0.01, np.delete(mu, 1) - 0.01])
         init_ll = np.array([hp.loglkl(starts[p], p) for p in range(2)])
         _replay_anneal(hp, starts, init_ll, reps, _toy_sched(S=s_steps, s0=2.4 / np.sqrt(d)), 3, [2, 1])
+        if d == 41:
+            _replay_anneal(hp, starts, init_ll, reps, _toy_sched(S=s_steps, s0=2.4 / np.sqrt(d)), 3, [3], lanes=16)
 
 
-def test_prior_box_rejections_bit_exact():
-    """Start next to the box edge with a huge step: many proposals leave the box and must be rejected."""
+@pytest.mark.parametrize('lanes', [32, 8])
+def test_prior_box_rejections_bit_exact(lanes):
+    """Start next to the box edge with a huge step and a flat target (T = 1e6): the deferred box test must fall
+    back to exact materialisation, reject what leaves the box and re-reference what stays inside."""
     hp, k = toy_free_problem(20)
     x0 = np.full((4, 20), 2.45)
     ll0 = np.array([hp.loglkl(x0[0])] * 4)
-    out, _ = _replay_anneal(hp, x0[:1], ll0[:1], 4, _toy_sched(t0=1e6, s0=3.0, S=300, mult=0.0), 2, [2])
+    out, _ = _replay_anneal(hp, x0[:1], ll0[:1], 5, _toy_sched(t0=1e6, s0=3.0, S=300, mult=0.0), 2, [2], lanes=lanes)
     assert out['accepted'].min() >= 0 and out['accepted'].max() < 300
     assert np.all(out['last_x'][..., :20] <= 2.5) and np.all(out['last_x'][..., :20] >= -2.5)
+    assert np.all(out['best_x'][..., :20] <= 2.5) and np.all(out['best_x'][..., :20] >= -2.5)
+
+
+def test_box_is_never_left_by_any_visited_point():
+    """Every recorded point of an MH chain that keeps bouncing off the box edge lies inside the box."""
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    chains = engine.ChainBatch(prob, np.full((64, 20), -2.4), 0, temperature=1e6, step_size=0.3)
+    smp = engine.Samples(prob, 64, 401, capi.RECORD_THINNED, 1)
+    acc = engine.mh_run(prob, chains, 400, SEED, smp, lanes=16).cpu().numpy()
+    x = smp.x.cpu().numpy()[:, :400, :20]
+    assert acc.min() > 0 and acc.max() < 400
+    assert x.min() >= -2.5 and x.max() <= 2.5
 
 
 def test_schedule_update_kernel_bit_exact():
@@ -284,17 +306,18 @@ def test_weighted_moments_on_the_shipped_bootstrap_chain():
     assert np.allclose(cov, ini['covmat'][i], rtol=1e-9, atol=1e-14)
 
 
+@pytest.mark.parametrize('lanes', [32, 16, 8])
 @pytest.mark.parametrize('mode', [capi.RECORD_ACCEPTED, capi.RECORD_THINNED])
-def test_mh_recording_bit_exact_vs_model_replay(mode):
+def test_mh_recording_bit_exact_vs_model_replay(mode, lanes):
     """jobtype mcmc: reference defaults (start 0, covmat 0.005*diag(width), T = step = 1), two launches."""
     hp, k = toy_free_problem(20)
     prob = DeviceProblem(hp, DEV)
     b, n1, n2, cap, thin = 6, 700, 333, 1100, 7
     chains = engine.ChainBatch(prob, np.zeros((b, 20)), 0, temperature=1.0, step_size=1.0)
     smp = engine.Samples(prob, b, cap, mode, thin)
-    a1 = engine.mh_run(prob, chains, n1, SEED, smp).cpu().numpy()
-    a2 = engine.mh_run(prob, chains, n2, SEED, smp).cpu().numpy()
-    model = dm.Model(hp)
+    a1 = engine.mh_run(prob, chains, n1, SEED, smp, lanes=lanes).cpu().numpy()
+    a2 = engine.mh_run(prob, chains, n2, SEED, smp, lanes=lanes).cpu().numpy()
+    model = dm.Model(hp, lanes)
     cnt = smp.count.cpu().numpy()
     gx, gl, gm = smp.x.cpu().numpy(), smp.loglkl.cpu().numpy(), smp.mult.cpu().numpy()
     for c in range(b):
@@ -312,6 +335,33 @@ def test_mh_recording_bit_exact_vs_model_replay(mode):
             assert gm[c, :r].sum() == n1 + n2 + 1           # sum(mults) = steps + 1 (optimise_task.py:27)
             assert r == 1 + a1[c] + a2[c]
     assert np.array_equal(chains.steps_done.cpu().numpy(), np.full(b, n1 + n2))
+
+
+def test_misaligned_chains_in_one_warp_take_the_generic_path():
+    """Chains whose step counters differ modulo 4 share a warp (8 lanes per chain): results still equal the
+    per-chain model (every step redraws its Philox block)."""
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    b, n_steps = 8, 203
+    offs = np.array([0, 1, 2, 3, 5, 7, 4, 8], dtype=np.int32)
+    chains = engine.ChainBatch(prob, np.zeros((b, 20)), 0, temperature=1.0, step_size=1.0, steps_done=offs)
+    acc = engine.mh_run(prob, chains, n_steps, SEED, lanes=8).cpu().numpy()
+    model = dm.Model(hp, 8)
+    xs = chains.x.cpu().numpy()
+    for c in range(b):
+        z, e = _gpu_variates(c, int(offs[c]), n_steps, 20)
+        ch = model.new_chain(np.zeros(20), 0, chain_id=c, temperature=1.0, step_size=1.0, steps_done=int(offs[c]))
+        m, _ = model.mh_chain(ch, n_steps, SEED, z, e)
+        assert acc[c] == m
+        assert np.array_equal(xs[c], np.ctypeslib.as_array(ch.x, (hp.npad,)))
+
+
+def test_lane_choice_follows_batch_size():
+    assert engine.choose_lanes(32, 4096) == 32
+    assert engine.choose_lanes(32, 8192) == 16
+    assert engine.choose_lanes(32, 65536) == 8
+    assert engine.choose_lanes(64, 65536) == 16
+    assert engine.choose_lanes(256, 65536) == 32
 
 
 def test_mh_sample_overflow_is_reported():

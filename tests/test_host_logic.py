@@ -212,18 +212,36 @@ def test_shard_grid_covers_every_chain_once():
 
 
 def _gloo_worker(rank, world, port, p, r, q):
+    """What SimulatedAnnealing.run_schedule / global_records do for N > 1, on CPU tensors over gloo: every rank
+    fills its per-iteration record block, all-gathers it, and decodes all blocks into global chain order."""
     import torch
     import torch.distributed as dist
+    from prospect_public_b200.engine import Records
     os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
     dist.init_process_group('gloo', rank=rank, world_size=world)
-    from prospect_public_b200.distributed import RecordGatherer
+    npad, n_alloc = 32, max(len(shard_grid(p, r, k, world)[0]) for k in range(world))
     pt, rep = shard_grid(p, r, rank, world)
     gid = global_chain_index(pt, rep, p)
-    g = RecordGatherer(p, r, 3, 'cpu')
-    local = torch.stack([torch.as_tensor(gid, dtype=torch.float64), torch.as_tensor(gid * 2.0),
-                         torch.full((len(gid),), float(rank), dtype=torch.float64)], dim=1)
-    out = g.gather(local)
-    q.put((rank, out.numpy()))
+    b = len(gid)
+    acc_d = (n_alloc + 1) // 2
+    stride = 4 * n_alloc + acc_d + 2 * n_alloc * npad
+    block = torch.zeros(stride, dtype=torch.float64)
+    block[0:b] = torch.as_tensor(gid, dtype=torch.float64)                       # best_loglkl := global id
+    block[3 * n_alloc:3 * n_alloc + b] = float(rank)                             # step_size := owner rank
+    block[4 * n_alloc:4 * n_alloc + acc_d].view(torch.int32)[:b] = torch.as_tensor(2 * gid, dtype=torch.int32)
+    bx = block[4 * n_alloc + acc_d:4 * n_alloc + acc_d + n_alloc * npad].view(n_alloc, npad)
+    bx[:b, 0] = torch.as_tensor(gid, dtype=torch.float64) + 0.5
+    gathered = torch.zeros((world, stride), dtype=torch.float64)
+    dist.all_gather_into_tensor(gathered.view(-1), block)
+    g = gathered.numpy()
+    out = np.zeros((p * r, 4))
+    for k in range(world):
+        kp, kr = shard_grid(p, r, k, world)
+        ids = global_chain_index(kp, kr, p)
+        dec = Records.decode(g[k], len(ids), n_alloc, npad)
+        out[ids, 0], out[ids, 1], out[ids, 2] = dec['best_loglkl'], dec['accepted'], dec['step_size']
+        out[ids, 3] = dec['best_x'][:, 0]
+    q.put((rank, out))
     dist.destroy_process_group()
 
 
@@ -243,5 +261,6 @@ def test_record_all_gather_world2_gloo(p, r):
     for rank in range(2):
         assert np.array_equal(outs[rank][:, 0], np.arange(p * r))
         assert np.array_equal(outs[rank][:, 1], 2.0 * np.arange(p * r))
+        assert np.array_equal(outs[rank][:, 3], np.arange(p * r) + 0.5)
     owners = outs[0][:, 2]
     assert set(owners) == {0.0, 1.0}
