@@ -254,8 +254,7 @@ static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain
             if (acc) {
                 for (int c = 0; c < np; ++c) {
                     s->w[c] = wt[c];
-                    s->gt[c] = s->gt[c] + (double)(2.0f * (hl[c] * z[c]));
-                    gf[c] = (float)s->gt[c];
+                    gf[c] = fmaf(hl[c] + hl[c], z[c], gf[c]);      /* FP32 gradient between two FP64 anchors */
                 }
                 s->ll = s->ll + (double)delta;
                 s->nacc += 1;

@@ -27,15 +27,10 @@ __host__ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1,
                                                         uint32_t k0, uint32_t k1, uint32_t out[4]) {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
-#ifdef __CUDA_ARCH__
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), hi1 = __umulhi(0xCD9E8D57u, c2);
-#else
-        const uint32_t hi0 = (uint32_t)(((uint64_t)0xD2511F53u * c0) >> 32);
-        const uint32_t hi1 = (uint32_t)(((uint64_t)0xCD9E8D57u * c2) >> 32);
-#endif
-        const uint32_t lo0 = 0xD2511F53u * c0, lo1 = 0xCD9E8D57u * c2;
-        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
-        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        // one 32x32->64 multiply per word (IMAD.WIDE.U32) yields both halves
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c0 = n0; c1 = (uint32_t)p1; c2 = n2; c3 = (uint32_t)p0;
         k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;

@@ -64,8 +64,8 @@ __device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL]
 //   best     = bref + Lt * bw
 template <int CPL>
 struct ChainState {
-    double xref[CPL], gt[CPL], bref[CPL];
-    float w[CPL], bw[CPL], gf[CPL], hl[CPL];
+    double xref[CPL], bref[CPL];
+    float w[CPL], bw[CPL], gf[CPL], hl[CPL];   // gf: whitened gradient, FP32 between two FP64 anchors
     double ll, best_ll;
     float m2;             // squared whitened radius around xref that provably stays inside the prior box
     int32_t nacc;
@@ -82,8 +82,11 @@ struct ChainState {
 // materialised (n x n matvec), tested exactly and becomes the new reference point.
 // Predicates are per group; everything containing a shuffle or __syncwarp runs under warp-uniform control.
 // ----------------------------------------------------------------------------------------------
-template <int LPC, int CPL, int REC>
-__device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
+// FULL = false is the lean copy used inside the unrolled Philox block: it handles every step whose accepted
+// moves stay inside the safe radius and returns true -- without touching the state -- when some chain needs the
+// exact box test (or a recording action); the caller then replays that step through the FULL copy.
+template <int LPC, int CPL, int REC, bool FULL>
+__device__ __forceinline__ bool one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
                                          ChainState<CPL>& c, float* ws, RecCursor& rc) {
     float tt = 0.0f;
@@ -93,6 +96,7 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
     const float delta = __fmul_rn(sf, tt);
     const bool lik = live && (delta < __fmul_rn(Tf, ek));
     bool acc = false;
+    if (!FULL && REC != PB200_RECORD_NONE) return true;      // recording kernels always take the full copy
     if (__any_sync(kFull, lik)) {
         float wt[CPL], rr = 0.0f;
 #pragma unroll
@@ -104,6 +108,7 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
         const bool exact = lik && (REC == PB200_RECORD_ACCEPTED || !(rr <= c.m2));
         acc = lik;
         if (__any_sync(kFull, exact)) {
+            if (!FULL) return true;
             double xt[CPL];
             materialise<LPC, CPL>(lt_pt, gl, c.xref, wt, ws, xt);
             bool outside = false;
@@ -126,8 +131,7 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
 #pragma unroll
             for (int r = 0; r < CPL; ++r) {
                 c.w[r] = wt[r];
-                c.gt[r] = __dadd_rn(c.gt[r], (double)__fmul_rn(2.0f, __fmul_rn(c.hl[r], zk[r])));
-                c.gf[r] = (float)c.gt[r];
+                c.gf[r] = __fmaf_rn(__fadd_rn(c.hl[r], c.hl[r]), zk[r], c.gf[r]);     // gt += step * lam * z
             }
             c.ll = __dadd_rn(c.ll, (double)delta);
             c.nacc += 1;
@@ -156,6 +160,7 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
             if (now) record_row<LPC, CPL>(rc, xn, c.ll, 1, gl);
         }
     }
+    return false;
 }
 
 // MH steps [t_begin, t_begin + n_steps) of the warp's chains.  Philox blocks cover 4 consecutive steps: when
@@ -167,51 +172,43 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
                                           ChainState<CPL>& c, float* ws, RecCursor& rc) {
+    asm volatile("" : "+f"(Tf), "+f"(sf));      // keep the FP32 copies live instead of re-converting the doubles
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) {
-        c.gf[r] = (float)c.gt[r];
-        c.hl[r] = __fmul_rn(half_s, lam[r]);
-    }
+    for (int r = 0; r < CPL; ++r) c.hl[r] = __fmul_rn(half_s, lam[r]);
     const uint32_t lead = __shfl_sync(kFull, t_begin, 0);
     const bool aligned = __all_sync(kFull, (t_begin & 3u) == (lead & 3u));
     float z[CPL][4], e[4], zk[CPL];
-    if (aligned) {
-        uint32_t i = 0;                         // steps done (warp-uniform); this group's step index is t_begin + i
-        while (i < n_steps) {
-            const uint32_t t = t_begin + i, off = (lead + i) & 3u;
-            draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
-            if (off == 0u && n_steps - i >= 4u) {
+    uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
+    while (i < n_steps) {
+        const uint32_t t = t_begin + i;
+        draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+        uint32_t off = (lead + i) & 3u, cnt = aligned ? min(4u - off, n_steps - i) : 1u;
+        if (REC == PB200_RECORD_NONE && aligned && off == 0u && cnt == 4u) {
+            // whole block: lean unrolled copies; the first step that needs the exact path ends the fast lane
+            bool slow = false;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) {
+                if (!slow) {
 #pragma unroll
                     for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
-                    one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t + k, Tf, sf, zk, e[k], c, ws, rc);
+                    slow = one_step<LPC, CPL, REC, false>(p, pt, lt_pt, gl, gi, live, t + k, Tf, sf, zk, e[k], c, ws, rc);
+                    if (!slow) { ++i; }
                 }
-                i += 4;
-            } else {
-                const uint32_t cnt = min(4u - off, n_steps - i);
-#pragma unroll 1
-                for (uint32_t q = 0; q < cnt; ++q) {
-                    const uint32_t k = off + q;
-#pragma unroll
-                    for (int r = 0; r < CPL; ++r)
-                        zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
-                    const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
-                    one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t + q, Tf, sf, zk, ek, c, ws, rc);
-                }
-                i += cnt;
             }
+            if (!slow) continue;
+            off = (lead + i) & 3u;               // replay the rest of the block through the full copy
+            cnt = 4u - off;
         }
-    } else {
+        if (!aligned) off = t & 3u;              // per-group sub-step, block redrawn every step
 #pragma unroll 1
-        for (uint32_t i = 0; i < n_steps; ++i) {
-            const uint32_t t = t_begin + i, k = t & 3u;
-            draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+        for (uint32_t q = 0; q < cnt; ++q) {
+            const uint32_t k = off + q;
 #pragma unroll
             for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
             const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
-            one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, t, Tf, sf, zk, ek, c, ws, rc);
+            one_step<LPC, CPL, REC, true>(p, pt, lt_pt, gl, gi, live, t_begin + i, Tf, sf, zk, ek, c, ws, rc);
+            ++i;
         }
     }
 }
@@ -220,9 +217,10 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
 template <int LPC, int CPL>
 __device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, const double (&x)[CPL],
                                        ChainState<CPL>& c, double* qs) {
-    c.ll = exact_eval<LPC, CPL, true>(p, pt, x, gl, qs, c.gt);
+    double gt[CPL];
+    c.ll = exact_eval<LPC, CPL, true>(p, pt, x, gl, qs, gt);
 #pragma unroll
-    for (int r = 0; r < CPL; ++r) { c.xref[r] = x[r]; c.w[r] = 0.0f; }
+    for (int r = 0; r < CPL; ++r) { c.xref[r] = x[r]; c.w[r] = 0.0f; c.gf[r] = (float)gt[r]; }
     c.m2 = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
 }
 
@@ -645,11 +643,12 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
 
 // lanes per chain: small groups serve several chains per warp instruction, large groups give more warps.
 static int choose_lanes(int npad, int n_chains) {
+    // Measured on B200 (30-D toy, profiles/): fewer lanes per chain = fewer warp instructions per chain-step, but the
+    // kernel is latency-bound below ~3.5 warps per SM sub-partition, so keep >= 2048 warps in flight when the batch allows.
     if (npad > 64) return 32;
-    const long long warps32 = n_chains;                    // warps with one chain each
-    const long long want = 148LL * 4 * 6;                  // ~6 warps per SM sub-partition keep the issue slots busy
-    if (npad == 32 && warps32 / 4 >= want) return 8;
-    if (warps32 / 2 >= want) return 16;
+    const long long want = 2048;
+    if (npad == 32 && (long long)n_chains / 4 >= want) return 8;
+    if ((long long)n_chains / 2 >= want) return 16;
     return 32;
 }
 
