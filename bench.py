@@ -264,8 +264,17 @@ def main():
                 peak, src = float(json.load(f)['hbm_gbs']), 'measured'
         except Exception:
             pass
+        traffic = None                                 # DRAM bytes per launch from the committed ncu capture
+        try:
+            with open(os.path.join(ROOT, 'profiles', 'r01_global30_lanes16.json')) as f:
+                met = json.load(f)['metrics']
+            if args.workload == 'global30':
+                traffic = sum(float(met[k].split()[0]) * {'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Gbyte': 1e9}[
+                    met[k].split()[1]] for k in ('dram__bytes_read.sum', 'dram__bytes_write.sum'))
+        except Exception:
+            pass
         roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': None, 'kernel': 'anneal_kernel<1> (20 iterations fused in one launch)',
+                    'traffic': traffic, 'kernel': f'anneal_kernel (lanes per chain {engine.choose_lanes(sa.problem.npad, b_local)}, 20 iterations fused in one launch)',
                     'kernel_ms': k_ms, 'peak_source': src,
                     'algorithmic_bytes_per_chain_step': STREAM_BYTES_PER_STEP,
                     'note': 'streaming-formulation bound; the kernel keeps chain state in registers, so DRAM '
