@@ -39,12 +39,12 @@ D = 30
 STREAM_BYTES_PER_STEP = 2 * 4 * 32 + 16          # Bytes(n) = 2*4*n_pad + 16
 
 
-def workload_profile_kw(name, n_gpus):
+def workload_profile_kw(name, n_gpus, reps_per_gpu=4096):
     base = dict(temperature_range=[0.1, 0.001], max_iterations=20, step_size_schedule='adaptive',
                 step_size_adaptive_interval=[0.19, 0.21], step_size_adaptive_multiplier=0.3,
                 step_size_adaptive_initial=0.1, steps_per_iteration=250)
     if name == 'global30':
-        return 'global_optimisation', dict(base, repetitions=4096 * n_gpus), 1, 4096 * n_gpus
+        return 'global_optimisation', dict(base, repetitions=reps_per_gpu * n_gpus), 1, reps_per_gpu * n_gpus
     if name == 'profile30':
         p = 32 * n_gpus
         return 'profile', dict(base, repetitions=256, values=f'np.linspace(-1.0, 2.0, {p})'), p, 256
@@ -116,7 +116,7 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import multiprocessing as mp
-    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, args.gpus)
+    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, args.gpus, args.reps_per_gpu)
     k = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_kernel.npz'))
     m = np.load(os.path.join(ROOT, 'tests', 'golden', f'toy{D}_mcmc.npz'))
     rows = np.concatenate([m[f'chain_{i}'] for i in range(4)], axis=0)
@@ -153,6 +153,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='global30', choices=['global30', 'profile30'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--reps-per-gpu', type=int, default=4096, help='global30 only: chains per GPU (experiments)')
     args = ap.parse_args()
     if args.impl == 'reference':
         return run_reference_arm(args)
@@ -179,7 +180,7 @@ def main():
     torch.cuda.set_device(local)
     dev = f'cuda:{local}'
 
-    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, world)
+    jobtype, kw, n_points, reps = workload_profile_kw(args.workload, world, args.reps_per_gpu)
     tmp = tempfile.mkdtemp(prefix=f'pb200_bench_r{rank}_')
     paths, kgold, rows = toy_inputs(tmp)
     cfg = Configuration(annealing_yaml(paths, os.path.join(tmp, 'out'), jobtype=jobtype, write=False, **kw))

@@ -13,8 +13,17 @@
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
 
+// Minimum resident CTAs per SM (-> register budget 65536 / (CTAs * 128)) of the npad = 32 geometries; the values are
+// the measured optimum on B200 (profiles/README.md).  Tried and rejected: drawing the next Philox block piecewise
+// in front of each step (software pipelining) -- the extra live registers cost more than the overlap gained.
 #ifndef PB200_MIN_CTAS
-#define PB200_MIN_CTAS 7     // npad = 32 kernels: <= 72 registers -> 7 CTAs (28 warps) per SM, measured best on B200
+#define PB200_MIN_CTAS 7     // 32 lanes per chain: <= 72 registers, 28 warps per SM
+#endif
+#ifndef PB200_MIN_CTAS_16
+#define PB200_MIN_CTAS_16 5  // 16 lanes per chain: <= 96 registers
+#endif
+#ifndef PB200_MIN_CTAS_8
+#define PB200_MIN_CTAS_8 4   // 8 lanes per chain: <= 128 registers
 #endif
 
 #include <cmath>
@@ -228,7 +237,7 @@ template <int LPC, int CPL>
 struct Geometry {
     static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
-    static constexpr int kMinCtas = NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? 5 : 4));
+    static constexpr int kMinCtas = NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8));
 };
 
 // ----------------------------------------------------------------------------------------------
