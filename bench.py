@@ -36,7 +36,7 @@ import numpy as np  # noqa: E402
 
 METRIC, UNIT = 'chain-steps/s', 'chain-steps/s'
 D = 30
-STREAM_BYTES_PER_STEP = 2 * 4 * 32 + 16          # Bytes(n) = 2*4*n_pad + 16
+STREAM_BYTES_PER_STEP = 2 * 4 * 32 + 16          # Bytes(n) = 2*4*n_pad + 16 (n_pad = 32)
 
 
 def workload_profile_kw(name, n_gpus, reps_per_gpu=4096):
@@ -48,7 +48,23 @@ def workload_profile_kw(name, n_gpus, reps_per_gpu=4096):
     if name == 'profile30':
         p = 32 * n_gpus
         return 'profile', dict(base, repetitions=256, values=f'np.linspace(-1.0, 2.0, {p})'), p, 256
+    if name == 'profile256':        # BASELINE.json configs[3]: 64 points x 128 repetitions on 8 GPUs = 8 points per GPU
+        p = 8 * n_gpus
+        return 'profile', dict(base, repetitions=128, values=None, step_size_adaptive_initial=0.15), p, 128
     raise SystemExit(f'unknown workload {name}')
+
+
+def spd_inputs(folder, n_points):
+    """256-D synthetic SPD target (not from the reference recipe, which is indefinite at this size): start near the
+    mean, proposal = closed-form conditional covariance, profile values within +-2 sigma of the profiled parameter."""
+    from prospect_public_b200.toy import conditional_covariance, spd_target, write_toy_inputs
+    mu, cov = spd_target(256, seed=4)
+    paths = write_toy_inputs(folder, mu, cov, None)
+    sig = float(np.sqrt(cov[1, 1]))
+    extra = {'values': (mu[1] + sig * np.linspace(-2.0, 2.0, n_points)).tolist(), 'start_from_mcmc': None,
+             'start_from_position': (np.delete(mu, 1) + 0.01).tolist(),
+             'start_from_covmat': conditional_covariance(cov).tolist()}
+    return paths, {'means': mu, 'covmat': cov}, None, extra
 
 
 def toy_inputs(folder):
@@ -151,7 +167,7 @@ def main():
     ap.add_argument('--steps', type=int, default=30)
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='global30', choices=['global30', 'profile30'])
+    ap.add_argument('--workload', default='global30', choices=['global30', 'profile30', 'profile256'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--reps-per-gpu', type=int, default=4096, help='global30 only: chains per GPU (experiments)')
     args = ap.parse_args()
@@ -182,7 +198,11 @@ def main():
 
     jobtype, kw, n_points, reps = workload_profile_kw(args.workload, world, args.reps_per_gpu)
     tmp = tempfile.mkdtemp(prefix=f'pb200_bench_r{rank}_')
-    paths, kgold, rows = toy_inputs(tmp)
+    if args.workload == 'profile256':
+        paths, kgold, rows, extra = spd_inputs(tmp, n_points)
+        kw.update(extra)
+    else:
+        paths, kgold, rows = toy_inputs(tmp)
     cfg = Configuration(annealing_yaml(paths, os.path.join(tmp, 'out'), jobtype=jobtype, write=False, **kw))
     kernel = initialise_kernel(cfg.kernel, None, rank, dev)
     starts, values = initialise_optimiser(cfg, kernel)
@@ -258,7 +278,8 @@ def main():
     roofline = None
     if world == 1:
         k_ms = sum(a.elapsed_time(b) for a, b in kev) / args.steps
-        achieved = STREAM_BYTES_PER_STEP * b_local * n_iter * steps / (k_ms * 1e-3) / 1e9
+        stream_bytes = 2 * 4 * sa.problem.npad + 16
+        achieved = stream_bytes * b_local * n_iter * steps / (k_ms * 1e-3) / 1e9
         peak, src = 6650.0, 'fallback'
         try:
             with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
@@ -277,7 +298,7 @@ def main():
         roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
                     'traffic': traffic, 'kernel': f'anneal_kernel (lanes per chain {engine.choose_lanes(sa.problem.npad, b_local)}, 20 iterations fused in one launch)',
                     'kernel_ms': k_ms, 'peak_source': src,
-                    'algorithmic_bytes_per_chain_step': STREAM_BYTES_PER_STEP,
+                    'algorithmic_bytes_per_chain_step': stream_bytes,
                     'note': 'streaming-formulation bound; the kernel keeps chain state in registers, so DRAM '
                             'traffic is ~0 and the binding resource is FP32/MUFU issue (DESIGN.md)'}
 
@@ -307,7 +328,7 @@ def main():
     e2e_value = chain_steps_per_step * e2e_steps / float(t.item())
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and rows is not None:
         from oracle import reference_port as rp
         n_sample = 6
         t0 = time.perf_counter()
@@ -322,7 +343,7 @@ def main():
         line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
                 'warmup': args.warmup, 'ms_per_step': dev_ms_max / args.steps, 'higher_is_better': True,
                 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                'config': {'workload': f'{args.workload}: 30-D Gaussian toy (reference recipe, seed 0), {jobtype}, '
+                'config': {'workload': f'{args.workload}: ' + ('256-D synthetic SPD Gaussian' if args.workload == 'profile256' else '30-D Gaussian toy (reference recipe, seed 0)') + f', {jobtype}, '
                                        f'{n_points} point(s) x {reps} repetitions = {n_points * reps} chains '
                                        f'({b_local} per GPU) x {n_iter} iterations x {steps} steps',
                            'chain_steps_per_step': chain_steps_per_step, 'l2': 'flushed (192 MiB write) between steps',

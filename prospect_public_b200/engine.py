@@ -35,6 +35,7 @@ class ChainBatch:
 
     def __init__(self, problem: DeviceProblem, x0, point, chain_id=None, temperature=1.0, step_size=1.0,
                  current_best=math.inf, steps_done=0):
+        from .problem import upload_packed
         dev = problem.device
         self.problem = problem
         x0 = np.asarray(x0, dtype=np.float64)
@@ -42,22 +43,20 @@ class ChainBatch:
         self.n_chains = b
         xp = np.zeros((b, problem.npad))
         xp[:, :problem.n] = x0[:, :problem.n]
-        self.x = torch.as_tensor(xp, device=dev)
-        full = lambda v, dt: torch.as_tensor(np.broadcast_to(np.asarray(v, dtype=dt), (b,)).copy(), device=dev)
-        self.loglkl = torch.zeros(b, dtype=torch.float64, device=dev)
-        self.temperature = full(temperature, np.float64)
-        self.step_size = full(step_size, np.float64)
-        self.current_best = full(current_best, np.float64)
-        self.point = full(point, np.int32)
+        full = lambda v, dt: np.broadcast_to(np.asarray(v, dtype=dt), (b,)).copy()
         ids = np.arange(b, dtype=np.uint32) if chain_id is None else np.asarray(chain_id, dtype=np.uint32)
-        self.chain_id = torch.as_tensor(ids.view(np.int32).copy(), device=dev)
-        self.steps_done = full(steps_done, np.int32)
-        self.iteration = torch.zeros(b, dtype=torch.int32, device=dev)
-        self.status = torch.zeros(b, dtype=torch.int32, device=dev)
-        self.secant_stage = torch.zeros(b, dtype=torch.int32, device=dev)
-        self.secant_prev_mult = torch.zeros(b, dtype=torch.float64, device=dev)
-        self.secant_cur_mult = torch.zeros(b, dtype=torch.float64, device=dev)
-        self.secant_prev_ar = torch.zeros(b, dtype=torch.float64, device=dev)
+        host = {
+            'x': xp, 'loglkl': np.zeros(b), 'temperature': full(temperature, np.float64),
+            'step_size': full(step_size, np.float64), 'current_best': full(current_best, np.float64),
+            'secant_prev_mult': np.zeros(b), 'secant_cur_mult': np.zeros(b), 'secant_prev_ar': np.zeros(b),
+            'point': full(point, np.int32), 'chain_id': ids.view(np.int32).copy(),
+            'steps_done': full(steps_done, np.int32), 'iteration': np.zeros(b, dtype=np.int32),
+            'status': np.zeros(b, dtype=np.int32), 'secant_stage': np.zeros(b, dtype=np.int32),
+        }
+        t = upload_packed(host, dev)          # one pinned staging buffer, one H2D copy
+        self._storage = t.pop('_storage')
+        for name, tensor in t.items():
+            setattr(self, name, tensor)
         self.c = capi.Chains(b, *(capi.ptr(getattr(self, k)) for k in (
             'x', 'loglkl', 'temperature', 'step_size', 'current_best', 'point', 'chain_id', 'steps_done',
             'iteration', 'status', 'secant_stage', 'secant_prev_mult', 'secant_cur_mult', 'secant_prev_ar')))

@@ -76,8 +76,7 @@ class SimulatedAnnealing:
         pt, rep = shard_grid(self.n_points, self.reps, self.rank, self.world)
         self.point_global, self.rep = pt, rep
         self.local_points = np.unique(pt)
-        local_of = {g: i for i, g in enumerate(self.local_points)}
-        point_local = np.array([local_of[g] for g in pt], dtype=np.int32)
+        point_local = np.searchsorted(self.local_points, pt).astype(np.int32)
         fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
         self.problem = kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covs[self.local_points])
         cb = np.broadcast_to(np.asarray(s.get('current_best_loglkl', math.inf), dtype=np.float64), (self.n_points,))

@@ -138,6 +138,32 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
                        fixed_index, fixed_values)
 
 
+_TORCH_DTYPES = {'<f8': 'float64', '<f4': 'float32', '<i4': 'int32', '<u4': 'int32', '<i8': 'int64'}
+
+
+def upload_packed(arrays, device):
+    """One pinned staging buffer + ONE host-to-device copy for a dict of numpy arrays; returns {name: tensor}
+    views (256-byte aligned) into a single device allocation.  Keeps set-up latency off the end-to-end path."""
+    import torch
+    offsets, total = {}, 0
+    for name, a in arrays.items():
+        total = (total + 255) // 256 * 256
+        offsets[name] = total
+        total += a.nbytes
+    host = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=True)
+    hv = host.numpy()
+    for name, a in arrays.items():
+        hv[offsets[name]:offsets[name] + a.nbytes] = np.ascontiguousarray(a).reshape(-1).view(np.uint8)
+    dev = torch.empty(max(total, 1), dtype=torch.uint8, device=device)
+    dev.copy_(host, non_blocking=True)
+    out = {}
+    for name, a in arrays.items():
+        dt = getattr(torch, _TORCH_DTYPES[a.dtype.str])
+        out[name] = dev[offsets[name]:offsets[name] + a.nbytes].view(dt).view(a.shape)
+    out['_storage'] = (dev, host)      # keep both alive until the copy has been consumed
+    return out
+
+
 class DeviceProblem:
     """Device image of a HostProblem + the ctypes struct handed to libpb200."""
 
@@ -148,8 +174,9 @@ class DeviceProblem:
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise capi.Pb200Error('prospect_public_b200 runs on CUDA devices only (no CPU fallback)')
-        self.t = {name: torch.as_tensor(np.ascontiguousarray(getattr(host, name)), device=self.device)
-                  for name in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t', 'lam', 'lt_norm', 'g_t', 'h')}
+        names = ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t', 'lam', 'lt_norm', 'g_t', 'h')
+        self.t = upload_packed({name: getattr(host, name) for name in names}, self.device)
+        self._storage = self.t.pop('_storage')
         self.c = capi.Problem(host.d, host.n, host.npad, host.n_points,
                               *(capi.ptr(self.t[k]) for k in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t',
                                                               'lam', 'lt_norm', 'g_t', 'h')))

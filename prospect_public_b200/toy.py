@@ -63,3 +63,23 @@ def mcmc_yaml(paths, out_dir, n_chains=4, steps=2000, rm1=0.01, write=True, seed
         'kernel': {'type': 'analytical', 'conf': '', 'param': paths['kernel_yaml']},
         'mcmc': sec,
     }
+
+
+def spd_target(d, seed=0, lam_range=(1e-3, 1e-1)):
+    """Synthetic correlated SPD Gaussian for dimensions where the reference recipe is indefinite (d >= 64,
+    SURVEY.md F3): C = Q diag(lam) Q^T with lam log-uniform and Q from the QR of a seeded Gaussian matrix,
+    means ~ U(0, 1).  Returns (means [d], covmat [d, d])."""
+    rng = np.random.default_rng(seed)
+    q, _ = np.linalg.qr(rng.standard_normal((d, d)))
+    lam = np.exp(rng.uniform(np.log(lam_range[0]), np.log(lam_range[1]), d))
+    cov = (q * lam) @ q.T
+    return rng.uniform(0.0, 1.0, d), 0.5 * (cov + cov.T)
+
+
+def conditional_covariance(covmat, n_keep=None):
+    """Covariance of the first n slots given the last one in the reference's residual ordering: inv(S[:n, :n]),
+    S = sym(inv(C)).  The ideal proposal covariance for a profile point (closed form, no bootstrap MCMC)."""
+    s = np.linalg.inv(covmat)
+    s = 0.5 * (s + s.T)
+    n = covmat.shape[0] - 1 if n_keep is None else n_keep
+    return np.linalg.inv(s[:n, :n])
