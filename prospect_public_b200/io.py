@@ -51,21 +51,22 @@ def dump_pickle(obj, folder, name):
     os.replace(tmp, os.path.join(folder, f'{name}.pkl'))
 
 
-def load_config(folder):
-    path = os.path.join(folder, 'config.pkl')
+def load_pickle(folder, name):
+    path = os.path.join(folder, f'{name}.pkl')
     if not os.path.isfile(path):
         raise ValueError(f'Could not find {path}.')
     with open(path, 'rb') as f:
         return pickle.load(f)
 
 
-def load_state(folder):
-    path = os.path.join(folder, 'state.pkl')
-    if not os.path.isfile(path):
-        raise ValueError('No state.pkl found in your argument folder. Please provide either a folder with a '
-                         'PROSPECT state.pkl dump or an input.yaml file.')
-    with open(path, 'rb') as f:
-        return pickle.load(f)
+def load_config(folder):
+    """The run's configuration: this package's pb200_config.pkl if present, else PROSPECT's own config.pkl
+    (read through stand-in classes when PROSPECT is not installed)."""
+    if os.path.isfile(os.path.join(folder, 'pb200_config.pkl')):
+        return load_pickle(folder, 'pb200_config')
+    from .compat import _Registered
+    with _Registered():
+        return load_pickle(folder, 'config')
 
 
 def load_profile(prospect_folder, direct_txt=False):

@@ -64,8 +64,8 @@ def run(user_inp, quiet=True):
     return out
 
 
-def run_annealing(config, keep_positions=True):
-    """jobtype profile / global_optimisation."""
+def run_annealing(config, keep_positions=True, starts=None, values=None, seed=None, write=True):
+    """jobtype profile / global_optimisation.  `starts` / `values` / `seed` let reanneal() supply the start points."""
     import torch
     rank, world, _ = dist_info()
     device = _device()
@@ -78,7 +78,10 @@ def run_annealing(config, keep_positions=True):
     _barrier()
     if rank != 0:
         kernel = initialise_kernel(config.kernel, out_dir, rank, device)
-    starts, values = initialise_optimiser(config, kernel)
+    if starts is None:
+        starts, values = initialise_optimiser(config, kernel)
+    elif config.run.jobtype == 'profile':
+        kernel.set_fixed_parameters({prof.parameter: float(values[0])})
     n_iter = int(prof.max_iterations)
     reps = int(prof.repetitions)
     settings = {
@@ -93,7 +96,7 @@ def run_annealing(config, keep_positions=True):
         'repetitions': reps,
         'fixed_param_val': values if config.run.jobtype == 'profile' else None,
         'max_rows': n_iter,
-        'seed': config.seed,
+        'seed': config.seed if seed is None else seed,
     }
     sa = SimulatedAnnealing(config, kernel, settings, keep_positions=keep_positions)
     torch.cuda.synchronize()
@@ -109,42 +112,59 @@ def run_annealing(config, keep_positions=True):
     rec = analysis.RunRecord(values, reps, starts.names, best_ll, acc, best_x, status == capi.CONVERGED,
                              starts.initial_loglkl, starts.positions, starts.covmats, temperature, step)
     result = {'record': rec, 'chain_steps': chain_steps, 'loop_seconds': loop_s, 'optimiser': sa,
-              'status': status, 'values': values}
-    if rank == 0:
-        if config.run.jobtype == 'profile':
-            sub = os.path.join(config.io.dir, 'profile') if config.io.write else None
-            if sub is not None:
-                reduced = None
-                if world == 1:
-                    reduced = {k: v.cpu().numpy() for k, v in sa.reduce_over_iterations().items()}
-                srt, profile, intervals = analysis.analyse_profile(rec, sub, prof.parameter, prof.confidence_levels,
-                                                                   reduced)
-            else:
-                srt = analysis.sort_bestfits(rec)
-                profile = analysis.compute_profile(rec, srt)
-                intervals = analysis.compute_intervals_neyman(profile, prof.confidence_levels)
-            result.update({'bestfits': srt, 'profile': profile, 'intervals': intervals})
-        else:
-            if config.io.write:
-                result['bestfits'] = analysis.analyse_global_optimisation(
-                    rec, os.path.join(config.io.dir, 'global_optimisation'))
-            else:
-                cb, ci = rec.per_chain_best()
-                result['bestfits'] = {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}
-        if config.io.write:
-            dump_snapshot(config, rec)
+              'status': status, 'values': values, 'seed': sa.seed}
+    if rank == 0 and write:
+        result.update(write_outputs(config, rec, sa if world == 1 else None))
     _barrier()
     return result
 
 
-def dump_snapshot(config, rec):
-    """config.pkl + state.pkl (dense records; a few MB instead of one pickled chain per task)."""
-    pio.dump_pickle(config, config.io.dir, 'config')
-    state = {'format': STATE_FORMAT, 'jobtype': config.run.jobtype,
+def write_outputs(config, rec, sa=None):
+    """Analysis + result files + snapshot of a finished (or re-annealed) run; returns the analysis products."""
+    prof = config.profile
+    result = {}
+    if config.run.jobtype == 'profile':
+        sub = os.path.join(config.io.dir, 'profile') if config.io.write else None
+        if sub is not None:
+            reduced = None
+            if sa is not None:
+                reduced = {k: v.cpu().numpy() for k, v in sa.reduce_over_iterations().items()}
+            srt, profile, intervals = analysis.analyse_profile(rec, sub, prof.parameter, prof.confidence_levels,
+                                                               reduced)
+        else:
+            srt = analysis.sort_bestfits(rec)
+            profile = analysis.compute_profile(rec, srt)
+            intervals = analysis.compute_intervals_neyman(profile, prof.confidence_levels)
+        result.update({'bestfits': srt, 'profile': profile, 'intervals': intervals})
+    else:
+        if config.io.write:
+            result['bestfits'] = analysis.analyse_global_optimisation(
+                rec, os.path.join(config.io.dir, 'global_optimisation'))
+        else:
+            cb, ci = rec.per_chain_best()
+            result['bestfits'] = {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}
+    if config.io.write:
+        dump_snapshot(config, rec)
+    return result
+
+
+def dump_snapshot(config, rec, reference_compatible=True):
+    """Snapshot of a finished run:
+      pb200_config.pkl / pb200_state.pkl   this package's own dense records (a few MB);
+      config.pkl / state.pkl               PROSPECT's own pickle layout (compat.export_reference_snapshot), so that
+                                           `prospect-analyse`, `prospect.run.load`, `load_profile` and `reanneal` of the
+                                           reference work on the folder unchanged;
+      status.txt                           one-paragraph summary."""
+    from . import compat
+    pio.dump_pickle(config, config.io.dir, 'pb200_config')
+    state = {'format': STATE_FORMAT, 'jobtype': config.run.jobtype, 'seed': config.seed, 'epoch': 0,
              'record': {k: getattr(rec, k) for k in ('values', 'reps', 'names', 'best_loglkl', 'accepted', 'best_x',
                                                      'converged', 'initial_loglkl', 'initial_position',
                                                      'initial_covmat', 'temperature', 'step_size')}}
-    pio.dump_pickle(state, config.io.dir, 'state')
+    pio.dump_pickle(state, config.io.dir, 'pb200_state')
+    if reference_compatible:
+        n_tasks = int((rec.accepted >= 0).sum())
+        compat.export_reference_snapshot(config, rec, config.io.dir, compact=n_tasks > 20000)
     with open(os.path.join(config.io.dir, 'status.txt'), 'w') as f:
         ran = rec.accepted >= 0
         f.write(f"Status of job '{config.io.jobname}'\nJobtype: {config.run.jobtype}\n")
@@ -152,23 +172,119 @@ def dump_snapshot(config, rec):
                 f'converged: {int(np.sum(rec.converged))}\n')
 
 
-def analyse(prospect_folder):
-    """Re-run the analysis of a finished folder (prospect/run.py:93-117)."""
-    config = pio.load_config(prospect_folder)
+def load_record(prospect_folder):
+    """(config, RunRecord) of a folder written by this package."""
+    config = pio.load_pickle(prospect_folder, 'pb200_config')
     config.io.dir = prospect_folder
-    state = pio.load_state(prospect_folder)
+    state = pio.load_pickle(prospect_folder, 'pb200_state')
     if not isinstance(state, dict) or state.get('format') != STATE_FORMAT:
-        raise ValueError('state.pkl was not written by prospect_public_b200')
+        raise ValueError('pb200_state.pkl was not written by prospect_public_b200')
     s = state['record']
     rec = analysis.RunRecord(s['values'], s['reps'], s['names'], s['best_loglkl'], s['accepted'], s['best_x'],
                              s['converged'], s['initial_loglkl'], s['initial_position'], s['initial_covmat'],
                              s['temperature'], s['step_size'])
+    return config, rec
+
+
+def analyse(prospect_folder):
+    """Re-run the analysis of a finished folder (prospect/run.py:93-117)."""
+    config, rec = load_record(prospect_folder)
     if config.run.jobtype == 'profile':
         return analysis.analyse_profile(rec, os.path.join(prospect_folder, 'profile'), config.profile.parameter,
                                         config.profile.confidence_levels)
     if config.run.jobtype == 'global_optimisation':
         return analysis.analyse_global_optimisation(rec, os.path.join(prospect_folder, 'global_optimisation'))
     raise KeyError(f'Jobtype {config.run.jobtype} not understood.')
+
+
+def merge_records(old, new, k_offset):
+    """Stack a re-annealing's records under the old ones.  Chains are matched by (value, repetition); values or
+    repetitions present in only one of the two runs get rows marked `accepted = -1` in the other part."""
+    values = np.array(sorted(set(old.values.tolist()) | set(new.values.tolist())))
+    if len(old.values) == 0:
+        values = np.zeros(0)
+    n_pts, reps = max(1, len(values)), max(old.reps, new.reps)
+    k_tot, n = k_offset + new.best_loglkl.shape[0], old.best_x.shape[2]
+    best = np.full((k_tot, n_pts * reps), np.inf)
+    acc = np.full((k_tot, n_pts * reps), -1, dtype=np.int32)
+    bx = np.zeros((k_tot, n_pts * reps, n))
+    temp, step = np.zeros((k_tot, n_pts * reps)), np.zeros((k_tot, n_pts * reps))
+    conv = np.zeros(n_pts * reps, dtype=bool)
+    init_ll, init_pos = np.zeros(n_pts), np.zeros((n_pts, n))
+    init_cov = np.zeros((n_pts, n, n))
+    for part, k0 in ((old, 0), (new, k_offset)):
+        kk = part.best_loglkl.shape[0]
+        for p_src in range(part.n_points):
+            p_dst = int(np.nonzero(values == part.values[p_src])[0][0]) if len(values) else 0
+            if part is old or not np.any(old.values == part.values[p_src] if len(values) else True):
+                init_ll[p_dst], init_pos[p_dst] = part.initial_loglkl[p_src], part.initial_position[p_src]
+                init_cov[p_dst] = part.initial_covmat[p_src]
+            for rep in range(part.reps):
+                src, dst = rep * part.n_points + p_src, rep * n_pts + p_dst
+                best[k0:k0 + kk, dst] = part.best_loglkl[:, src]
+                acc[k0:k0 + kk, dst] = part.accepted[:, src]
+                bx[k0:k0 + kk, dst] = part.best_x[:, src]
+                if part.temperature is not None:
+                    temp[k0:k0 + kk, dst] = part.temperature[:, src]
+                if part.step_size is not None:
+                    step[k0:k0 + kk, dst] = part.step_size[:, src]
+                conv[dst] = part.converged[src] if part is new else conv[dst]
+    return analysis.RunRecord(values, reps, old.names, best, acc, bx, conv, init_ll, init_pos, init_cov, temp, step)
+
+
+def reanneal(yaml_schedule, prospect_folder):
+    """Restart every profile value from its best point so far with a new schedule (prospect/profile.py:17-97):
+    `yaml_schedule` holds {'profile': {...overrides...}} (temperature_range, max_iterations, step-size settings,
+    steps_per_iteration, repetitions, values).  Values without an old bestfit are initialised from the starting
+    MCMC as in a fresh run.  Unlike the reference, which only queues the tasks for a later `prospect <folder>`,
+    the new iterations run at once; their records are appended under the old ones and every output file is
+    rewritten.  The new chains draw from fresh Philox streams (the seed is advanced per re-annealing)."""
+    import yaml as _yaml
+    new_schedule = _yaml.full_load(open(yaml_schedule, 'r')) if isinstance(yaml_schedule, str) else yaml_schedule
+    if 'profile' not in new_schedule:
+        raise KeyError("Reanneal yaml file must contain 'profile' as the first and only key.")
+    config_old, rec_old = load_record(prospect_folder)
+    cfg = {sec: dict(entries) for sec, entries in config_old.config_dict.items()}
+    cfg['profile'].update(new_schedule['profile'])
+    cfg['io'] = dict(cfg['io'], dir=prospect_folder, overwrite_dir=True)
+    config = Configuration(cfg)
+    config.io.dir = config.config_dict['io']['dir'] = prospect_folder
+    is_profile = config.run.jobtype == 'profile'
+    device = _device()
+    kernel = initialise_kernel(config.kernel, prospect_folder, 0, device)
+    srt = analysis.sort_bestfits(rec_old)
+    p_idx = np.arange(rec_old.n_points)
+    old_best = srt['chain_best'][srt['best_rep'], p_idx]
+    old_pos = analysis._best_positions(rec_old, srt)
+    values = np.asarray(config.profile.values, dtype=np.float64) if is_profile else np.zeros(0)
+    n_pts = max(1, len(values))
+    n = rec_old.best_x.shape[2]
+    positions, covmats, init_ll = np.zeros((n_pts, n)), np.zeros((n_pts, n, n)), np.zeros(n_pts)
+    fresh = []
+    for p in range(n_pts):
+        hit = np.nonzero(rec_old.values == values[p])[0] if is_profile else np.array([0])
+        if len(hit) and np.isfinite(old_best[hit[0]]):
+            positions[p], covmats[p], init_ll[p] = old_pos[hit[0]], rec_old.initial_covmat[hit[0]], old_best[hit[0]]
+        else:
+            fresh.append(p)
+    if fresh:
+        sub = Configuration(dict(cfg, profile=dict(cfg['profile'], values=values[fresh])))
+        sp, _ = initialise_optimiser(sub, initialise_kernel(config.kernel, prospect_folder, 0, device))
+        positions[fresh], covmats[fresh], init_ll[fresh] = sp.positions, sp.covmats, sp.initial_loglkl
+    from .initialise import StartingPoints
+    starts = StartingPoints(rec_old.names, positions, covmats, init_ll)
+    state = pio.load_pickle(prospect_folder, 'pb200_state')
+    epoch = int(state.get('epoch', 0)) + 1
+    seed = (int(state.get('seed', config.seed)) + 0x9E3779B97F4A7C15 * epoch) & 0xFFFFFFFFFFFFFFFF
+    out = run_annealing(config, starts=starts, values=values, seed=seed, write=False)
+    rec = merge_records(rec_old, out['record'], rec_old.best_loglkl.shape[0])
+    out['record'] = rec
+    if dist_info()[0] == 0:
+        out.update(write_outputs(config, rec))
+        st = pio.load_pickle(prospect_folder, 'pb200_state')
+        st.update(epoch=epoch, seed=int(state.get('seed', config.seed)))
+        pio.dump_pickle(st, prospect_folder, 'pb200_state')
+    return out
 
 
 def gelman_rubin(means, covs, weights):
@@ -236,9 +352,12 @@ def run_from_shell(argv=None):
     parser = argparse.ArgumentParser(prog='prospect_public_b200')
     parser.add_argument('input_file', help='input .yaml')
     parser.add_argument('--analyse', action='store_true', help='re-analyse an existing run folder')
+    parser.add_argument('--reanneal', metavar='YAML', help='re-anneal the run folder with the schedule in YAML')
     args = parser.parse_args(argv)
     if args.analyse:
         analyse(args.input_file)
+    elif args.reanneal:
+        reanneal(args.reanneal, args.input_file)
     else:
         out = run(args.input_file)
         if dist_info()[0] == 0:

@@ -230,3 +230,29 @@ def test_wide_kernel_profile_d256(tmp_path):
     for p, v in enumerate(vals):
         cf, _ = closed_form.profile_minimum(mu, cov, 1, v)
         assert 2 * abs(best[p] - cf) <= 1e-3, (p, best[p], cf)
+
+
+def test_reanneal_continues_from_the_best_points(tmp_path):
+    """N2 (prospect/profile.py:17-97): a finished run is re-annealed with a colder schedule from each value's
+    best point; the new iterations are appended, the profile can only improve, every file is rewritten."""
+    from prospect_public_b200.run import load_record, reanneal
+    paths, k = _inputs(tmp_path, 20)
+    out_dir = str(tmp_path / 'out')
+    first = run(annealing_yaml(paths, out_dir, repetitions=2))
+    ll_first = first['profile']['loglkls'].copy()
+    second = reanneal({'profile': {'temperature_range': [1.0e-3, 1.0e-7], 'max_iterations': 25,
+                                   'step_size_adaptive_initial': 0.02, 'repetitions': 3}}, out_dir)
+    rec = second['record']
+    assert rec.best_loglkl.shape == (45, 30) and rec.reps == 3
+    assert np.all((rec.accepted[:20].reshape(20, 3, 10)[:, 2] == -1))          # the third repetition is new
+    assert np.all(rec.accepted[20:] >= 0)
+    ll_second = second['profile']['loglkls']
+    assert np.all(ll_second <= ll_first + 1e-12)
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, np.linspace(-1.0, 2.0, 10))
+    assert np.max(2 * np.abs(ll_second - cf)) <= 1e-3
+    # re-annealed chains started from the old best: their first record cannot be worse than it
+    assert np.all(rec.best_loglkl[20].reshape(3, 10).min(axis=0) <= ll_first + 1e-12)
+    _, rec_disk = load_record(out_dir)
+    assert rec_disk.best_loglkl.shape == (45, 30)
+    prof = load_profile(out_dir)
+    assert np.allclose(prof['-loglkl'], ll_second, rtol=1e-9)

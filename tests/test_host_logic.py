@@ -264,3 +264,51 @@ def test_record_all_gather_world2_gloo(p, r):
         assert np.array_equal(outs[rank][:, 3], np.arange(p * r) + 0.5)
     owners = outs[0][:, 2]
     assert set(owners) == {0.0, 1.0}
+
+
+REFERENCE = '/root/reference'
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the reference checkout only exists in the build container')
+def test_reference_reads_our_snapshot(toy20, tmp_path):
+    """N1: config.pkl / state.pkl written by compat.export_reference_snapshot are consumed by the UNMODIFIED
+    reference (`prospect.run.load` -> `Scheduler.get_analysis_task().run`, `prospect.profile.load_profile`) and give
+    its own profile/x2.txt back."""
+    import subprocess
+    import sys
+    from prospect_public_b200 import compat
+    from prospect_public_b200.io import prepare_run
+    with open(os.path.join(GOLDEN, 'toy20_profile_run.json')) as f:
+        gold = json.load(f)
+    out = tmp_path / 'run'
+    cfg = Configuration(annealing_yaml(toy20, str(out), plot_profile=False, plot_schedule=False))
+    prepare_run(cfg)
+    rec = _record_from_golden(gold, 19, 1, np.linspace(-1.0, 2.0, 10))
+    rec.temperature = np.full(rec.best_loglkl.shape, 0.1)
+    rec.step_size = np.full(rec.best_loglkl.shape, 0.1)
+    n_tasks = compat.export_reference_snapshot(cfg, rec, str(out))
+    assert n_tasks == 10 + 200
+    script = (
+        "import sys, json, numpy as np\n"
+        "from prospect.run import load\n"
+        "from prospect.profile import load_profile\n"
+        f"folder = {str(out)!r}\n"
+        "snap = load(folder)\n"
+        # prospect.run.analyse itself raises KeyError for jobtype 'profile' (if / if / elif / else chain,
+        # prospect/run.py:95-114); do what it intends (SURVEY.md F6)
+        "task = snap.get_analysis_task()\n"
+        "task.run([t for t in snap.tasks.done.values() if t.id in task.required_task_ids])\n"
+        "prof = load_profile(folder)\n"
+        "types = sorted({t.type for t in snap.tasks.done.values()})\n"
+        "print('RESULT', json.dumps({'n': len(prof['x2']), 'types': types, 'ntasks': len(snap.tasks.done)}))\n")
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(GOLDEN, '_shims'), REFERENCE]))
+    proc = subprocess.run([sys.executable, '-c', script], capture_output=True, text=True, env=env, cwd=str(tmp_path))
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    line = [ln for ln in proc.stdout.splitlines() if ln.startswith('RESULT')][0]
+    res = json.loads(line[len('RESULT '):])
+    assert res == {'n': 10, 'types': ['InitialiseOptimiserTask', 'OptimiseTask'], 'ntasks': 210}
+    assert (out / 'profile' / 'x2.txt').read_text() == gold['files']['x2.txt']
+    assert (out / 'profile' / 'x2_status.txt').read_text() == gold['files']['x2_status.txt']
+    # and our own reader understands PROSPECT's config.pkl without PROSPECT being importable
+    from prospect_public_b200.io import load_profile
+    assert len(load_profile(str(out))['x2']) == 10
