@@ -69,7 +69,8 @@ class Records:
     """Per-(iteration, chain) bestfit records (struct pb200_records).
 
     One contiguous FP64 block per iteration -- [best_loglkl | last_loglkl | temperature | step_size | accepted
-    (int32) | best_x | last_x] -- so a rank can all-gather `buf[k]` at an iteration boundary without packing.
+    (int32) | best_x] -- so a rank can all-gather `buf[k]` at an iteration boundary without packing; the last
+    positions (only needed locally) live in a second buffer with the same iteration stride.
     `n_alloc` >= n_chains pads the block to a rank-independent size."""
 
     def __init__(self, problem: DeviceProblem, n_chains, max_iterations, keep_positions=True, n_alloc=None):
@@ -78,9 +79,11 @@ class Records:
         self.max_iterations, self.n_chains, self.n_alloc, self.npad = k, n_chains, b, npad
         acc_d = (b + 1) // 2
         self.offsets = {'best_loglkl': 0, 'last_loglkl': b, 'temperature': 2 * b, 'step_size': 3 * b,
-                        'accepted': 4 * b, 'best_x': 4 * b + acc_d, 'last_x': 4 * b + acc_d + b * npad}
-        self.stride = 4 * b + acc_d + (2 * b * npad if keep_positions else 0)
+                        'accepted': 4 * b, 'best_x': 4 * b + acc_d}
+        self.stride = max(4 * b + acc_d + (b * npad if keep_positions else 0), b * npad if keep_positions else 0)
+        self.scalar_len = 4 * b + acc_d          # the per-iteration prefix ranks all-gather at every boundary
         self.buf = torch.zeros((k, self.stride), dtype=torch.float64, device=dev)
+        self.buf_last = torch.zeros((k, self.stride), dtype=torch.float64, device=dev) if keep_positions else None
         o = self.offsets
         self.best_loglkl = self.buf[:, o['best_loglkl']:o['best_loglkl'] + n_chains]
         self.last_loglkl = self.buf[:, o['last_loglkl']:o['last_loglkl'] + n_chains]
@@ -90,7 +93,7 @@ class Records:
         self.best_x = self.last_x = None
         if keep_positions:
             self.best_x = self.buf[:, o['best_x']:o['best_x'] + b * npad].unflatten(1, (b, npad))[:, :n_chains]
-            self.last_x = self.buf[:, o['last_x']:o['last_x'] + b * npad].unflatten(1, (b, npad))[:, :n_chains]
+            self.last_x = self.buf_last[:, :b * npad].unflatten(1, (b, npad))[:, :n_chains]
         self.best_loglkl.fill_(math.inf)
         self.last_loglkl.fill_(math.inf)
         self.accepted.fill_(-1)
@@ -98,17 +101,18 @@ class Records:
         addr = lambda name: C.c_void_p(base + 8 * o[name])
         self.c = capi.Records(k, self.stride, addr('best_loglkl'), addr('last_loglkl'), addr('temperature'),
                               addr('step_size'), addr('accepted'), addr('best_x') if keep_positions else None,
-                              addr('last_x') if keep_positions else None)
+                              C.c_void_p(self.buf_last.data_ptr()) if keep_positions else None)
 
     @staticmethod
     def decode(block, n_chains, n_alloc, npad, keep_positions=True):
-        """Split gathered blocks [..., stride] (numpy) back into named arrays of the first n_chains chains."""
+        """Split gathered blocks [..., stride or scalar_len] (numpy) back into named arrays of the first n_chains
+        chains (positions only if the block carries them)."""
         b, acc_d = n_alloc, (n_alloc + 1) // 2
         out = {'best_loglkl': block[..., 0:n_chains], 'last_loglkl': block[..., b:b + n_chains],
                'temperature': block[..., 2 * b:2 * b + n_chains], 'step_size': block[..., 3 * b:3 * b + n_chains]}
         acc = np.ascontiguousarray(block[..., 4 * b:4 * b + acc_d]).view(np.int32)
         out['accepted'] = acc[..., :n_chains]
-        if keep_positions:
+        if keep_positions and block.shape[-1] >= 4 * b + acc_d + b * npad:
             o = 4 * b + acc_d
             bx = block[..., o:o + b * npad]
             out['best_x'] = bx.reshape(bx.shape[:-1] + (b, npad))[..., :n_chains, :]

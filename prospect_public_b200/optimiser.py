@@ -153,8 +153,10 @@ class SimulatedAnnealing:
     # --- whole schedules ---------------------------------------------------------------------------
     def run_schedule(self, n_iterations, iterations_per_launch=None, gather=True):
         """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: one
-        launch per iteration and an all-gather of that iteration's records on a side stream, overlapping the
-        next iteration's compute (there is no dependency between them)."""
+        launch per iteration and an all-gather of that iteration's per-chain scalars (bestfit chi^2, last chi^2,
+        temperature, step size, accepted count) on a side stream, overlapping the next iteration's compute (there is
+        no dependency between them); the bestfit positions of all iterations follow in one all-gather at the end
+        (global_records), which keeps the per-boundary collective latency-sized."""
         import torch
         if self.world == 1 or not gather:
             per = n_iterations if iterations_per_launch is None else iterations_per_launch
@@ -168,7 +170,7 @@ class SimulatedAnnealing:
         if self._gatherer is None:
             self._gatherer = True
             self._comm_stream = torch.cuda.Stream(device=self.problem.device)
-            self.gathered = torch.zeros((self.max_rows, self.world, self.records.stride), dtype=torch.float64,
+            self.gathered = torch.zeros((self.max_rows, self.world, self.records.scalar_len), dtype=torch.float64,
                                         device=self.problem.device)
         compute = torch.cuda.current_stream()
         for _ in range(n_iterations):
@@ -178,7 +180,7 @@ class SimulatedAnnealing:
             ev.record(compute)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
-                dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k])
+                dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k, :self.records.scalar_len])
         compute.wait_stream(self._comm_stream)
         return self.gathered
 
@@ -193,7 +195,17 @@ class SimulatedAnnealing:
                                                                       'temperature')}
             out['best_x'] = r.best_x[:, :, :n].cpu().numpy() if r.best_x is not None else None
             return out
-        g = self.gathered.cpu().numpy()                       # [K, world, stride]
+        import torch
+        import torch.distributed as dist
+        g = self.gathered.cpu().numpy()                       # [K, world, scalar_len]
+        gx = None
+        if self.keep_positions:
+            r = self.records
+            o, width = r.offsets['best_x'], r.n_alloc * r.npad
+            local = r.buf[:, o:o + width].contiguous()
+            allx = torch.empty((self.world,) + tuple(local.shape), dtype=torch.float64, device=local.device)
+            dist.all_gather_into_tensor(allx.view(-1), local.view(-1))
+            gx = allx.cpu().numpy().reshape(self.world, k, r.n_alloc, r.npad)
         b_glob = self.n_points * self.reps
         out = {'best_loglkl': np.full((k, b_glob), np.inf), 'accepted': np.full((k, b_glob), -1, dtype=np.int32),
                'step_size': np.zeros((k, b_glob)), 'temperature': np.zeros((k, b_glob)),
@@ -201,11 +213,11 @@ class SimulatedAnnealing:
         for rank in range(self.world):
             pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
             ids = global_chain_index(pt, rep, self.n_points)
-            dec = engine.Records.decode(g[:, rank], len(ids), self.b_alloc, self.problem.npad, self.keep_positions)
+            dec = engine.Records.decode(g[:, rank], len(ids), self.b_alloc, self.problem.npad, False)
             for name in ('best_loglkl', 'accepted', 'step_size', 'temperature'):
                 out[name][:, ids] = dec[name]
             if self.keep_positions:
-                out['best_x'][:, ids] = dec['best_x'][..., :n]
+                out['best_x'][:, ids] = gx[rank, :, :len(ids), :n]
         return out
 
     def global_status(self):

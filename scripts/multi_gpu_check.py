@@ -1,0 +1,35 @@
+"""torchrun check of the sharded yaml -> run() path: the profile must agree with the analytic one and rank 0
+must write the PROSPECT output tree.  usage: python -m torch.distributed.run --nproc-per-node N scripts/multi_gpu_check.py"""
+import os, sys, tempfile
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from oracle import closed_form
+from prospect_public_b200.run import run
+from prospect_public_b200.toy import annealing_yaml, write_toy_inputs
+from prospect_public_b200.distributed import dist_info
+
+root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+k = np.load(os.path.join(root, 'tests/golden/toy20_kernel.npz')); m = np.load(os.path.join(root, 'tests/golden/toy20_mcmc.npz'))
+base = os.path.join(tempfile.gettempdir(), 'pb200_mgpu_check')
+rank = int(os.environ.get('RANK', '0'))
+if rank == 0:
+    paths = write_toy_inputs(base, k['means'], k['covmat'], [m[f'chain_{i}'] for i in range(4)])
+import torch, torch.distributed as dist
+from prospect_public_b200.distributed import init_from_env
+init_from_env('nccl'); dist.barrier()
+paths = {'kernel_pkl': os.path.join(base, 'random_gauss.pkl'), 'kernel_yaml': os.path.join(base, 'kernel_load_random_gauss.yaml'),
+         'mcmc_root': os.path.join(base, 'mcmc', 'test')}
+for label, kw in (('points sharded (10 values x 6 reps)', dict(repetitions=6)),
+                  ('reps sharded (1 value x 64 reps)', dict(repetitions=64, values=[0.5]))):
+    res = run(annealing_yaml(paths, os.path.join(base, 'out'), temperature_range=[0.1, 1.0e-6], max_iterations=30, **kw))
+    if dist_info()[0] == 0:
+        vals = res['values']
+        cf = closed_form.profile_curve(k['means'], k['covmat'], 1, vals)
+        err = np.max(2 * np.abs(res['profile']['loglkls'] - cf))
+        ran = (res['record'].accepted >= 0).all()
+        files = os.path.isfile(os.path.join(base, 'out', 'profile', 'x2.txt'))
+        print(f'{label}: world {dist_info()[1]} max |dchi2| vs analytic {err:.2e} all chains recorded {ran} files {files} '
+              f'chain_steps {res["chain_steps"]}')
+        assert err <= 1e-3 and ran and files
+    dist.barrier()
+dist.destroy_process_group()

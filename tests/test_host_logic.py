@@ -224,7 +224,7 @@ def _gloo_worker(rank, world, port, p, r, q):
     gid = global_chain_index(pt, rep, p)
     b = len(gid)
     acc_d = (n_alloc + 1) // 2
-    stride = 4 * n_alloc + acc_d + 2 * n_alloc * npad
+    stride = 4 * n_alloc + acc_d + n_alloc * npad
     block = torch.zeros(stride, dtype=torch.float64)
     block[0:b] = torch.as_tensor(gid, dtype=torch.float64)                       # best_loglkl := global id
     block[3 * n_alloc:3 * n_alloc + b] = float(rank)                             # step_size := owner rank
@@ -239,6 +239,8 @@ def _gloo_worker(rank, world, port, p, r, q):
         kp, kr = shard_grid(p, r, k, world)
         ids = global_chain_index(kp, kr, p)
         dec = Records.decode(g[k], len(ids), n_alloc, npad)
+        sc = Records.decode(g[k][:4 * n_alloc + acc_d], len(ids), n_alloc, npad)       # scalar prefix only
+        assert 'best_x' not in sc and np.array_equal(sc['accepted'], dec['accepted'])
         out[ids, 0], out[ids, 1], out[ids, 2] = dec['best_loglkl'], dec['accepted'], dec['step_size']
         out[ids, 3] = dec['best_x'][:, 0]
     q.put((rank, out))
