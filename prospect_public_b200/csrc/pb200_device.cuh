@@ -13,7 +13,10 @@
 
 namespace pb200 {
 
-constexpr int kWarpsPerCta = 4;
+#ifndef PB200_WARPS_PER_CTA
+#define PB200_WARPS_PER_CTA 4
+#endif
+constexpr int kWarpsPerCta = PB200_WARPS_PER_CTA;   // warps never synchronise with each other: small CTAs only balance the grid
 constexpr unsigned kFull = 0xffffffffu;
 constexpr uint32_t kAcceptSlot = 0xffffffffu;   // Philox counter word of the accept/reject variates
 

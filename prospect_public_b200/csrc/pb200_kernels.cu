@@ -237,7 +237,8 @@ template <int LPC, int CPL>
 struct Geometry {
     static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
-    static constexpr int kMinCtas = NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8));
+    static constexpr int kMinCtas =
+        (NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8))) * 4 / kWarpsPerCta;
 };
 
 // ----------------------------------------------------------------------------------------------
