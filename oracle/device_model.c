@@ -194,90 +194,188 @@ static void rec_push(dm_recorder *r, const double *x, double ll, int mult) {
     r->count += 1;
 }
 
+/* per-run constants + scratch shared by the step routines */
+typedef struct {
+    const dm_problem *p;
+    int pt, lpc;
+    float Tf, sf;
+    float gf[MAXN], hl[MAXN];
+} dm_run;
+
+/* one sequential MH step (device: one_step) */
+static void seq_step(dm_run *R, dm_state *s, const float *zt, float ek, uint32_t t, dm_recorder *rec) {
+    const dm_problem *p = R->p;
+    const int np = p->npad, n = p->n, lpc = R->lpc, cpl = np / lpc, pt = R->pt;
+    const float sf = R->sf, Tf = R->Tf;
+    float z[MAXN], wt[MAXN], lanes[32];
+    double xt[MAXN];
+    const int always_exact = rec && rec->mode == 1;
+    for (int c = 0; c < np; ++c) z[c] = c < n ? zt[c] : 0.0f;
+    for (int gl = 0; gl < lpc; ++gl) {
+        float tt = 0.0f;
+        for (int r = 0; r < cpl; ++r) {
+            const int c = gl + lpc * r;
+            tt = fmaf(z[c], fmaf(R->hl[c], z[c], R->gf[c]), tt);
+        }
+        lanes[gl] = tt;
+    }
+    const float delta = sf * group_sum_f(lanes, lpc);
+    int acc = 0;
+    if (delta < Tf * ek) {
+        for (int gl = 0; gl < lpc; ++gl) {
+            float rr = 0.0f;
+            for (int r = 0; r < cpl; ++r) {
+                const int c = gl + lpc * r;
+                wt[c] = fmaf(sf, z[c], s->w[c]);
+                rr = fmaf(wt[c], wt[c], rr);
+            }
+            lanes[gl] = rr;
+        }
+        const float rr = group_sum_f(lanes, lpc);
+        acc = 1;
+        if (always_exact || !(rr <= s->m2)) {
+            materialise(p, pt, s->xref, wt, xt);
+            int outside = 0;
+            for (int c = 0; c < np; ++c)
+                if (xt[c] < p->lo[c] || xt[c] > p->hi[c]) outside = 1;
+            if (outside) {
+                acc = 0;
+            } else {
+                memcpy(s->xref, xt, sizeof(double) * np);
+                memset(wt, 0, sizeof(float) * np);
+                s->m2 = safe_radius2(p, pt, s->xref);
+            }
+        }
+        if (acc) {
+            for (int c = 0; c < np; ++c) {
+                s->w[c] = wt[c];
+                R->gf[c] = fmaf(R->hl[c] + R->hl[c], z[c], R->gf[c]);   /* FP32 gradient between two FP64 anchors */
+            }
+            s->ll = s->ll + (double)delta;
+            s->nacc += 1;
+            if (s->ll < s->best_ll) {
+                s->best_ll = s->ll;
+                memcpy(s->bw, s->w, sizeof(float) * np);
+                memcpy(s->bref, s->xref, sizeof(double) * np);
+            }
+        }
+    }
+    if (rec && rec->mode == 1) {
+        if (acc) {
+            if (rec->count - 1 < rec->capacity) rec->mult[rec->count - 1] = rec->cur_mult;
+            rec->cur_mult = 1;
+            rec_push(rec, s->xref, s->ll, 1);
+        } else {
+            rec->cur_mult += 1;
+        }
+    } else if (rec && rec->mode == 2) {
+        if ((t + 1) % (uint32_t)rec->thin == 0) {
+            materialise(p, pt, s->xref, s->w, xt);
+            rec_push(rec, xt, s->ll, 1);
+        }
+    }
+}
+
+/*
+ * Four steps of one Philox block at once (device: block_step): 16 dot products reduced together, the accept
+ * decisions resolved with scalars.  zb[k] points at the n normals of step k.  Returns 1 (nothing committed) when the
+ * block must be replayed step by step because the box bound is not provably safe.
+ */
+static int block_steps(dm_run *R, dm_state *s, const float *zb[4], const float e[4]) {
+    const dm_problem *p = R->p;
+    const int np = p->npad, n = p->n, lpc = R->lpc, cpl = np / lpc;
+    const float sf = R->sf, Tf = R->Tf;
+    float v[16][32];
+    for (int gl = 0; gl < lpc; ++gl) {
+        float a[16];
+        for (int i = 0; i < 16; ++i) a[i] = 0.0f;
+        for (int r = 0; r < cpl; ++r) {
+            const int c = gl + lpc * r;
+            const float g = R->gf[c], h = R->hl[c];
+            float z[4], hz[4];
+            for (int k = 0; k < 4; ++k) z[k] = c < n ? zb[k][c] : 0.0f;
+            for (int k = 0; k < 4; ++k) {
+                hz[k] = h * z[k];
+                a[k] = fmaf(z[k], g, a[k]);
+                a[4 + k] = fmaf(hz[k], z[k], a[4 + k]);
+                a[14] = fmaf(z[k], z[k], a[14]);
+            }
+            a[8] = fmaf(hz[0], z[1], a[8]);
+            a[9] = fmaf(hz[0], z[2], a[9]);
+            a[10] = fmaf(hz[0], z[3], a[10]);
+            a[11] = fmaf(hz[1], z[2], a[11]);
+            a[12] = fmaf(hz[1], z[3], a[12]);
+            a[13] = fmaf(hz[2], z[3], a[13]);
+            a[15] = fmaf(s->w[c], s->w[c], a[15]);
+        }
+        for (int i = 0; i < 16; ++i) v[i][gl] = a[i];
+    }
+    float S[16];
+    for (int i = 0; i < 16; ++i) S[i] = group_sum_f(v[i], lpc);
+    float delta[4];
+    int acc[4];
+    delta[0] = sf * (S[0] + S[4]);
+    acc[0] = delta[0] < Tf * e[0];
+    const float x1 = acc[0] ? S[8] + S[8] : 0.0f;
+    delta[1] = sf * ((S[1] + S[5]) + x1);
+    acc[1] = delta[1] < Tf * e[1];
+    const float x2 = (acc[0] ? S[9] + S[9] : 0.0f) + (acc[1] ? S[11] + S[11] : 0.0f);
+    delta[2] = sf * ((S[2] + S[6]) + x2);
+    acc[2] = delta[2] < Tf * e[2];
+    const float x3 = ((acc[0] ? S[10] + S[10] : 0.0f) + (acc[1] ? S[12] + S[12] : 0.0f)) + (acc[2] ? S[13] + S[13] : 0.0f);
+    delta[3] = sf * ((S[3] + S[7]) + x3);
+    acc[3] = delta[3] < Tf * e[3];
+    const int any = acc[0] || acc[1] || acc[2] || acc[3];
+    const float bnd = sqrtf(S[15]) + (sf + sf) * sqrtf(S[14]);
+    if (any && !(bnd * bnd <= s->m2)) return 1;
+    for (int k = 0; k < 4; ++k) {
+        if (!acc[k]) continue;
+        for (int c = 0; c < np; ++c) {
+            const float zc = c < n ? zb[k][c] : 0.0f;
+            s->w[c] = fmaf(sf, zc, s->w[c]);
+            R->gf[c] = fmaf(R->hl[c] + R->hl[c], zc, R->gf[c]);
+        }
+        s->ll = s->ll + (double)delta[k];
+        s->nacc += 1;
+        if (s->ll < s->best_ll) {
+            s->best_ll = s->ll;
+            memcpy(s->bw, s->w, sizeof(float) * np);
+            memcpy(s->bref, s->xref, sizeof(double) * np);
+        }
+    }
+    return 0;
+}
+
 static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain_id, uint32_t t_begin,
                       uint32_t n_steps, float Tf, float sf, int lpc, dm_state *s, const float *z_replay,
                       const float *e_replay, uint32_t replay_step0, dm_recorder *rec) {
-    const int np = p->npad, n = p->n, cpl = np / lpc;
+    const int np = p->npad, n = p->n;
     const float *lam = p->lam + (size_t)pt * np;
-    float gf[MAXN], hl[MAXN], z[MAXN], wt[MAXN];
-    double xt[MAXN];
+    dm_run R;
+    R.p = p; R.pt = pt; R.lpc = lpc; R.Tf = Tf; R.sf = sf;
     const float half_s = 0.5f * sf;
-    for (int c = 0; c < np; ++c) { gf[c] = (float)s->gt[c]; hl[c] = half_s * lam[c]; }
+    for (int c = 0; c < np; ++c) { R.gf[c] = (float)s->gt[c]; R.hl[c] = half_s * lam[c]; }
     float *zbuf = NULL, *ebuf = NULL;
     if (!z_replay) {
         zbuf = (float *)malloc(sizeof(float) * (size_t)n_steps * n);
         ebuf = (float *)malloc(sizeof(float) * (size_t)n_steps);
         dm_variates(seed, chain_id, t_begin, (int32_t)n_steps, n, zbuf, ebuf);
     }
-    const int always_exact = rec && rec->mode == 1;
-    for (uint32_t i = 0; i < n_steps; ++i) {
+    const float *zs = z_replay ? z_replay + (size_t)(t_begin - replay_step0) * n : zbuf;
+    const float *es = e_replay ? e_replay + (t_begin - replay_step0) : ebuf;
+    const int recording = rec && rec->mode != 0;
+    uint32_t i = 0;
+    while (i < n_steps) {
         const uint32_t t = t_begin + i;
-        const float *zt = z_replay ? z_replay + (size_t)(t - replay_step0) * n : zbuf + (size_t)i * n;
-        const float ek = e_replay ? e_replay[t - replay_step0] : ebuf[i];
-        for (int c = 0; c < np; ++c) z[c] = c < n ? zt[c] : 0.0f;
-        float lanes[32];
-        for (int gl = 0; gl < lpc; ++gl) {
-            float tt = 0.0f;
-            for (int r = 0; r < cpl; ++r) {
-                const int c = gl + lpc * r;
-                tt = fmaf(z[c], fmaf(hl[c], z[c], gf[c]), tt);
-            }
-            lanes[gl] = tt;
-        }
-        const float delta = sf * group_sum_f(lanes, lpc);
-        int acc = 0;
-        if (delta < Tf * ek) {
-            for (int gl = 0; gl < lpc; ++gl) {
-                float rr = 0.0f;
-                for (int r = 0; r < cpl; ++r) {
-                    const int c = gl + lpc * r;
-                    wt[c] = fmaf(sf, z[c], s->w[c]);
-                    rr = fmaf(wt[c], wt[c], rr);
-                }
-                lanes[gl] = rr;
-            }
-            const float rr = group_sum_f(lanes, lpc);
-            acc = 1;
-            if (always_exact || !(rr <= s->m2)) {
-                materialise(p, pt, s->xref, wt, xt);
-                int outside = 0;
-                for (int c = 0; c < np; ++c)
-                    if (xt[c] < p->lo[c] || xt[c] > p->hi[c]) outside = 1;
-                if (outside) {
-                    acc = 0;
-                } else {
-                    memcpy(s->xref, xt, sizeof(double) * np);
-                    memset(wt, 0, sizeof(float) * np);
-                    s->m2 = safe_radius2(p, pt, s->xref);
-                }
-            }
-            if (acc) {
-                for (int c = 0; c < np; ++c) {
-                    s->w[c] = wt[c];
-                    gf[c] = fmaf(hl[c] + hl[c], z[c], gf[c]);      /* FP32 gradient between two FP64 anchors */
-                }
-                s->ll = s->ll + (double)delta;
-                s->nacc += 1;
-                if (s->ll < s->best_ll) {
-                    s->best_ll = s->ll;
-                    memcpy(s->bw, s->w, sizeof(float) * np);
-                    memcpy(s->bref, s->xref, sizeof(double) * np);
-                }
-            }
-        }
-        if (rec && rec->mode == 1) {
-            if (acc) {
-                if (rec->count - 1 < rec->capacity) rec->mult[rec->count - 1] = rec->cur_mult;
-                rec->cur_mult = 1;
-                rec_push(rec, s->xref, s->ll, 1);
-            } else {
-                rec->cur_mult += 1;
-            }
-        } else if (rec && rec->mode == 2) {
-            if ((t + 1) % (uint32_t)rec->thin == 0) {
-                materialise(p, pt, s->xref, s->w, xt);
-                rec_push(rec, xt, s->ll, 1);
-            }
+        if (lpc == 8 && !recording && (t & 3u) == 0u && n_steps - i >= 4u) {   /* a whole Philox block (8-lane geometry) */
+            const float *zb[4] = {zs + (size_t)i * n, zs + (size_t)(i + 1) * n, zs + (size_t)(i + 2) * n,
+                                  zs + (size_t)(i + 3) * n};
+            if (block_steps(&R, s, zb, es + i))
+                for (int k = 0; k < 4; ++k) seq_step(&R, s, zb[k], es[i + k], t + k, rec);
+            i += 4;
+        } else {
+            seq_step(&R, s, zs + (size_t)i * n, es[i], t, rec);
+            i += 1;
         }
     }
     free(zbuf); free(ebuf);

@@ -44,11 +44,18 @@ __device__ __forceinline__ float u01(uint32_t w) {
     return __fmaf_rn(__uint2float_rn(w), 2.3283064365386963e-10f, 1.1641532182693481e-10f);
 }
 
+// log2 of a uniform in [2^-33, 1]: never subnormal, so the .ftz form (one MUFU.LG2, no denormal fix-up) is exact enough.
+__device__ __forceinline__ float lg2_fast(float u) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(u));
+    return r;
+}
+
 // Box-Muller on the MUFU pipe: r = sqrt(-2 ln u1), theta = 2 pi u2 - pi.
 __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, float& z1) {
     const float u1 = u01(w0), u2 = u01(w1);
     float r;                                                          // sqrt(-2 ln2 * log2(u1)), one MUFU.SQRT
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * __log2f(u1)));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * lg2_fast(u1)));
     float s, c;
     __sincosf(__fmaf_rn(u2, 6.283185307179586f, -3.141592653589793f), &s, &c);
     z0 = r * c;
@@ -57,7 +64,7 @@ __device__ __forceinline__ void box_muller(uint32_t w0, uint32_t w1, float& z0, 
 
 // Exp(1) variate e = -ln u; the MH test exp(-Delta/T) > u becomes Delta < T * e.
 __device__ __forceinline__ float exp_variate(uint32_t w) {
-    return -0.6931471805599453f * __log2f(u01(w));
+    return -0.6931471805599453f * lg2_fast(u01(w));
 }
 
 // Reductions over the LPC lanes of a group (xor distances < LPC stay inside the group).

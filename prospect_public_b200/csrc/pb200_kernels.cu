@@ -45,6 +45,17 @@ static int check_cuda(cudaError_t e, const char* what) {
     return fail(std::string(what) + ": " + cudaGetErrorString(e));
 }
 
+template <int LPC, int CPL>
+struct Geometry {
+    static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    // four-steps-per-reduction (block_step) pays where few lanes per chain make the butterfly short: measured on B200 it
+    // wins for 8 lanes per chain (+14 % at 4096 chains) and loses for 16 / 32 (more shuffle instructions, issue-bound)
+    static constexpr bool kBlockMode = (LPC == 8);
+    // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
+    static constexpr int kMinCtas =
+        (NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8))) * 4 / kWarpsPerCta;
+};
+
 // Per-group recording cursor of mh_kernel.
 struct RecCursor {
     double* x;        // this chain's [capacity][npad]
@@ -91,11 +102,8 @@ struct ChainState {
 // materialised (n x n matvec), tested exactly and becomes the new reference point.
 // Predicates are per group; everything containing a shuffle or __syncwarp runs under warp-uniform control.
 // ----------------------------------------------------------------------------------------------
-// FULL = false is the lean copy used inside the unrolled Philox block: it handles every step whose accepted
-// moves stay inside the safe radius and returns true -- without touching the state -- when some chain needs the
-// exact box test (or a recording action); the caller then replays that step through the FULL copy.
-template <int LPC, int CPL, int REC, bool FULL>
-__device__ __forceinline__ bool one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
+template <int LPC, int CPL, int REC>
+__device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
                                          ChainState<CPL>& c, float* ws, RecCursor& rc) {
     float tt = 0.0f;
@@ -105,7 +113,6 @@ __device__ __forceinline__ bool one_step(const pb200_problem& p, int pt, const f
     const float delta = __fmul_rn(sf, tt);
     const bool lik = live && (delta < __fmul_rn(Tf, ek));
     bool acc = false;
-    if (!FULL && REC != PB200_RECORD_NONE) return true;      // recording kernels always take the full copy
     if (__any_sync(kFull, lik)) {
         float wt[CPL], rr = 0.0f;
 #pragma unroll
@@ -117,7 +124,6 @@ __device__ __forceinline__ bool one_step(const pb200_problem& p, int pt, const f
         const bool exact = lik && (REC == PB200_RECORD_ACCEPTED || !(rr <= c.m2));
         acc = lik;
         if (__any_sync(kFull, exact)) {
-            if (!FULL) return true;
             double xt[CPL];
             materialise<LPC, CPL>(lt_pt, gl, c.xref, wt, ws, xt);
             bool outside = false;
@@ -169,13 +175,120 @@ __device__ __forceinline__ bool one_step(const pb200_problem& p, int pt, const f
             if (now) record_row<LPC, CPL>(rc, xn, c.ll, 1, gl);
         }
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Four steps at once.  A chain is sequential in its steps, but inside one Philox block everything a step needs
+// from the state is linear in what the earlier steps of the block did: with the block-start gradient g,
+//   A_k = z_k . g,   B_k = sum_i hl_i z_ki^2,   C_jk = sum_i hl_i z_ji z_ki  (j < k)
+//   tt_k = A_k + B_k + 2 * sum_{accepted j < k} C_jk,       Delta_k = step * tt_k,
+// so the 14 dot products (+ |w|^2 and sum_k |z_k|^2 for the box bound) are reduced TOGETHER -- one butterfly with
+// 16 independent values in flight instead of four dependent reduce -> compare -> branch chains -- and the four
+// accept decisions are then resolved with scalar arithmetic.  This is what keeps a small batch (few warps per
+// SM) from being latency-bound.  Box safety for every intermediate point: |w_k| <= |w_0| + step * sum_j |z_j|
+// <= sqrt(R0) + 2 step sqrt(E).  Returns true, with nothing committed, when the group must replay the block
+// step by step (bound not provably inside the safe radius).
+// ----------------------------------------------------------------------------------------------
+template <int LPC, int CPL>
+__device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const float (&z)[CPL][4],
+                                           const float (&e)[4], ChainState<CPL>& c) {
+    float v[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const float g = c.gf[r], h = c.hl[r];
+        float hz[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            hz[k] = __fmul_rn(h, z[r][k]);
+            v[k] = __fmaf_rn(z[r][k], g, v[k]);                  // A_k
+            v[4 + k] = __fmaf_rn(hz[k], z[r][k], v[4 + k]);      // B_k
+            v[14] = __fmaf_rn(z[r][k], z[r][k], v[14]);          // E
+        }
+        v[8] = __fmaf_rn(hz[0], z[r][1], v[8]);                  // C01
+        v[9] = __fmaf_rn(hz[0], z[r][2], v[9]);                  // C02
+        v[10] = __fmaf_rn(hz[0], z[r][3], v[10]);                // C03
+        v[11] = __fmaf_rn(hz[1], z[r][2], v[11]);                // C12
+        v[12] = __fmaf_rn(hz[1], z[r][3], v[12]);                // C13
+        v[13] = __fmaf_rn(hz[2], z[r][3], v[13]);                // C23
+        v[15] = __fmaf_rn(c.w[r], c.w[r], v[15]);                // R0 = |w|^2
+    }
+#pragma unroll
+    for (int m = LPC / 2; m >= 1; m >>= 1) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(kFull, v[i], m));
+    }
+    float delta[4];
+    bool acc[4];
+    delta[0] = __fmul_rn(sf, __fadd_rn(v[0], v[4]));
+    acc[0] = live && (delta[0] < __fmul_rn(Tf, e[0]));
+    const float x1 = acc[0] ? __fadd_rn(v[8], v[8]) : 0.0f;
+    delta[1] = __fmul_rn(sf, __fadd_rn(__fadd_rn(v[1], v[5]), x1));
+    acc[1] = live && (delta[1] < __fmul_rn(Tf, e[1]));
+    const float x2 = __fadd_rn(acc[0] ? __fadd_rn(v[9], v[9]) : 0.0f, acc[1] ? __fadd_rn(v[11], v[11]) : 0.0f);
+    delta[2] = __fmul_rn(sf, __fadd_rn(__fadd_rn(v[2], v[6]), x2));
+    acc[2] = live && (delta[2] < __fmul_rn(Tf, e[2]));
+    const float x3 = __fadd_rn(__fadd_rn(acc[0] ? __fadd_rn(v[10], v[10]) : 0.0f,
+                                         acc[1] ? __fadd_rn(v[12], v[12]) : 0.0f),
+                               acc[2] ? __fadd_rn(v[13], v[13]) : 0.0f);
+    delta[3] = __fmul_rn(sf, __fadd_rn(__fadd_rn(v[3], v[7]), x3));
+    acc[3] = live && (delta[3] < __fmul_rn(Tf, e[3]));
+    const bool any = acc[0] || acc[1] || acc[2] || acc[3];
+    const float bnd = __fadd_rn(__fsqrt_rn(v[15]), __fmul_rn(__fadd_rn(sf, sf), __fsqrt_rn(v[14])));
+    if (any && !(__fmul_rn(bnd, bnd) <= c.m2)) return true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        if (acc[k]) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+                c.w[r] = __fmaf_rn(sf, z[r][k], c.w[r]);
+                c.gf[r] = __fmaf_rn(__fadd_rn(c.hl[r], c.hl[r]), z[r][k], c.gf[r]);
+            }
+            c.ll = __dadd_rn(c.ll, (double)delta[k]);
+            c.nacc += 1;
+            if (c.ll < c.best_ll) {
+                c.best_ll = c.ll;
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) { c.bw[r] = c.w[r]; c.bref[r] = c.xref[r]; }
+            }
+        }
+    }
     return false;
 }
 
-// MH steps [t_begin, t_begin + n_steps) of the warp's chains.  Philox blocks cover 4 consecutive steps: when
-// all chains of the warp share the block alignment (always, unless the caller mixed chains with different
-// histories) whole blocks run a branch-free unrolled body and the ragged head / tail one generic copy;
-// otherwise every step redraws its block (correct, 4x the RNG work).
+// MH steps [t_begin, t_begin + n_steps) of the chains of this warp whose step counter is congruent to `lead`
+// modulo 4 (`live` is false for the others).  Whole Philox blocks go through block_step, the ragged head / tail of
+// the range and blocks that need the exact box test through one_step.  Which path a step takes depends only on
+// the chain's own step index and state, never on its warp neighbours.
+template <int LPC, int CPL, int REC>
+__device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
+                                                int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
+                                                uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
+                                                ChainState<CPL>& c, float* ws, RecCursor& rc) {
+    float z[CPL][4], e[4], zk[CPL];
+    uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
+    while (i < n_steps) {
+        const uint32_t t = t_begin + i;
+        draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+        const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
+        bool todo = live;
+        if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && off == 0u && cnt == 4u) {
+            todo = block_step<LPC, CPL>(live, Tf, sf, z, e, c);
+            if (!__any_sync(kFull, todo)) { i += 4; continue; }
+        }
+#pragma unroll 1
+        for (uint32_t q = 0; q < cnt; ++q) {
+            const uint32_t k = off + q;
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
+            const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
+            one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, todo, t + q, Tf, sf, zk, ek, c, ws, rc);
+        }
+        i += cnt;
+    }
+}
+
 template <int LPC, int CPL, int REC>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
@@ -185,39 +298,19 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
     for (int r = 0; r < CPL; ++r) c.hl[r] = __fmul_rn(half_s, lam[r]);
-    const uint32_t lead = __shfl_sync(kFull, t_begin, 0);
-    const bool aligned = __all_sync(kFull, (t_begin & 3u) == (lead & 3u));
-    float z[CPL][4], e[4], zk[CPL];
-    uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
-    while (i < n_steps) {
-        const uint32_t t = t_begin + i;
-        draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
-        uint32_t off = (lead + i) & 3u, cnt = aligned ? min(4u - off, n_steps - i) : 1u;
-        if (REC == PB200_RECORD_NONE && aligned && off == 0u && cnt == 4u) {
-            // whole block: lean unrolled copies; the first step that needs the exact path ends the fast lane
-            bool slow = false;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                if (!slow) {
-#pragma unroll
-                    for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
-                    slow = one_step<LPC, CPL, REC, false>(p, pt, lt_pt, gl, gi, live, t + k, Tf, sf, zk, e[k], c, ws, rc);
-                    if (!slow) { ++i; }
-                }
-            }
-            if (!slow) continue;
-            off = (lead + i) & 3u;               // replay the rest of the block through the full copy
-            cnt = 4u - off;
-        }
-        if (!aligned) off = t & 3u;              // per-group sub-step, block redrawn every step
+    // chains of one warp normally advance in lockstep; if their step counters differ modulo 4 every alignment
+    // class gets its own pass so that each chain still sees its own block structure
+    const uint32_t lead = __shfl_sync(kFull, t_begin, 0) & 3u;
+    if (__all_sync(kFull, (t_begin & 3u) == lead)) {
+        run_steps_class<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf, sf, c,
+                                       ws, rc);
+    } else {
 #pragma unroll 1
-        for (uint32_t q = 0; q < cnt; ++q) {
-            const uint32_t k = off + q;
-#pragma unroll
-            for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
-            const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
-            one_step<LPC, CPL, REC, true>(p, pt, lt_pt, gl, gi, live, t_begin + i, Tf, sf, zk, ek, c, ws, rc);
-            ++i;
+        for (uint32_t a = 0; a < 4u; ++a) {
+            const bool mine = (t_begin & 3u) == a;
+            if (__any_sync(kFull, mine))
+                run_steps_class<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live && mine, k0, k1, chain_id, t_begin, a, n_steps,
+                                               Tf, sf, c, ws, rc);
         }
     }
 }
@@ -233,13 +326,6 @@ __device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, c
     c.m2 = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
 }
 
-template <int LPC, int CPL>
-struct Geometry {
-    static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
-    // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
-    static constexpr int kMinCtas =
-        (NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8))) * 4 / kWarpsPerCta;
-};
 
 // ----------------------------------------------------------------------------------------------
 // Fused annealing kernel: n_iter iterations x S steps per launch, one lane group per chain.
@@ -653,12 +739,11 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
 
 // lanes per chain: small groups serve several chains per warp instruction, large groups give more warps.
 static int choose_lanes(int npad, int n_chains) {
-    // Measured on B200 (30-D toy, profiles/): fewer lanes per chain = fewer warp instructions per chain-step, but the
-    // kernel is latency-bound below ~3.5 warps per SM sub-partition, so keep >= 2048 warps in flight when the batch allows.
+    // Measured on B200 (30-D toy, profiles/): fewer lanes per chain = fewer warp instructions per chain-step; the
+    // 8-lane geometry (four steps per reduction) is best from 4096 chains up, below that more warps matter more.
     if (npad > 64) return 32;
-    const long long want = 2048;
-    if (npad == 32 && (long long)n_chains / 4 >= want) return 8;
-    if ((long long)n_chains / 2 >= want) return 16;
+    if (npad == 32 && n_chains >= 4096) return 8;
+    if (n_chains >= 4096) return 16;
     return 32;
 }
 

@@ -37,3 +37,14 @@ pr = cProfile.Profile(); pr.enable()
 for s in range(5):
     sa = SimulatedAnnealing(cfg, kernel, settings(s)); sync()
 pr.disable(); pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+
+# the same loop without intermediate syncs (what bench.py's e2e arm does)
+sync(); t0 = time.perf_counter()
+for s in range(10):
+    sa = SimulatedAnnealing(cfg, kernel, settings(100 + s)); sa.run_schedule(20)
+    red = sa.reduce_over_iterations(); bf = sa.set_bestfit(19); out = {k: v.cpu() for k, v in red.items()}
+sync(); print('no-sync loop ms per step', round(1e3 * (time.perf_counter() - t0) / 10, 3))
+import torch
+for trial in range(3):
+    t0 = time.perf_counter(); h = torch.empty(1 << 20, dtype=torch.uint8, pin_memory=True); t1 = time.perf_counter()
+    print('pinned 1MB alloc ms', round(1e3 * (t1 - t0), 3)); del h
