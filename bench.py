@@ -213,7 +213,8 @@ def main():
                 'covmat': starts.covmats, 'temperature': cfg.profile.temperature_range[0],
                 'temperature_change': get_temperature_change(cfg), 'step_size': cfg.profile.step_size_range[0],
                 'step_size_change': get_initial_step_size_change(cfg), 'iteration_number': 0, 'repetitions': reps,
-                'fixed_param_val': values if jobtype == 'profile' else None, 'max_rows': n_iter, 'seed': seed}
+                'fixed_param_val': values if jobtype == 'profile' else None, 'max_rows': n_iter, 'seed': seed,
+                'streamed': os.environ.get('PB200_STREAMED', '0') == '1'}
 
     # ---------------- device-resident arm: state reset + L2 flush between steps are untimed ----------------
     sa = SimulatedAnnealing(cfg, kernel, settings(1234), keep_positions=True)
@@ -226,6 +227,7 @@ def main():
         for k, v in pristine.items():
             getattr(sa.batch, k).copy_(v)
         sa.iterations_done = 0
+        sa.step_counter = 0
         sa.seed = 1234 + step
         sa.records.accepted.fill_(-1)
         flush.add_(1.0)

@@ -178,6 +178,23 @@ int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t 
                  const pb200_samples* samples, int32_t* accepted_out, int32_t lanes_per_chain, void* stream);
 
 /*
+ * Streamed variant: the variate stream of one iteration is produced by a separate, fully parallel generator
+ * kernel (pb200_variates_fill) and the annealing kernel reads it back, so random-number generation (about 60 % of
+ * the instructions of the fused kernel) overlaps the latency-bound chain updates of the previous iteration when the
+ * two are issued on different streams.  All chains of the batch must share the step counter `step_begin`
+ * (chains.steps_done is ignored on input and advanced by steps_per_iteration on output).  Numbers are bit-identical
+ * to pb200_anneal_run.
+ *   zbuf: device buffer of pb200_variates_bytes(npad, n_chains, step_begin, steps_per_iteration) bytes,
+ *         layout [chain][block][npad + 1] float4 (slot npad = the four accept variates of the block).
+ */
+int64_t pb200_variates_bytes(int32_t npad, int32_t n_chains, uint32_t step_begin, int32_t n_steps);
+int pb200_variates_fill(const pb200_problem* prob, const pb200_chains* chains, uint32_t step_begin, int32_t n_steps,
+                        uint64_t seed, void* zbuf, void* stream);
+int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                              const pb200_records* rec, uint32_t step_begin, const void* zbuf,
+                              int32_t lanes_per_chain, void* stream);
+
+/*
  * lanes_per_chain (both samplers): how many lanes of a warp cooperate on one chain -- 32, 16 or 8 (16 / 8 only
  * for npad <= 64 / 32); 0 lets the library choose from the batch size.  A chain's random stream does not depend
  * on it; the floating-point summation order inside a step does (pb200_choose_lanes tells what 0 resolves to).

@@ -58,6 +58,11 @@ SIGNATURES = {
     'pb200_mh_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_int32, C.c_uint64, C.POINTER(Samples),
                                _vp, C.c_int32, _vp]),
     'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),
+    'pb200_variates_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_uint32, C.c_int32]),
+    'pb200_variates_fill': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_uint32, C.c_int32, C.c_uint64, _vp,
+                                      _vp]),
+    'pb200_anneal_run_streamed': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule),
+                                            C.POINTER(Records), C.c_uint32, _vp, C.c_int32, _vp]),
     'pb200_schedule_update': (C.c_int, [C.POINTER(Chains), C.POINTER(Schedule), _vp, _vp, _vp]),
     'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),

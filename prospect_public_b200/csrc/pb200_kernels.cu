@@ -9,6 +9,7 @@
 //   schedule_kernel           stand-alone adaptive step-size bookkeeping.
 //   chain_min_kernel + point_reduce_kernel   min over iterations / first-min repetition / mean (warp shuffles).
 //   moments_kernel            weighted first/second moments (covariance reduction), FP64.
+//   variates_kernel           stand-alone Philox + Box-Muller stream generator (feeds the streamed annealing path).
 //   rng_kernel                test hook exposing the variates.
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
@@ -261,24 +262,52 @@ __device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const 
 // modulo 4 (`live` is false for the others).  Whole Philox blocks go through block_step, the ragged head / tail of
 // the range and blocks that need the exact box test through one_step.  Which path a step takes depends only on
 // the chain's own step index and state, never on its warp neighbours.
-template <int LPC, int CPL, int REC>
+// Variates of one Philox block from the pre-generated stream (variates_kernel): one float4 (the 4 steps) per
+// coordinate, the accept variates in slot npad.  Eight lanes of a group read 128 contiguous bytes.
+template <int LPC, int CPL>
+__device__ __forceinline__ void fetch_block(const float4* __restrict__ row, int n, int gl, float (&z)[CPL][4],
+                                            float (&e)[4]) {
+    constexpr int NPAD = LPC * CPL;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int coord = gl + LPC * r;
+        const float4 v = coord < n ? __ldg(row + coord) : make_float4(0.f, 0.f, 0.f, 0.f);
+        z[r][0] = v.x; z[r][1] = v.y; z[r][2] = v.z; z[r][3] = v.w;
+    }
+    const float4 ev = __ldg(row + NPAD);
+    e[0] = ev.x; e[1] = ev.y; e[2] = ev.z; e[3] = ev.w;
+}
+
+template <int LPC, int CPL, int REC, bool ZBUF>
 __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
                                                 int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
                                                 uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
-                                                ChainState<CPL>& c, float* ws, RecCursor& rc) {
+                                                ChainState<CPL>& c, float* ws, RecCursor& rc,
+                                                const float4* __restrict__ zrow) {
+    constexpr int NPAD = LPC * CPL;
     float z[CPL][4], e[4], zk[CPL];
+    float zn[ZBUF ? CPL : 1][4], en[4];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
+    const uint32_t blk0 = t_begin >> 2;
+    if constexpr (ZBUF) fetch_block<LPC, CPL>(zrow, p.n, gl, z, e);
     while (i < n_steps) {
         const uint32_t t = t_begin + i;
-        draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+        if constexpr (ZBUF) {
+            // the next block's loads are issued before this block is processed (one block of latency cover)
+            const uint32_t nxt = (t >> 2) + 1u - blk0;
+            if (((t >> 2) + 1u) << 2 < t_begin + n_steps)
+                fetch_block<LPC, CPL>(zrow + (size_t)nxt * (NPAD + 1), p.n, gl, zn, en);
+        } else {
+            draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
+        }
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
-        bool todo = live;
+        bool todo = live, cnt_done = false;
         if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && off == 0u && cnt == 4u) {
             todo = block_step<LPC, CPL>(live, Tf, sf, z, e, c);
-            if (!__any_sync(kFull, todo)) { i += 4; continue; }
+            if (!__any_sync(kFull, todo)) cnt_done = true;
         }
 #pragma unroll 1
-        for (uint32_t q = 0; q < cnt; ++q) {
+        for (uint32_t q = 0; q < (cnt_done ? 0u : cnt); ++q) {
             const uint32_t k = off + q;
 #pragma unroll
             for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
@@ -286,14 +315,24 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, todo, t + q, Tf, sf, zk, ek, c, ws, rc);
         }
         i += cnt;
+        if constexpr (ZBUF) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[r][k] = zn[r][k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = en[k];
+        }
     }
 }
 
-template <int LPC, int CPL, int REC>
+template <int LPC, int CPL, int REC, bool ZBUF = false>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
-                                          ChainState<CPL>& c, float* ws, RecCursor& rc) {
+                                          ChainState<CPL>& c, float* ws, RecCursor& rc,
+                                          const float4* __restrict__ zrow = nullptr) {
     asm volatile("" : "+f"(Tf), "+f"(sf));      // keep the FP32 copies live instead of re-converting the doubles
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
@@ -302,15 +341,15 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
     // class gets its own pass so that each chain still sees its own block structure
     const uint32_t lead = __shfl_sync(kFull, t_begin, 0) & 3u;
     if (__all_sync(kFull, (t_begin & 3u) == lead)) {
-        run_steps_class<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf, sf, c,
-                                       ws, rc);
+        run_steps_class<LPC, CPL, REC, ZBUF>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
+                                             sf, c, ws, rc, zrow);
     } else {
 #pragma unroll 1
         for (uint32_t a = 0; a < 4u; ++a) {
             const bool mine = (t_begin & 3u) == a;
             if (__any_sync(kFull, mine))
-                run_steps_class<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live && mine, k0, k1, chain_id, t_begin, a, n_steps,
-                                               Tf, sf, c, ws, rc);
+                run_steps_class<LPC, CPL, REC, ZBUF>(p, pt, lt_pt, gl, gi, live && mine, k0, k1, chain_id, t_begin, a,
+                                                     n_steps, Tf, sf, c, ws, rc, zrow);
         }
     }
 }
@@ -330,10 +369,12 @@ __device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, c
 // ----------------------------------------------------------------------------------------------
 // Fused annealing kernel: n_iter iterations x S steps per launch, one lane group per chain.
 // ----------------------------------------------------------------------------------------------
-template <int LPC, int CPL>
+// ZBUF = true: ONE iteration whose variates were pre-generated by variates_kernel into `zbuf`
+// ([chain][nb][npad + 1] float4, first block = t_stream >> 2); all chains then share the step counter t_stream.
+template <int LPC, int CPL, bool ZBUF>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
 anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1) {
+              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane / LPC, gl = lane % LPC;
@@ -355,7 +396,8 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
     const bool was_live = live;
     const int pt = ch.point[chain];
     const uint32_t chain_id = ch.chain_id[chain];
-    uint32_t t = ch.steps_done[chain];
+    uint32_t t = ZBUF ? t_stream : ch.steps_done[chain];
+    const float4* zrow = ZBUF ? zbuf + (size_t)chain * nb * (NPAD + 1) : nullptr;
     const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
     double* qs = stage[wib][gi];
     float* ws = reinterpret_cast<float*>(qs);
@@ -376,9 +418,9 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
         c.nacc = 0;
 #pragma unroll
         for (int r = 0; r < CPL; ++r) { c.bref[r] = c.xref[r]; c.bw[r] = 0.0f; }
-        run_steps<LPC, CPL, PB200_RECORD_NONE>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
-                                               (uint32_t)s.steps_per_iteration, (float)st.temperature,
-                                               (float)st.step_size, lam, c, ws, rc);
+        run_steps<LPC, CPL, PB200_RECORD_NONE, ZBUF>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
+                                                     (uint32_t)s.steps_per_iteration, (float)st.temperature,
+                                                     (float)st.step_size, lam, c, ws, rc, zrow);
         // set_bestfit: positions are materialised, the reported chi^2 is re-evaluated in FP64 at them
         materialise<LPC, CPL>(lt_pt, gl, c.bref, c.bw, ws, bx);
         materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
@@ -664,6 +706,34 @@ moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ w, long
     }
 }
 
+// Stand-alone generator of the samplers' variate stream: one thread per (chain, Philox block, slot) makes the one
+// Philox-4x32-10 call whose four words become the four normals of coordinate `slot` in steps 4*blk .. 4*blk+3 (or,
+// for slot == n, the four accept variates) and stores them as ONE float4.  Embarrassingly parallel, no idle lanes,
+// 16-byte coalesced stores; the annealing kernel then streams them back (fetch_block).  Same device functions as
+// the inline path, so the numbers are bit-identical.
+__global__ void __launch_bounds__(256)
+variates_kernel(const uint32_t* __restrict__ chain_id, int n_chains, int n, int npad, int nb, uint32_t blk0,
+                uint32_t k0, uint32_t k1, float4* __restrict__ out) {
+    const long long total = (long long)n_chains * nb * (n + 1);
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int slot = (int)(idx % (n + 1));
+        const long long rest = idx / (n + 1);
+        const int b = (int)(rest % nb), chain = (int)(rest / nb);
+        uint32_t w[4];
+        philox4x32_10(blk0 + (uint32_t)b, slot == n ? kAcceptSlot : (uint32_t)slot, __ldg(chain_id + chain), 0u, k0, k1,
+                      w);
+        float4 v;
+        if (slot < n) {
+            box_muller(w[0], w[1], v.x, v.y);
+            box_muller(w[2], w[3], v.z, v.w);
+        } else {
+            v = make_float4(exp_variate(w[0]), exp_variate(w[1]), exp_variate(w[2]), exp_variate(w[3]));
+        }
+        out[((size_t)chain * nb + b) * (npad + 1) + (slot == n ? npad : slot)] = v;
+    }
+}
+
 __global__ void rng_kernel(uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t step0, int n_steps, int n,
                            float* __restrict__ out_z, float* __restrict__ out_e) {
     // one warp; CPL = 8 covers every n <= 256 with the production draw_block
@@ -787,9 +857,54 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
     const int per_cta = kWarpsPerCta * (32 / lanes);
     const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
-                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1)));
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, false><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
+                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");
+}
+
+int64_t pb200_variates_bytes(int32_t npad, int32_t n_chains, uint32_t step_begin, int32_t n_steps) {
+    if (n_steps <= 0 || n_chains <= 0) return 0;
+    const int64_t nb = (int64_t)((step_begin + (uint32_t)n_steps - 1u) >> 2) - (int64_t)(step_begin >> 2) + 1;
+    return (int64_t)n_chains * nb * (npad + 1) * (int64_t)sizeof(float4);
+}
+
+int pb200_variates_fill(const pb200_problem* prob, const pb200_chains* chains, uint32_t step_begin, int32_t n_steps,
+                        uint64_t seed, void* zbuf, void* stream) {
+    if (validate(prob)) return 1;
+    if (!chains || !zbuf) return fail("variates_fill: NULL argument");
+    if (chains->n_chains <= 0 || n_steps <= 0) return 0;
+    const uint32_t blk0 = step_begin >> 2;
+    const int nb = (int)(((step_begin + (uint32_t)n_steps - 1u) >> 2) - blk0 + 1u);
+    const long long total = (long long)chains->n_chains * nb * (prob->n + 1);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
+    variates_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chains->chain_id, chains->n_chains, prob->n, prob->npad,
+                                                             nb, blk0, (uint32_t)seed, (uint32_t)(seed >> 32),
+                                                             (float4*)zbuf);
+    return check_cuda(cudaGetLastError(), "variates_kernel launch");
+}
+
+int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                              const pb200_records* rec, uint32_t step_begin, const void* zbuf,
+                              int32_t lanes_per_chain, void* stream) {
+    if (validate(prob)) return 1;
+    if (!chains || !sched || !rec || !zbuf) return fail("anneal_run_streamed: NULL argument");
+    if (chains->n_chains <= 0) return 0;
+    if (sched->steps_per_iteration <= 0) return fail("anneal_run_streamed: steps_per_iteration must be > 0");
+    if (sched->step_mode < 0 || sched->step_mode > 2) return fail("anneal_run_streamed: unknown step_mode");
+    if (!rec->best_loglkl || !rec->last_loglkl || !rec->temperature || !rec->step_size || !rec->accepted)
+        return fail("anneal_run_streamed: records have NULL device pointers");
+    if (rec->iter_stride < chains->n_chains) return fail("anneal_run_streamed: records iter_stride < n_chains");
+    int lanes;
+    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int per_cta = kWarpsPerCta * (32 / lanes);
+    const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
+    const uint32_t blk0 = step_begin >> 2;
+    const int nb = (int)(((step_begin + (uint32_t)sched->steps_per_iteration - 1u) >> 2) - blk0 + 1u);
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, true><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
+                                                    *prob, *chains, *sched, *rec, 1, 0u, 0u, (const float4*)zbuf, nb,
+                                                    step_begin)));
+    return check_cuda(cudaGetLastError(), "anneal_kernel (streamed) launch");
 }
 
 int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,

@@ -165,6 +165,28 @@ def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, 
                                            _stream_ptr(stream)))
 
 
+def variates_buffer(problem, n_chains, n_steps):
+    """Device buffer large enough for the variate stream of `n_steps` steps of `n_chains` chains at any alignment."""
+    nbytes = capi.lib().pb200_variates_bytes(int(problem.npad), int(n_chains), 3, int(n_steps))
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=problem.device)
+
+
+def variates_fill(problem, chains: ChainBatch, step_begin, n_steps, seed, zbuf, stream=None):
+    """Generate the normals / accept variates of steps [step_begin, step_begin + n_steps) of every chain into zbuf."""
+    _count()
+    capi.check(capi.lib().pb200_variates_fill(C.byref(problem.c), C.byref(chains.c), int(step_begin), int(n_steps),
+                                              C.c_uint64(seed), capi.ptr(zbuf), _stream_ptr(stream)))
+
+
+def anneal_run_streamed(problem, chains: ChainBatch, schedule, records: Records, step_begin, zbuf, stream=None,
+                        lanes=0):
+    """One annealing iteration reading its variates from zbuf (see pb200_anneal_run_streamed)."""
+    _count()
+    capi.check(capi.lib().pb200_anneal_run_streamed(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
+                                                    C.byref(records.c), int(step_begin), capi.ptr(zbuf), int(lanes),
+                                                    _stream_ptr(stream)))
+
+
 def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None, lanes=0):
     accepted = torch.zeros(chains.n_chains, dtype=torch.int32, device=problem.device)
     _count()

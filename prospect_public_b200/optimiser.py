@@ -98,6 +98,13 @@ class SimulatedAnnealing:
                                       n_alloc=self.b_alloc)
         self.lanes = int(s.get('lanes_per_chain', 0))
         self.seed = int(s.get('seed', 0))
+        self.step_counter = 0                 # MH steps taken so far by every live chain (they advance in lockstep)
+        # streamed=True generates each iteration's variates with the stand-alone generator kernel on a side stream.
+        # Measured on B200 (profiles/README.md) it is SLOWER than the fused kernel at every batch size tried: the fused
+        # kernel hides its RNG instructions in the stall cycles of the latency-bound chain updates, and per-iteration
+        # launches re-synchronise all chains.  Kept as a tested alternative (bit-identical results), off by default.
+        self.streamed = bool(s.get('streamed', False))
+        self._zbufs = None
         self.iterations_done = int(s.get('iteration_number', 0))
         self.bestfit = None
         self._gatherer = None
@@ -113,6 +120,38 @@ class SimulatedAnnealing:
         engine.anneal_run(self.problem, self.batch, self.schedule, self.records, n_iterations, self.seed, stream,
                           self.lanes)
         self.iterations_done += n_iterations
+        self.step_counter += n_iterations * self.schedule.steps_per_iteration
+
+    def optimise_streamed(self, n_iterations):
+        """`n_iterations` iterations, one launch each, with the variate stream of iteration k+1 generated on a side
+        stream (variates_kernel: fully parallel Philox + Box-Muller) while iteration k's chains advance: random-number
+        generation is ~60 % of the fused kernel's instructions but independent of the chain state, the chain
+        updates are latency-bound -- two kernels in flight fill the machine with either.  Double-buffered."""
+        import torch
+        from . import engine
+        steps = self.schedule.steps_per_iteration
+        if self._zbufs is None:
+            self._zbufs = [engine.variates_buffer(self.problem, self.n_chains, steps) for _ in range(2)]
+            self._gen_stream = torch.cuda.Stream(device=self.problem.device)
+            self._ev_gen = [torch.cuda.Event() for _ in range(2)]
+            self._ev_free = [torch.cuda.Event() for _ in range(2)]
+        comp = torch.cuda.current_stream()
+        self._gen_stream.wait_stream(comp)
+        for k in range(n_iterations):
+            b = k % 2
+            t0 = self.step_counter
+            with torch.cuda.stream(self._gen_stream):
+                if k >= 2:
+                    self._gen_stream.wait_event(self._ev_free[b])
+                engine.variates_fill(self.problem, self.batch, t0, steps, self.seed, self._zbufs[b])
+                self._ev_gen[b].record(self._gen_stream)
+            comp.wait_event(self._ev_gen[b])
+            engine.anneal_run_streamed(self.problem, self.batch, self.schedule, self.records, t0, self._zbufs[b],
+                                       lanes=self.lanes)
+            self._ev_free[b].record(comp)
+            self.iterations_done += 1
+            self.step_counter += steps
+            yield self.iterations_done - 1
 
     def set_bestfit(self, iteration=None):
         """Host view of one iteration's records: loglkl, acceptance_rate, accepted_steps, position per chain
@@ -159,6 +198,10 @@ class SimulatedAnnealing:
         (global_records), which keeps the per-boundary collective latency-sized."""
         import torch
         if self.world == 1 or not gather:
+            if self.streamed and iterations_per_launch is None:
+                for _ in self.optimise_streamed(n_iterations):
+                    pass
+                return None
             per = n_iterations if iterations_per_launch is None else iterations_per_launch
             done = 0
             while done < n_iterations:
@@ -173,9 +216,13 @@ class SimulatedAnnealing:
             self.gathered = torch.zeros((self.max_rows, self.world, self.records.scalar_len), dtype=torch.float64,
                                         device=self.problem.device)
         compute = torch.cuda.current_stream()
+        iterate = self.optimise_streamed(n_iterations) if self.streamed else None
         for _ in range(n_iterations):
             k = self.iterations_done
-            self.optimise(1)
+            if iterate is not None:
+                next(iterate)
+            else:
+                self.optimise(1)
             ev = torch.cuda.Event()
             ev.record(compute)
             with torch.cuda.stream(self._comm_stream):

@@ -92,7 +92,8 @@ def test_loglkl_batch_matches_reference(d):
     assert np.allclose(ll0.cpu().numpy(), init_ll, rtol=1e-12, atol=0)
 
 
-def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED, lanes=32):
+def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED, lanes=32,
+                   streamed=False):
     """Run B = reps * P chains on the GPU and through the scalar model with the GPU's variates."""
     prob = DeviceProblem(hp, DEV)
     p_count = hp.n_points
@@ -107,8 +108,14 @@ def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode
                                  s.get('tol'))
     recs = engine.Records(prob, b, n_iter)
     done = 0
+    zbuf = engine.variates_buffer(prob, b, s['S']) if streamed else None
     for chunk in launches:
-        engine.anneal_run(prob, chains, sched, recs, chunk, SEED, lanes=lanes)
+        if streamed:        # one launch per iteration, variates pre-generated by the stand-alone generator kernel
+            for it in range(done, done + chunk):
+                engine.variates_fill(prob, chains, it * s['S'], s['S'], SEED, zbuf)
+                engine.anneal_run_streamed(prob, chains, sched, recs, it * s['S'], zbuf, lanes=lanes)
+        else:
+            engine.anneal_run(prob, chains, sched, recs, chunk, SEED, lanes=lanes)
         done += chunk
     assert done == n_iter
     torch.cuda.synchronize()
@@ -154,6 +161,19 @@ def test_anneal_bit_exact_vs_model_replay(d, lanes):
     out, _ = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 4, [4], lanes=lanes)
     ar = (1 + out['accepted']) / 251.0
     assert 0.02 < ar.mean() < 0.8
+
+
+@pytest.mark.parametrize('lanes', [32, 16, 8])
+def test_streamed_variates_path_bit_exact(lanes):
+    """pb200_variates_fill + pb200_anneal_run_streamed == the fused kernel == the model (S = 250 is not a multiple of
+    4, so iterations start at every block alignment)."""
+    hp, starts, init_ll, values, k = toy_profile_problem(30, points=[0, 9, 17, 31])
+    a, fa = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 5, [5], lanes=lanes, streamed=True)
+    b, fb = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 5, [5], lanes=lanes, streamed=False)
+    for key in a:
+        assert np.array_equal(a[key], b[key]), key
+    for key in fa:
+        assert np.array_equal(fa[key], fb[key]), key
 
 
 def test_anneal_launch_partitioning_is_invisible():
