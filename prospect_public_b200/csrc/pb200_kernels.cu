@@ -82,7 +82,8 @@ __device__ __forceinline__ void record_row(RecCursor& rc, const double (&x)[CPL]
 
 // Registers of one chain, spread over the LPC lanes of its group.
 //   position = xref + Lt * w   (w: whitened displacement accumulated since xref was last materialised)
-//   best     = bref + Lt * bw
+//   best     = (best_rel ? xref : bref) + Lt * bw      (bref is only written when xref moves away from under a
+//                                                        best point, so a new best costs CPL moves, not 3*CPL)
 template <int CPL>
 struct ChainState {
     double xref[CPL], bref[CPL];
@@ -90,6 +91,7 @@ struct ChainState {
     double ll, best_ll;
     float m2;             // squared whitened radius around xref that provably stays inside the prior box
     int32_t nacc;
+    bool best_rel;        // the best point is expressed relative to the CURRENT xref
 };
 
 // ----------------------------------------------------------------------------------------------
@@ -138,7 +140,12 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
             acc = lik && !(exact && outside);
             if (reref) {
 #pragma unroll
-                for (int r = 0; r < CPL; ++r) { c.xref[r] = xt[r]; wt[r] = 0.0f; }
+                for (int r = 0; r < CPL; ++r) {
+                    if (c.best_rel) c.bref[r] = c.xref[r];      // the best point stays where it was
+                    c.xref[r] = xt[r];
+                    wt[r] = 0.0f;
+                }
+                c.best_rel = false;
             }
             const float m2n = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
             if (reref) c.m2 = m2n;
@@ -153,8 +160,9 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
             c.nacc += 1;
             if (c.ll < c.best_ll) {
                 c.best_ll = c.ll;
+                c.best_rel = true;
 #pragma unroll
-                for (int r = 0; r < CPL; ++r) { c.bw[r] = c.w[r]; c.bref[r] = c.xref[r]; }
+                for (int r = 0; r < CPL; ++r) c.bw[r] = c.w[r];
             }
         }
     }
@@ -238,22 +246,29 @@ __device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const 
     const bool any = acc[0] || acc[1] || acc[2] || acc[3];
     const float bnd = __fadd_rn(__fsqrt_rn(v[15]), __fmul_rn(__fadd_rn(sf, sf), __fsqrt_rn(v[14])));
     if (any && !(__fmul_rn(bnd, bnd) <= c.m2)) return true;
+    // scalar pass: running loglkl, accept count, and which step (if any) sets a new best
+    int kb = -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         if (acc[k]) {
-#pragma unroll
-            for (int r = 0; r < CPL; ++r) {
-                c.w[r] = __fmaf_rn(sf, z[r][k], c.w[r]);
-                c.gf[r] = __fmaf_rn(__fadd_rn(c.hl[r], c.hl[r]), z[r][k], c.gf[r]);
-            }
             c.ll = __dadd_rn(c.ll, (double)delta[k]);
             c.nacc += 1;
-            if (c.ll < c.best_ll) {
-                c.best_ll = c.ll;
-#pragma unroll
-                for (int r = 0; r < CPL; ++r) { c.bw[r] = c.w[r]; c.bref[r] = c.xref[r]; }
-            }
+            if (c.ll < c.best_ll) { c.best_ll = c.ll; kb = k; }
         }
+    }
+    if (kb >= 0) c.best_rel = true;
+    // vector pass: predicated, branch-free
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const float h2 = __fadd_rn(c.hl[r], c.hl[r]);
+        float w = c.w[r], g = c.gf[r], b = c.bw[r];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            w = acc[k] ? __fmaf_rn(sf, z[r][k], w) : w;
+            g = acc[k] ? __fmaf_rn(h2, z[r][k], g) : g;
+            b = (kb == k) ? w : b;
+        }
+        c.w[r] = w; c.gf[r] = g; c.bw[r] = b;
     }
     return false;
 }
@@ -417,11 +432,16 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
         c.best_ll = c.ll;
         c.nacc = 0;
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) { c.bref[r] = c.xref[r]; c.bw[r] = 0.0f; }
+        for (int r = 0; r < CPL; ++r) c.bw[r] = 0.0f;
+        c.best_rel = true;
         run_steps<LPC, CPL, PB200_RECORD_NONE, ZBUF>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
                                                      (uint32_t)s.steps_per_iteration, (float)st.temperature,
                                                      (float)st.step_size, lam, c, ws, rc, zrow);
         // set_bestfit: positions are materialised, the reported chi^2 is re-evaluated in FP64 at them
+        if (c.best_rel) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) c.bref[r] = c.xref[r];
+        }
         materialise<LPC, CPL>(lt_pt, gl, c.bref, c.bw, ws, bx);
         materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
         double unused[CPL];
@@ -507,6 +527,7 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
     c.nacc = 0;
 #pragma unroll
     for (int r = 0; r < CPL; ++r) { c.bref[r] = c.xref[r]; c.bw[r] = 0.0f; }
+    c.best_rel = true;
 
     RecCursor rc{};
     if (REC != PB200_RECORD_NONE) {
