@@ -256,3 +256,58 @@ def test_reanneal_continues_from_the_best_points(tmp_path):
     assert rec_disk.best_loglkl.shape == (45, 30)
     prof = load_profile(out_dir)
     assert np.allclose(prof['-loglkl'], ll_second, rtol=1e-9)
+
+
+def test_start_from_profile_and_explicit_gaussian_kernel(tmp_path):
+    """N4: `start_from_profile` (+ covmat from the MCMC) starts every value from the nearest old bestfit
+    (initialise_optimiser_task.py:39-62); and the explicit `function: gaussian` kernel-settings file
+    (input/example_toy/kernel_settings/kernel_gauss.yaml) works through the same CUDA kernel."""
+    import yaml
+    paths, k = _inputs(tmp_path, 20)
+    first = run(annealing_yaml(paths, str(tmp_path / 'a'), temperature_range=[0.1, 1.0e-5], max_iterations=25))
+    old_txt = str(tmp_path / 'a' / 'profile' / 'x2.txt')
+    second = run(annealing_yaml(paths, str(tmp_path / 'b'), start_from_profile=old_txt,
+                                values='np.linspace(-0.9, 1.9, 8)', temperature_range=[1.0e-4, 1.0e-7],
+                                max_iterations=15, step_size_adaptive_initial=0.01))
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, np.linspace(-0.9, 1.9, 8))
+    assert np.max(2 * np.abs(second['profile']['loglkls'] - cf)) <= 1e-3
+    # the start points are old bestfits (not bin bestfits): close to the old profile's positions
+    old = load_profile(str(tmp_path / 'a'))
+    near = np.argmin(np.abs(old['x2'][:, None] - np.linspace(-0.9, 1.9, 8)[None, :]), axis=0)
+    assert np.allclose(second['record'].initial_position[:, 0], old['x1'][near])
+
+    kfile = tmp_path / 'kernel_gauss.yaml'
+    with open(kfile, 'w') as f:
+        yaml.dump({'function': 'gaussian', 'dimension': 2, 'param_dict': {'x1': [-5.0, 5.0], 'x2': [-5.0, 5.0]},
+                   'means': {'x1': 1.0, 'x2': 1.0}, 'covmat': [[0.25, 0.1], [0.1, 0.5]]}, f)
+    y = annealing_yaml(paths, str(tmp_path / 'g'), jobtype='global_optimisation', repetitions=64,
+                       start_from_mcmc=None, start_from_position=[3.0, -2.0],
+                       start_from_covmat=[[0.25, 0.1], [0.1, 0.5]], temperature_range=[1.0, 1.0e-8],
+                       max_iterations=40, step_size_adaptive_initial=1.0)
+    y['kernel']['param'] = str(kfile)
+    res = run(y)
+    cb = res['bestfits']['chain_best'][:, 0]
+    assert cb.min() >= -1e-12 and np.median(cb) < 1e-6
+    rec = res['record']
+    best_rep = res['bestfits']['best_rep']
+    x = rec.best_x[res['bestfits']['chain_iter'][best_rep, 0], best_rep]
+    assert np.allclose(x, [1.0, 1.0], atol=1e-3)
+
+
+def test_ignore_prior_lifts_the_box(tmp_path):
+    """kernel.ignore_prior: true (base_kernel.py:15-16) -- chains may leave [-2.5, 2.5]."""
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.mcmc import initialise_mcmc
+    paths, k = _inputs(tmp_path, 20)
+    for ignore, expect_outside in ((False, False), (True, True)):
+        y = mcmc_yaml(paths, str(tmp_path / f'o{ignore}'), n_chains=256, steps=400, write=False,
+                      temperature=1.0e6, step_size=3.0)
+        y['kernel']['ignore_prior'] = ignore
+        cfg = Configuration(y)
+        kernel = initialise_kernel(cfg.kernel, None, 0)
+        sampler = initialise_mcmc(cfg.mcmc, kernel, seed=5, record='thinned', thin=400)
+        sampler.run_steps(400)
+        x, _, _, cnt = sampler.samples_numpy()
+        assert np.all(cnt == 1)
+        outside = np.any(np.abs(x[:, 0, :]) > 2.5)
+        assert outside == expect_outside

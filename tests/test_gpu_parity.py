@@ -392,3 +392,14 @@ def test_mh_sample_overflow_is_reported():
     smp = engine.Samples(prob, 2, 8, capi.RECORD_THINNED, 1)
     engine.mh_run(prob, chains, 50, SEED, smp)
     assert np.all(smp.count.cpu().numpy() == 50)            # > capacity: rows were dropped, never written OOB
+
+
+def test_secant_multiplier_failure_path_stops_the_chain():
+    """'adaptive' multiplier with an interval that contains every acceptance rate: the reference hits its
+    unbound-local (optimiser.py:99-103) after the first iteration; here the chain gets status FAILED, keeps its
+    first record and never runs again -- identically in the kernel and in the model."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[1, 5])
+    out, fin = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(interval=(0.0, 1.0)), 4, [2, 2],
+                              mode=capi.STEP_ADAPTIVE_SECANT, lanes=16)
+    assert np.all(fin['status'] == capi.FAILED) and np.all(fin['iteration'] == 1)
+    assert np.all(out['accepted'][0] >= 0) and np.all(out['accepted'][1:] == -1)
