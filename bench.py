@@ -330,6 +330,22 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = chain_steps_per_step * e2e_steps / float(t.item())
 
+    # ---------------- time-to-profile: yaml -> run() -> profile/<p>.txt (+ snapshot) on disk, once ----------------
+    ttp = None
+    if args.workload != 'profile256':
+        from prospect_public_b200.run import run as run_job
+        pkw = dict(workload_profile_kw('profile30', world)[1])
+        ycfg = annealing_yaml(toy_inputs(tmp)[0], os.path.join(tmp, 'ttp'), jobtype='profile', write=True, **pkw)
+        barrier()
+        t0 = time.perf_counter()
+        res = run_job(ycfg)
+        barrier()
+        ttp = {'seconds': res.get('time_to_profile_s', time.perf_counter() - t0),
+               'seconds_incl_snapshot': time.perf_counter() - t0, 'loop_seconds': res['loop_seconds'],
+               'chain_steps': int(res['chain_steps']),
+               'job': f'30-D toy profile, {32 * world} values x 256 repetitions x 20 iterations x 250 steps, '
+                      'seconds = yaml read to profile/x2.txt written; the PROSPECT-compatible config.pkl/state.pkl follow'}
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and rows is not None:
         from oracle import reference_port as rp
@@ -355,7 +371,8 @@ def main():
                 'clocks': sampler.summary(),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'steps': e2e_steps, 'warmup': e2e_warm},
-                'gpu_launches': gpu_launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline}
+                'gpu_launches': gpu_launches, 'roofline': roofline, 'cpu_baseline': cpu_baseline,
+                'time_to_profile': ttp}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

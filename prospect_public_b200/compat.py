@@ -140,7 +140,7 @@ def export_reference_snapshot(config, rec, folder, compact=False):
                 c = rep * n_pts + p
                 its = np.nonzero(ran[:, c])[0]
                 if compact and len(its):
-                    its = np.unique([ci[rep, p], its[-1]])
+                    its = sorted({int(ci[rep, p]), int(its[-1])})
                 for k in its:
                     pos = {nm: [float(rec.best_x[k, c, i])] for i, nm in enumerate(names)}
                     settings = {

@@ -59,7 +59,9 @@ def run(user_inp, quiet=True):
         out = run_mcmc(config)
     else:
         out = run_annealing(config)
-    out['time_to_result_s'] = time.perf_counter() - t_start
+    out['time_to_result_s'] = time.perf_counter() - t_start          # incl. the snapshot pickles
+    if 't_results_written' in out:
+        out['time_to_profile_s'] = out['t_results_written'] - t_start  # yaml read -> result files written
     out['config'] = config
     return out
 
@@ -143,6 +145,7 @@ def write_outputs(config, rec, sa=None):
         else:
             cb, ci = rec.per_chain_best()
             result['bestfits'] = {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}
+    result['t_results_written'] = time.perf_counter()      # profile/<p>.txt (or results.txt) is on disk here
     if config.io.write:
         dump_snapshot(config, rec)
     return result
