@@ -290,7 +290,7 @@ def main():
             pass
         traffic = None                                 # DRAM bytes per launch from the committed ncu capture
         try:
-            with open(os.path.join(ROOT, 'profiles', 'r01_global30_lanes16.json')) as f:
+            with open(os.path.join(ROOT, 'profiles', 'r01_final_global30_lanes8.json')) as f:
                 met = json.load(f)['metrics']
             if args.workload == 'global30':
                 traffic = sum(float(met[k].split()[0]) * {'Mbyte': 1e6, 'Kbyte': 1e3, 'byte': 1.0, 'Gbyte': 1e9}[

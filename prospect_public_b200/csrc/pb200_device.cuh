@@ -106,9 +106,20 @@ __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t ch
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
         const int coord = gl + LPC * r;
+#ifdef PB200_EXPERIMENT_FAKE_RNG   /* timing experiment only: cheap stand-in variates, results are meaningless */
+        {
+            const uint32_t hsh = blk * 2654435761u + (uint32_t)coord * 40503u + chain_id * 97u + k0;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                w[k] = (hsh >> k) * 0x9E3779B9u | 0x01000000u;
+                z[r][k] = __uint_as_float(0x3f800000u | ((hsh * (2u * k + 3u)) & 0x7fffffu)) - 1.5f;
+            }
+        }
+#else
         philox4x32_10(blk, coord == n ? kAcceptSlot : (uint32_t)coord, chain_id, 0u, k0, k1, w);
         box_muller(w[0], w[1], z[r][0], z[r][1]);
         box_muller(w[2], w[3], z[r][2], z[r][3]);
+#endif
         if (coord >= n) { z[r][0] = z[r][1] = z[r][2] = z[r][3] = 0.0f; }
         if (r == acc_r) {
 #pragma unroll
@@ -120,6 +131,91 @@ __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t ch
 #pragma unroll
         for (int k = 0; k < 4; ++k) e[k] = exp_variate(w[k]);
     }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Shared-memory ring between a PRODUCER warp (Philox + Box-Muller) and the CONSUMER warp that advances the chains
+// (anneal_ws_kernel).  One slot = the variates of one Philox block for the 32 lanes of the pair: float4 [CPL][32]
+// normals (lane-major, so both sides touch their own 16 bytes: conflict-free LDS.128 / STS.128) + float4 [G] accept
+// variates.  full[slot] / empty[slot] are mbarriers with 32 arrivals (every lane arrives for its own accesses).
+// ----------------------------------------------------------------------------------------------
+constexpr int kRingDepth = 4;
+
+__device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0u;
+}
+
+struct Ring {
+    uint32_t data, full, empty, stop;   // shared-space addresses: slots, mbarriers [kRingDepth] each, stop word
+    uint32_t count;                     // blocks produced / consumed so far by this side
+};
+
+template <int CPL>
+__device__ __forceinline__ constexpr int ring_slot_bytes() { return (CPL + 1) * 32 * 16; }
+
+// Consumer side: wait for the next block, copy it to registers, hand the slot back.  A producer that never
+// delivers would hang the GPU, so the wait is bounded and traps (the launch then fails loudly).
+template <int LPC, int CPL>
+__device__ __forceinline__ void ring_fetch(Ring& rg, int lane, int gi, float (&z)[CPL][4], float (&e)[4]) {
+    const uint32_t slot = rg.count % kRingDepth, parity = (rg.count / kRingDepth) & 1u;
+    const uint32_t bar = rg.full + 8u * slot;
+    if (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
+        const long long t0 = clock64();
+        while (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
+            if (clock64() - t0 > 8000000000LL) __trap();
+        }
+    }
+    const uint32_t base = rg.data + slot * (uint32_t)ring_slot_bytes<CPL>();
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(z[r][0]), "=f"(z[r][1]), "=f"(z[r][2]), "=f"(z[r][3])
+                     : "r"(base + (uint32_t)(r * 32 + lane) * 16u));
+    }
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(e[0]), "=f"(e[1]), "=f"(e[2]), "=f"(e[3])
+                 : "r"(base + (uint32_t)(CPL * 32 + gi) * 16u));
+    mbar_arrive(rg.empty + 8u * slot);
+    rg.count += 1;
+}
+
+// Producer side.  Returns false when the consumer has raised the stop word (it left its iteration loop early).
+template <int LPC, int CPL>
+__device__ __forceinline__ bool ring_store(Ring& rg, int lane, int gi, int gl, const float (&z)[CPL][4],
+                                           const float (&e)[4]) {
+    const uint32_t slot = rg.count % kRingDepth, parity = ((rg.count / kRingDepth) & 1u) ^ 1u;
+    const uint32_t bar = rg.empty + 8u * slot;
+    while (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
+        uint32_t stop;
+        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(stop) : "r"(rg.stop));
+        if (__any_sync(kFull, stop != 0u)) return false;
+    }
+    const uint32_t base = rg.data + slot * (uint32_t)ring_slot_bytes<CPL>();
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(r * 32 + lane) * 16u),
+                     "f"(z[r][0]), "f"(z[r][1]), "f"(z[r][2]), "f"(z[r][3]) : "memory");
+    }
+    if (gl == 0) {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(base + (uint32_t)(CPL * 32 + gi) * 16u),
+                     "f"(e[0]), "f"(e[1]), "f"(e[2]), "f"(e[3]) : "memory");
+    }
+    mbar_arrive(rg.full + 8u * slot);
+    rg.count += 1;
+    return true;
 }
 
 // ----------------------------------------------------------------------------------------------

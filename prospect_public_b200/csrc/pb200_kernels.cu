@@ -293,13 +293,19 @@ __device__ __forceinline__ void fetch_block(const float4* __restrict__ row, int 
     e[0] = ev.x; e[1] = ev.y; e[2] = ev.z; e[3] = ev.w;
 }
 
-template <int LPC, int CPL, int REC, bool ZBUF>
+// Where the variates of a Philox block come from.
+constexpr int kSrcPhilox = 0;   // drawn in place by the warp that uses them
+constexpr int kSrcStream = 1;   // pre-generated by variates_kernel into global memory (one iteration per launch)
+constexpr int kSrcRing = 2;     // produced by the partner warp into a shared-memory ring (anneal_ws_kernel)
+
+template <int LPC, int CPL, int REC, int SRC>
 __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
                                                 int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
                                                 uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
                                                 ChainState<CPL>& c, float* ws, RecCursor& rc,
-                                                const float4* __restrict__ zrow) {
+                                                const float4* __restrict__ zrow, Ring& ring) {
     constexpr int NPAD = LPC * CPL;
+    constexpr bool ZBUF = SRC == kSrcStream;
     float z[CPL][4], e[4], zk[CPL];
     float zn[ZBUF ? CPL : 1][4], en[4];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
@@ -312,13 +318,21 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             const uint32_t nxt = (t >> 2) + 1u - blk0;
             if (((t >> 2) + 1u) << 2 < t_begin + n_steps)
                 fetch_block<LPC, CPL>(zrow + (size_t)nxt * (NPAD + 1), p.n, gl, zn, en);
+        } else if constexpr (SRC == kSrcRing) {
+            ring_fetch<LPC, CPL>(ring, gi * LPC + gl, gi, z, e);
         } else {
             draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
         }
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
         bool todo = live, cnt_done = false;
         if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && off == 0u && cnt == 4u) {
+#ifdef PB200_EXPERIMENT_FAKE_UPDATE   /* timing experiment only: consume the variates with no chain update */
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) c.w[r] += (z[r][0] + z[r][1]) * (z[r][2] + z[r][3]) * e[r & 3];
+            todo = false;
+#else
             todo = block_step<LPC, CPL>(live, Tf, sf, z, e, c);
+#endif
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }
 #pragma unroll 1
@@ -342,29 +356,32 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
     }
 }
 
-template <int LPC, int CPL, int REC, bool ZBUF = false>
+template <int LPC, int CPL, int REC, int SRC = kSrcPhilox>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
-                                          ChainState<CPL>& c, float* ws, RecCursor& rc,
+                                          ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring,
                                           const float4* __restrict__ zrow = nullptr) {
     asm volatile("" : "+f"(Tf), "+f"(sf));      // keep the FP32 copies live instead of re-converting the doubles
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
     for (int r = 0; r < CPL; ++r) c.hl[r] = __fmul_rn(half_s, lam[r]);
-    // chains of one warp normally advance in lockstep; if their step counters differ modulo 4 every alignment
-    // class gets its own pass so that each chain still sees its own block structure
-    const uint32_t lead = __shfl_sync(kFull, t_begin, 0) & 3u;
-    if (__all_sync(kFull, (t_begin & 3u) == lead)) {
-        run_steps_class<LPC, CPL, REC, ZBUF>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
-                                             sf, c, ws, rc, zrow);
+    // chains of one warp normally advance in lockstep; if the step counters of its LIVE chains differ modulo 4 every
+    // alignment class gets its own pass so that each chain still sees its own block structure
+    const unsigned lm = __ballot_sync(kFull, live);
+    if (SRC != kSrcRing && lm == 0u) return;
+    const uint32_t lead = __shfl_sync(kFull, t_begin, lm ? __ffs(lm) - 1 : 0) & 3u;
+    if (SRC == kSrcRing || __all_sync(kFull, !live || (t_begin & 3u) == lead)) {
+        // (ring: the kernel only pairs a producer with warps whose live chains share one alignment class)
+        run_steps_class<LPC, CPL, REC, SRC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
+                                            sf, c, ws, rc, zrow, ring);
     } else {
 #pragma unroll 1
         for (uint32_t a = 0; a < 4u; ++a) {
-            const bool mine = (t_begin & 3u) == a;
+            const bool mine = live && (t_begin & 3u) == a;
             if (__any_sync(kFull, mine))
-                run_steps_class<LPC, CPL, REC, ZBUF>(p, pt, lt_pt, gl, gi, live && mine, k0, k1, chain_id, t_begin, a,
-                                                     n_steps, Tf, sf, c, ws, rc, zrow);
+                run_steps_class<LPC, CPL, REC, SRC>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
+                                                    n_steps, Tf, sf, c, ws, rc, zrow, ring);
         }
     }
 }
@@ -382,19 +399,22 @@ __device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, c
 
 
 // ----------------------------------------------------------------------------------------------
-// Fused annealing kernel: n_iter iterations x S steps per launch, one lane group per chain.
-// ----------------------------------------------------------------------------------------------
-// ZBUF = true: ONE iteration whose variates were pre-generated by variates_kernel into `zbuf`
+// Fused annealing: n_iter iterations x S steps per launch, one lane group per chain.  `warp_slot` is the index of
+// this warp among the warps that own chains, `stage_warp` its [G][NPAD] double staging rows in shared memory.
+// SRC = kSrcStream: ONE iteration whose variates were pre-generated by variates_kernel into `zbuf`
 // ([chain][nb][npad + 1] float4, first block = t_stream >> 2); all chains then share the step counter t_stream.
-template <int LPC, int CPL, bool ZBUF>
-__global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
-anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream) {
+// SRC = kSrcRing: the variates come from the partner warp through `ring` (anneal_ws_kernel).
+// ----------------------------------------------------------------------------------------------
+template <int LPC, int CPL, int SRC>
+__device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_chains& ch, const pb200_schedule& s,
+                                            const pb200_records& rec, int n_iter, uint32_t k0, uint32_t k1,
+                                            const float4* __restrict__ zbuf, int nb, uint32_t t_stream, int warp_slot,
+                                            double* stage_warp, Ring& ring) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
-    __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane / LPC, gl = lane % LPC;
-    const int slot = (blockIdx.x * kWarpsPerCta + wib) * G + gi;
-    if ((blockIdx.x * kWarpsPerCta + wib) * G >= ch.n_chains) return;         // whole warp idle
+    constexpr bool ZBUF = SRC == kSrcStream;
+    const int lane = threadIdx.x & 31, gi = lane / LPC, gl = lane % LPC;
+    const int slot = warp_slot * G + gi;
+    if (warp_slot * G >= ch.n_chains) return;         // whole warp idle
     const bool alive = slot < ch.n_chains;
     const int chain = alive ? slot : ch.n_chains - 1;
     SchedState st;
@@ -414,7 +434,7 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
     uint32_t t = ZBUF ? t_stream : ch.steps_done[chain];
     const float4* zrow = ZBUF ? zbuf + (size_t)chain * nb * (NPAD + 1) : nullptr;
     const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
-    double* qs = stage[wib][gi];
+    double* qs = stage_warp + gi * NPAD;
     float* ws = reinterpret_cast<float*>(qs);
 
     float lam[CPL];
@@ -434,9 +454,9 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
 #pragma unroll
         for (int r = 0; r < CPL; ++r) c.bw[r] = 0.0f;
         c.best_rel = true;
-        run_steps<LPC, CPL, PB200_RECORD_NONE, ZBUF>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
-                                                     (uint32_t)s.steps_per_iteration, (float)st.temperature,
-                                                     (float)st.step_size, lam, c, ws, rc, zrow);
+        run_steps<LPC, CPL, PB200_RECORD_NONE, SRC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
+                                                    (uint32_t)s.steps_per_iteration, (float)st.temperature,
+                                                    (float)st.step_size, lam, c, ws, rc, ring, zrow);
         // set_bestfit: positions are materialised, the reported chi^2 is re-evaluated in FP64 at them
         if (c.best_rel) {
 #pragma unroll
@@ -487,6 +507,106 @@ anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records 
             ch.steps_done[chain] = t;
         }
     }
+}
+
+template <int LPC, int CPL, bool ZBUF>
+__global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
+anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
+              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream) {
+    constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
+    const int wib = threadIdx.x >> 5;
+    Ring none{};
+    anneal_body<LPC, CPL, ZBUF ? kSrcStream : kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, zbuf, nb, t_stream,
+                                                          blockIdx.x * kWarpsPerCta + wib, &stage[wib][0][0], none);
+}
+
+// ----------------------------------------------------------------------------------------------
+// Warp-specialised variant for batches too small to fill the SMs with chain warps (a few warps per scheduler): the
+// chain update is one long dependent instruction chain per block of steps, the Philox + Box-Muller work is wide and
+// independent.  Every chain warp (consumer) gets a partner warp (producer) that draws its variates into a
+// shared-memory ring kRingDepth blocks ahead, so the scheduler always has an independent instruction stream to
+// issue from.  Same counters, same arithmetic, same results as anneal_kernel.  A pair whose live chains do not share
+// one step-counter alignment class falls back to drawing in place.
+// ----------------------------------------------------------------------------------------------
+#ifndef PB200_WS_PAIRS
+#define PB200_WS_PAIRS 2          // consumer/producer pairs per CTA
+#endif
+#ifndef PB200_WS_INTERLEAVE
+#define PB200_WS_INTERLEAVE 1     // 1: warps alternate consumer / producer; 0: consumers first
+#endif
+constexpr int kWsPairs = PB200_WS_PAIRS;
+// register budget: 128 per thread for npad = 32 (65536 / (128 * 64 * pairs) CTAs per SM), unconstrained above
+constexpr int ws_min_ctas(int npad) { return npad == 32 ? (8 / kWsPairs > 0 ? 8 / kWsPairs : 1) : 1; }
+
+template <int LPC, int CPL>
+__device__ __forceinline__ void produce_variates(int n, int n_iter, uint32_t steps, uint32_t k0, uint32_t k1,
+                                                 uint32_t chain_id, uint32_t t, uint32_t lead, int gi, int gl,
+                                                 Ring& ring) {
+    float z[CPL][4], e[4];
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+        uint32_t i = 0;
+        while (i < steps) {                     // mirrors run_steps_class: one block per pass, ragged head / tail
+            const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, steps - i);
+            draw_block<LPC, CPL>(k0, k1, chain_id, (t + i) >> 2, n, gl, z, e);
+            if (!ring_store<LPC, CPL>(ring, gi * LPC + gl, gi, gl, z, e)) return;
+            i += cnt;
+        }
+        t += steps;
+        lead = (lead + steps) & 3u;
+    }
+}
+
+template <int LPC, int CPL>
+__global__ void __launch_bounds__(64 * kWsPairs, ws_min_ctas(LPC * CPL))
+anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
+                 uint32_t k1) {
+    constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    __shared__ __align__(16) unsigned char slots[kWsPairs][kRingDepth][ring_slot_bytes<CPL>()];
+    __shared__ __align__(16) double stage[kWsPairs][G][NPAD];
+    __shared__ __align__(8) unsigned long long bars[kWsPairs][2 * kRingDepth];
+    __shared__ uint32_t stop[kWsPairs];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, gi = lane / LPC, gl = lane % LPC;
+    const int pair = PB200_WS_INTERLEAVE ? wib >> 1 : wib % kWsPairs;
+    const bool producer = PB200_WS_INTERLEAVE ? (wib & 1) != 0 : wib >= kWsPairs;
+    if (threadIdx.x < kWsPairs) {
+        for (int b = 0; b < 2 * kRingDepth; ++b) mbar_init(smem_addr(&bars[threadIdx.x][b]), 32u);
+        stop[threadIdx.x] = 0u;
+    }
+    const int warp_slot = blockIdx.x * kWsPairs + pair;
+    const bool idle = warp_slot * G >= ch.n_chains;
+    const int slot = warp_slot * G + gi;
+    const bool alive = !idle && slot < ch.n_chains;
+    const int chain = alive ? slot : ch.n_chains - 1;
+    const bool live = alive && ch.status[chain] == PB200_ACTIVE;
+    const uint32_t t = ch.steps_done[chain];
+    const uint32_t chain_id = ch.chain_id[chain];
+    __syncthreads();      // barriers initialised; both warps of a pair have read the same chain state
+    if (idle) return;
+    const unsigned lm = __ballot_sync(kFull, live);
+    const uint32_t lead_t = __shfl_sync(kFull, t, lm ? __ffs(lm) - 1 : 0);
+    const bool paired = lm != 0u && __all_sync(kFull, !live || (t & 3u) == (lead_t & 3u));
+    Ring ring;
+    ring.data = smem_addr(&slots[pair][0][0]);
+    ring.full = smem_addr(&bars[pair][0]);
+    ring.empty = smem_addr(&bars[pair][kRingDepth]);
+    ring.stop = smem_addr(&stop[pair]);
+    ring.count = 0u;
+    if (producer) {
+        if (paired)
+            produce_variates<LPC, CPL>(p.n, n_iter, (uint32_t)s.steps_per_iteration, k0, k1, chain_id,
+                                       live ? t : lead_t, lead_t & 3u, gi, gl, ring);
+        return;
+    }
+    if (paired)
+        anneal_body<LPC, CPL, kSrcRing>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot, &stage[pair][0][0],
+                                        ring);
+    else
+        anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot,
+                                          &stage[pair][0][0], ring);
+    __syncwarp();
+    if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ring.stop), "r"(1u) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -547,9 +667,11 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
         }
     }
     uint32_t done = 0;
+    Ring no_ring{};
     while (done < (uint32_t)n_steps) {
         const uint32_t chunk = min((uint32_t)n_steps - done, kResync);
-        run_steps<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc);
+        run_steps<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc,
+                                 no_ring);
         done += chunk;
         materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
         anchor<LPC, CPL>(p, pt, gl, x, c, qs);
@@ -849,6 +971,19 @@ static int resolve_lanes(int requested, int npad, int n_chains, int* out) {
     return 0;
 }
 
+// Producer warps (anneal_ws_kernel) pay while the chain warps alone leave the schedulers idle: measured on B200 for the
+// 8-lane geometry up to kWsMaxChains chains.  PB200_WS=0 / 1 forces the choice (A/B runs, tests).
+#ifndef PB200_WS_MAX_CHAINS
+#define PB200_WS_MAX_CHAINS 6144
+#endif
+static bool use_producer_warps(int lanes, int n_chains) {
+    if (const char* env = std::getenv("PB200_WS")) {
+        if (env[0] == '0') return false;
+        if (env[0] == '1') return true;
+    }
+    return lanes == 8 && n_chains <= PB200_WS_MAX_CHAINS;
+}
+
 #define PB200_DISPATCH_GEOMETRY(npad, lanes, CALL)                                   \
     switch ((npad) * 64 + (lanes)) {                                                 \
         case 32 * 64 + 32:  { constexpr int LPC = 32, CPL = 1; CALL; } break;        \
@@ -878,6 +1013,13 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
     const int per_cta = kWarpsPerCta * (32 / lanes);
     const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (use_producer_warps(lanes, chains->n_chains)) {
+        const int pairs = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);
+        const int ws_blocks = (pairs + kWsPairs - 1) / kWsPairs;
+        PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_ws_kernel<LPC, CPL><<<ws_blocks, 64 * kWsPairs, 0, st>>>(
+                                                        *prob, *chains, *sched, *rec, n_iter, k0, k1)));
+        return check_cuda(cudaGetLastError(), "anneal_ws_kernel launch");
+    }
     PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, false><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
                                                     *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");

@@ -152,11 +152,14 @@ def _toy_sched(**kw):
     return base
 
 
+@pytest.mark.parametrize('producer_warps', ['0', '1'])
 @pytest.mark.parametrize('lanes', [32, 16, 8])
 @pytest.mark.parametrize('d', [20, 30])
-def test_anneal_bit_exact_vs_model_replay(d, lanes):
+def test_anneal_bit_exact_vs_model_replay(d, lanes, producer_warps, monkeypatch):
     """K1-style schedule, all profile points x 3 repetitions, 4 iterations in one launch, for every lane-group
-    geometry (32 / 16 / 8 lanes per chain; 30 chains do not fill the last warp of the 16- and 8-lane grids)."""
+    geometry (32 / 16 / 8 lanes per chain; 30 chains do not fill the last warp of the 16- and 8-lane grids), with the
+    variates drawn in place (anneal_kernel) and by producer warps through shared memory (anneal_ws_kernel)."""
+    monkeypatch.setenv('PB200_WS', producer_warps)
     hp, starts, init_ll, values, k = toy_profile_problem(d, points=None if d == 20 else list(range(0, 32, 4)))
     out, _ = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 4, [4], lanes=lanes)
     ar = (1 + out['accepted']) / 251.0
@@ -403,3 +406,52 @@ def test_secant_multiplier_failure_path_stops_the_chain():
                               mode=capi.STEP_ADAPTIVE_SECANT, lanes=16)
     assert np.all(fin['status'] == capi.FAILED) and np.all(fin['iteration'] == 1)
     assert np.all(out['accepted'][0] >= 0) and np.all(out['accepted'][1:] == -1)
+
+
+@pytest.mark.parametrize('lanes', [32, 8])
+def test_producer_warps_early_stop_box_and_wide_paths(lanes, monkeypatch):
+    """anneal_ws_kernel on the paths that stress its hand-shake: chains of one warp converging at different
+    iterations (the consumer leaves early and must release its producer), split launches (ring restarts at every
+    block alignment), exact box tests, and a multi-coordinate-per-lane geometry."""
+    monkeypatch.setenv('PB200_WS', '1')
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[2, 6])
+    _, fin = _replay_anneal(hp, starts, init_ll, 6, _toy_sched(tol=0.02, t0=0.01), 12, [5, 7], lanes=lanes)
+    assert (fin['status'] == capi.CONVERGED).any() and len(np.unique(fin['iteration'])) > 1
+    _, fin = _replay_anneal(hp, starts, init_ll, 2, _toy_sched(tol=1e9), 6, [6], lanes=lanes)     # all stop at once
+    assert np.all(fin['status'] == capi.CONVERGED) and np.all(fin['iteration'] == 1)
+    hpf, _ = toy_free_problem(20)
+    x0 = np.full((1, 20), 2.45)
+    _replay_anneal(hpf, x0, np.array([hpf.loglkl(x0[0])]), 5, _toy_sched(t0=1e6, s0=3.0, S=300, mult=0.0), 2, [1, 1],
+                   lanes=lanes)
+    if lanes == 32:
+        mu, cov = spd_target(41, seed=41)
+        vals = np.array([mu[1] - 0.05, mu[1] + 0.08])
+        prop = conditional_covariance(cov, 1)
+        hpw = build_problem(mu, cov, [-2.5] * 41, [2.5] * 41, 1, vals, np.stack([prop, prop]))
+        st = np.stack([np.delete(mu, 1) + 0.01, np.delete(mu, 1) - 0.01])
+        ll = np.array([hpw.loglkl(st[p], p) for p in range(2)])
+        _replay_anneal(hpw, st, ll, 3, _toy_sched(S=61, s0=2.4 / np.sqrt(41)), 3, [3], lanes=16)
+
+
+def test_producer_warps_fall_back_for_misaligned_chains(monkeypatch):
+    """Chains of one warp whose step counters differ modulo 4 cannot share a producer: that pair draws in place and
+    gives the same results as the plain kernel."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0, 3, 5, 8])
+    prob = DeviceProblem(hp, DEV)
+    b = 12
+    point = np.tile(np.arange(4), 3).astype(np.int32)
+    offs = np.array([0, 1, 2, 3, 4, 4, 8, 12, 5, 7, 4, 8], dtype=np.int32)       # warp 0 mixed, warp 1 aligned
+    res = {}
+    for ws in ('0', '1'):
+        monkeypatch.setenv('PB200_WS', ws)
+        chains = engine.ChainBatch(prob, np.tile(starts, (3, 1)), point, temperature=0.1, step_size=0.1,
+                                   current_best=np.tile(init_ll, 3), steps_done=offs)
+        recs = engine.Records(prob, b, 3)
+        sched = engine.make_schedule(101, 0.8, capi.STEP_ADAPTIVE_FIXED, 1.0, (0.19, 0.21), 0.3, None)
+        engine.anneal_run(prob, chains, sched, recs, 3, SEED, lanes=8)
+        torch.cuda.synchronize()
+        res[ws] = [getattr(recs, key).cpu().numpy() for key in ('best_loglkl', 'last_loglkl', 'accepted', 'best_x')]
+        res[ws].append(chains.steps_done.cpu().numpy())
+    for a, c in zip(res['0'], res['1']):
+        assert np.array_equal(a, c)
+    assert np.array_equal(res['1'][-1], offs + 303)
