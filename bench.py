@@ -298,7 +298,9 @@ def main():
         except Exception:
             pass
         roofline = {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
-                    'traffic': traffic, 'kernel': f'anneal_kernel (lanes per chain {engine.choose_lanes(sa.problem.npad, b_local)}, 20 iterations fused in one launch)',
+                    'traffic': traffic, 'kernel': (lambda ln: f"{'anneal_ws_kernel (chain warps + producer warps)' if engine.uses_producer_warps(ln, b_local) else 'anneal_kernel'}"
+                                        f" (lanes per chain {ln}, {n_iter} iterations fused in one launch)")(
+                        engine.choose_lanes(sa.problem.npad, b_local)),
                     'kernel_ms': k_ms, 'peak_source': src,
                     'algorithmic_bytes_per_chain_step': stream_bytes,
                     'note': 'streaming-formulation bound; the kernel keeps chain state in registers, so DRAM '

@@ -202,6 +202,14 @@ int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* cha
 int pb200_choose_lanes(int32_t npad, int32_t n_chains);
 
 /*
+ * 1 if pb200_anneal_run serves this (lanes_per_chain, n_chains) with the producer-warp kernel (anneal_ws_kernel:
+ * every chain warp is paired with a warp that draws its variates into a shared-memory ring), 0 for the plain fused
+ * kernel.  Results are identical either way; small batches run faster with producer warps.  PB200_WS=0/1 in the
+ * environment forces the choice.
+ */
+int pb200_uses_producer_warps(int32_t lanes_per_chain, int32_t n_chains);
+
+/*
  * Stand-alone adaptive step-size / temperature bookkeeping for B chains (the same device function the
  * fused kernel calls).  Replaces SimulatedAnnealing.get_next_iteration_settings
  * (prospect/optimiser.py:87-162) + the chi2_tolerance test of OptimiseTask.emit_tasks.
@@ -231,6 +239,21 @@ int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int
  */
 int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, int32_t ld, int32_t n,
                            double* out, void* stream);
+
+/*
+ * Per-chain weighted first moments of recorded chains (struct pb200_samples buffers): for every chain c over its
+ * rows r < min(count[c], capacity), in row order,
+ *   out_sw[c] = sum_r mult,   out_swx[c][i] = sum_r mult * x_i,   out_scaled[c][i] = out_swx[c][i] / sqrt(out_sw[c])
+ * (out_scaled rows are 0 for an empty chain).  With pb200_weighted_moments over x (all rows, w = mult) and over
+ * out_scaled (w = NULL) these are the sufficient statistics of the pooled covariance and of the Gelman-Rubin R-1 the
+ * reference gets from getdist (prospect/tasks/mcmc_task.py:28-61, prospect/analysis.py:27-32); they are plain sums,
+ * so ranks all-reduce them.
+ *   x [B][capacity][ld] device, mult [B][capacity] device int32, count [B] device int32,
+ *   out_sw [B], out_swx [B][n], out_scaled [B][n] device FP64 (out_scaled may be NULL).
+ */
+int pb200_chain_moments(const double* x, const int32_t* mult, const int32_t* count, int32_t n_chains,
+                        int32_t capacity, int32_t ld, int32_t n, double* out_sw, double* out_swx,
+                        double* out_scaled, void* stream);
 
 /*
  * Test hook: the N(0,1) / Exp(1) variates the samplers draw for one chain, steps [step0, step0+n_steps).

@@ -58,6 +58,7 @@ SIGNATURES = {
     'pb200_mh_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_int32, C.c_uint64, C.POINTER(Samples),
                                _vp, C.c_int32, _vp]),
     'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),
+    'pb200_uses_producer_warps': (C.c_int, [C.c_int32, C.c_int32]),
     'pb200_variates_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_uint32, C.c_int32]),
     'pb200_variates_fill': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_uint32, C.c_int32, C.c_uint64, _vp,
                                       _vp]),
@@ -67,6 +68,7 @@ SIGNATURES = {
     'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),
     'pb200_weighted_moments': (C.c_int, [_vp, _vp, C.c_int64, C.c_int32, C.c_int32, _vp, _vp]),
+    'pb200_chain_moments': (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]),
     'pb200_rng_variates': (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint32, C.c_int32, C.c_int32, _vp, _vp, _vp]),
     'pb200_philox4x32_10': (None, [C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
 }

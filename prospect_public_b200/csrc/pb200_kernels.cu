@@ -9,6 +9,7 @@
 //   schedule_kernel           stand-alone adaptive step-size bookkeeping.
 //   chain_min_kernel + point_reduce_kernel   min over iterations / first-min repetition / mean (warp shuffles).
 //   moments_kernel            weighted first/second moments (covariance reduction), FP64.
+//   chain_moments_kernel      per-chain weighted first moments of recorded chains (Gelman-Rubin statistics).
 //   variates_kernel           stand-alone Philox + Box-Muller stream generator (feeds the streamed annealing path).
 //   rng_kernel                test hook exposing the variates.
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
@@ -849,6 +850,44 @@ moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ w, long
     }
 }
 
+// Per-chain weighted first moments of the recorded chains (sufficient statistics of R-1 together with the pooled
+// second moments): one warp per chain, lanes over coordinates, rows in order (plain multiply + add so that a
+// sequential host loop reproduces every bit).  A row is one coalesced 8 * npad byte read.
+constexpr int kChainMomWarps = 8;
+
+__global__ void __launch_bounds__(32 * kChainMomWarps)
+chain_moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ mult, const int32_t* __restrict__ count,
+                     int n_chains, int capacity, int ld, int n, double* __restrict__ out_sw,
+                     double* __restrict__ out_swx, double* __restrict__ out_scaled) {
+    const int lane = threadIdx.x & 31, chain = blockIdx.x * kChainMomWarps + (threadIdx.x >> 5);
+    if (chain >= n_chains) return;
+    const int rows = min(count[chain], capacity);
+    const double* __restrict__ xc = x + (size_t)chain * capacity * ld;
+    const int32_t* __restrict__ mc = mult + (size_t)chain * capacity;
+    double acc[8], sw = 0.0;                       // n <= 256: at most 8 coordinates per lane
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.0;
+    for (int r = 0; r < rows; ++r) {
+        const double w = (double)__ldg(mc + r);
+        sw = __dadd_rn(sw, w);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = lane + 32 * j;
+            if (c < n) acc[j] = __dadd_rn(acc[j], __dmul_rn(w, __ldg(xc + (size_t)r * ld + c)));
+        }
+    }
+    const double scale = sw > 0.0 ? 1.0 / sqrt(sw) : 0.0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = lane + 32 * j;
+        if (c < n) {
+            out_swx[(size_t)chain * n + c] = acc[j];
+            if (out_scaled) out_scaled[(size_t)chain * n + c] = __dmul_rn(acc[j], scale);
+        }
+    }
+    if (lane == 0) out_sw[chain] = sw;
+}
+
 // Stand-alone generator of the samplers' variate stream: one thread per (chain, Philox block, slot) makes the one
 // Philox-4x32-10 call whose four words become the four normals of coordinate `slot` in steps 4*blk .. 4*blk+3 (or,
 // for slot == n, the four accept variates) and stores them as ONE float4.  Embarrassingly parallel, no idle lanes,
@@ -996,6 +1035,9 @@ static bool use_producer_warps(int lanes, int n_chains) {
     }
 
 int pb200_choose_lanes(int32_t npad, int32_t n_chains) { return choose_lanes(npad, n_chains); }
+int pb200_uses_producer_warps(int32_t lanes_per_chain, int32_t n_chains) {
+    return use_producer_warps(lanes_per_chain, n_chains) ? 1 : 0;
+}
 
 int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
                      const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream) {
@@ -1139,6 +1181,18 @@ int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, in
     const size_t smem = sizeof(double) * kMomTile * (n + 1);
     moments_kernel<<<dim3(gx, chunks), kMomThreads, smem, st>>>(x, w, (long long)n_rows, ld, n, out);
     return check_cuda(cudaGetLastError(), "moments_kernel launch");
+}
+
+int pb200_chain_moments(const double* x, const int32_t* mult, const int32_t* count, int32_t n_chains,
+                        int32_t capacity, int32_t ld, int32_t n, double* out_sw, double* out_swx,
+                        double* out_scaled, void* stream) {
+    if (!x || !mult || !count || !out_sw || !out_swx) return fail("chain_moments: NULL argument");
+    if (n < 1 || n > 256 || ld < n || capacity < 1) return fail("chain_moments: need 1 <= n <= 256, ld >= n, capacity >= 1");
+    if (n_chains <= 0) return 0;
+    chain_moments_kernel<<<(n_chains + kChainMomWarps - 1) / kChainMomWarps, 32 * kChainMomWarps, 0,
+                           (cudaStream_t)stream>>>(x, mult, count, n_chains, capacity, ld, n, out_sw, out_swx,
+                                                   out_scaled);
+    return check_cuda(cudaGetLastError(), "chain_moments_kernel launch");
 }
 
 int pb200_rng_variates(uint64_t seed, uint32_t chain_id, uint32_t step0, int32_t n_steps, int32_t n, float* out_z,

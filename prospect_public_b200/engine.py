@@ -158,6 +158,11 @@ def choose_lanes(npad, n_chains):
     return int(capi.lib().pb200_choose_lanes(int(npad), int(n_chains)))
 
 
+def uses_producer_warps(lanes, n_chains):
+    """Whether anneal_run serves this batch with the producer-warp kernel (pb200_uses_producer_warps)."""
+    return bool(capi.lib().pb200_uses_producer_warps(int(lanes), int(n_chains)))
+
+
 def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, stream=None, lanes=0):
     _count()
     capi.check(capi.lib().pb200_anneal_run(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
@@ -231,6 +236,38 @@ def weighted_moments(x, n, weights=None, stream=None):
     capi.check(capi.lib().pb200_weighted_moments(capi.ptr(x2), capi.ptr(weights), x2.shape[0], x2.shape[1], int(n),
                                                  capi.ptr(out), _stream_ptr(stream)))
     return out[0], out[1:1 + n], out[1 + n:].reshape(n, n)
+
+
+def chain_moments(samples, n, stream=None):
+    """Per-chain weighted first moments of recorded chains: (sum_w [B], sum_wx [B, n], sum_wx / sqrt(sum_w) [B, n])."""
+    b = samples.x.shape[0]
+    dev = samples.x.device
+    sw = torch.empty(b, dtype=torch.float64, device=dev)
+    swx = torch.empty((b, n), dtype=torch.float64, device=dev)
+    scaled = torch.empty((b, n), dtype=torch.float64, device=dev)
+    _count()
+    capi.check(capi.lib().pb200_chain_moments(capi.ptr(samples.x), capi.ptr(samples.mult), capi.ptr(samples.count), b,
+                                              samples.capacity, samples.x.shape[-1], int(n), capi.ptr(sw),
+                                              capi.ptr(swx), capi.ptr(scaled), _stream_ptr(stream)))
+    return sw, swx, scaled
+
+
+def chain_statistics(samples, n, stream=None):
+    """Flat FP64 device vector [sum_w, sum_wx (n), sum_wxx (n*n), sum_c swx_c swx_c^T / sw_c (n*n), n_chains] of the
+    recorded chains of this rank: plain sums, so ranks all-reduce it (run.convergence_from_statistics)."""
+    b = samples.x.shape[0]
+    out = torch.zeros(2 + n + 2 * n * n, dtype=torch.float64, device=samples.x.device)
+    if b == 0:
+        return out
+    sw, swx, scaled = chain_moments(samples, n, stream)
+    tot_w, tot_wx, tot_wxx = weighted_moments(samples.x, n, samples.mult.reshape(-1), stream)
+    _, _, syy = weighted_moments(scaled, n, None, stream)
+    out[0] = tot_w
+    out[1:1 + n] = tot_wx
+    out[1 + n:1 + n + n * n] = tot_wxx.reshape(-1)
+    out[1 + n + n * n:1 + n + 2 * n * n] = syy.reshape(-1)
+    out[-1] = (sw > 0).sum()             # chains with at least one recorded row
+    return out
 
 
 def covariance_from_moments(sum_w, sum_wx, sum_wxx):

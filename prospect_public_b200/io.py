@@ -101,12 +101,15 @@ def write_parameters(param_dict, output_dir, jobname):
             f.write(line)
 
 
-def write_chains(output_dir, jobname, *chain_list):
+def write_chains(output_dir, jobname, *chain_list, first_index=0):
     for i, chain in enumerate(chain_list):
-        np.savetxt(f'{output_dir}/{jobname}_{i}.txt', chain.data, delimiter=' ')
+        np.savetxt(f'{output_dir}/{jobname}_{first_index + i}.txt', chain.data, delimiter=' ')
 
 
-def unpack_mcmc(param_dict, output_dir, jobname, *chain_list):
+def unpack_mcmc(param_dict, output_dir, jobname, *chain_list, first_index=0, write_names=True):
+    """`first_index` / `write_names`: a rank that owns chains [first_index, ...) of a sharded run writes only its own
+    chain files; rank 0 also writes the .paramnames / .ranges pair."""
     os.makedirs(output_dir, exist_ok=True)
-    write_parameters(param_dict, output_dir, jobname)
-    write_chains(output_dir, jobname, *chain_list)
+    if write_names:
+        write_parameters(param_dict, output_dir, jobname)
+    write_chains(output_dir, jobname, *chain_list, first_index=first_index)

@@ -306,16 +306,44 @@ def gelman_rubin(means, covs, weights):
     return float(np.linalg.eigvalsh(inv @ between @ inv.T).max())
 
 
+def convergence_from_statistics(stats, n):
+    """(R-1, pooled mean [n], pooled covariance [n, n]) from the flat statistics vector of engine.chain_statistics
+    (summed over ranks).  Same quantity as gelman_rubin(): with sw_c, m_c the weight and mean of chain c,
+    within = sum_c (swxx_c - sw_c m_c m_c^T) / sum_c sw_c and between = (sum_c sw_c m_c m_c^T / sum_c sw_c - m m^T)
+    * C / (C - 1).  PARITY UNPINNED like gelman_rubin (getdist absent)."""
+    st = np.asarray(stats, dtype=np.float64)
+    sw, swx = st[0], st[1:1 + n]
+    swxx = st[1 + n:1 + n + n * n].reshape(n, n)
+    syy = st[1 + n + n * n:1 + n + 2 * n * n].reshape(n, n)
+    n_chains = int(round(st[-1]))
+    mean = swx / sw
+    cov = swxx / sw - np.outer(mean, mean)
+    if n_chains < 2:
+        return 0.0, mean, cov
+    within = (swxx - syy) / sw
+    between = (syy / sw - np.outer(mean, mean)) * n_chains / (n_chains - 1)
+    inv = np.linalg.inv(np.linalg.cholesky(within))
+    return float(np.linalg.eigvalsh(inv @ between @ inv.T).max()), mean, cov
+
+
+def shard_chains(n_chains, rank, world):
+    """Contiguous block [lo, hi) of the global chain indices owned by `rank` (blocks differ by at most one chain)."""
+    return n_chains * rank // world, n_chains * (rank + 1) // world
+
+
 def run_mcmc(config, max_rounds=64):
     """jobtype mcmc (tasks/mcmc_task.py:10-81): N_chains chains advance `steps_per_iteration` per round on the
-    GPU; after each round the chains are unpacked to <dir>/mcmc/<jobname>_<i>.txt (+ .paramnames / .ranges) and
-    R-1 decides whether to continue."""
+    GPU(s); after each round the chains are unpacked to <dir>/mcmc/<jobname>_<i>.txt (+ .paramnames / .ranges) and
+    R-1 decides whether to continue.
+
+    Several GPUs (one process each): rank r owns the contiguous chain block shard_chains(); Philox streams are keyed
+    by the GLOBAL chain index, so every chain is the same whatever the number of GPUs.  The only exchange is one
+    all-reduce (sum, FP64) per round of the 2 + n + 2 n^2 sufficient statistics of the pooled covariance and R-1
+    (SURVEY.md section 8e); every rank writes its own chain files."""
     import torch
     from . import engine
     from .mcmc import initialise_mcmc
     rank, world, _ = dist_info()
-    if world > 1:
-        raise NotImplementedError('jobtype mcmc runs on one GPU per job in this round.')
     device = _device()
     mc = config.mcmc
     if mc.steps_per_iteration is None:
@@ -323,31 +351,43 @@ def run_mcmc(config, max_rounds=64):
     if config.run.numpy_random_seed is not None:
         np.random.seed(int(config.run.numpy_random_seed))
     out_dir = config.io.dir if config.io.write else None
-    kernel = initialise_kernel(config.kernel, out_dir, 0, device)
-    sampler = initialise_mcmc(mc, kernel, seed=config.seed)
-    n = sampler.problem.n
-    rounds, conv = 0, np.inf
+    if rank == 0:
+        kernel = initialise_kernel(config.kernel, out_dir, 0, device)   # may create analytical/random_gauss.pkl
+    _barrier()
+    if rank != 0:
+        kernel = initialise_kernel(config.kernel, out_dir, rank, device)
+    lo, hi = shard_chains(int(mc.N_chains), rank, world)
+    sampler = initialise_mcmc(mc, kernel, seed=config.seed, n_chains=hi - lo,
+                              chain_ids=np.arange(lo, hi, dtype=np.uint32)) if hi > lo else None
+    n = len(kernel.varying_param_names)
+    rounds, conv, mean, cov = 0, np.inf, None, None
+    if world > 1:
+        import torch.distributed as dist
+        _barrier()
+    torch.cuda.synchronize()
     t0 = time.perf_counter()
     while rounds < max_rounds:
-        sampler.run_steps(mc.steps_per_iteration)
+        if sampler is not None:
+            sampler.run_steps(mc.steps_per_iteration)
+            stats = engine.chain_statistics(sampler._samples, n)
+        else:
+            stats = torch.zeros(2 + n + 2 * n * n, dtype=torch.float64, device=device)
         rounds += 1
-        x, ll, mult, cnt = None, None, None, sampler._samples.count.cpu().numpy()
-        means, covs, wsum = [], [], []
-        s = sampler._samples
-        for c in range(sampler.n_chains):
-            sw, swx, swxx = engine.weighted_moments(s.x[c, :cnt[c]], n, s.mult[c, :cnt[c]].contiguous())
-            means.append((swx / sw).cpu().numpy())
-            covs.append(engine.covariance_from_moments(sw, swx, swxx).cpu().numpy())
-            wsum.append(float(sw))
-        conv = gelman_rubin(np.array(means), np.array(covs), wsum) if sampler.n_chains > 1 else 0.0
-        if config.io.write and mc.unpack_at_dump:
+        if world > 1:
+            if dist.get_backend() != 'nccl':
+                stats = stats.cpu()
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        conv, mean, cov = convergence_from_statistics(stats.cpu().numpy(), n)
+        if config.io.write and mc.unpack_at_dump and sampler is not None:
             pio.unpack_mcmc(kernel.param['varying'], os.path.join(config.io.dir, 'mcmc'), config.io.jobname,
-                            *sampler.chains)
+                            *sampler.chains, first_index=lo, write_names=rank == 0)
         if conv < mc.convergence_Rm1:
             break
     torch.cuda.synchronize()
-    return {'sampler': sampler, 'rounds': rounds, 'Rm1': conv, 'loop_seconds': time.perf_counter() - t0,
-            'chain_steps': rounds * mc.steps_per_iteration * sampler.n_chains}
+    _barrier()
+    return {'sampler': sampler, 'rounds': rounds, 'Rm1': conv, 'mean': mean, 'covmat': cov,
+            'loop_seconds': time.perf_counter() - t0, 'chain_range': (lo, hi),
+            'chain_steps': rounds * mc.steps_per_iteration * int(mc.N_chains)}
 
 
 def run_from_shell(argv=None):

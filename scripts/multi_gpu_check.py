@@ -32,4 +32,29 @@ for label, kw in (('points sharded (10 values x 6 reps)', dict(repetitions=6)),
               f'chain_steps {res["chain_steps"]}')
         assert err <= 1e-3 and ran and files
     dist.barrier()
+# jobtype mcmc sharded over the ranks: chain files and statistics must not depend on the number of GPUs
+from prospect_public_b200.config import Configuration
+from prospect_public_b200.kernels import initialise_kernel
+from prospect_public_b200.mcmc import initialise_mcmc
+from prospect_public_b200.toy import mcmc_yaml
+from prospect_public_b200 import engine
+from prospect_public_b200.run import convergence_from_statistics
+mc_dir = os.path.join(base, 'out_mcmc')
+y = mcmc_yaml(paths, mc_dir, n_chains=19, steps=600, rm1=1e9)
+res = run(y)
+dist.barrier()
+if dist_info()[0] == 0:
+    cfg = Configuration(mcmc_yaml(paths, os.path.join(base, 'unused'), n_chains=19, steps=600, rm1=1e9, write=False))
+    kern = initialise_kernel(cfg.kernel, None, 0, 'cuda:0')
+    single = initialise_mcmc(cfg.mcmc, kern, seed=cfg.seed, n_chains=19, chain_ids=np.arange(19, dtype=np.uint32))
+    single.run_steps(600)
+    for i, ch in enumerate(single.chains):
+        disk = np.loadtxt(os.path.join(mc_dir, 'mcmc', f'test_{i}.txt'))
+        assert np.array_equal(disk, ch.data), i
+    rm1, mean, cov = convergence_from_statistics(engine.chain_statistics(single._samples, single.problem.n).cpu().numpy(),
+                                                 single.problem.n)
+    assert abs(rm1 - res['Rm1']) <= 1e-9 * abs(rm1) and np.allclose(cov, res['covmat'], rtol=1e-9, atol=1e-15)
+    print(f'mcmc sharded: world {dist_info()[1]} 19 chain files identical to a single-GPU run, R-1 {res["Rm1"]:.6f} '
+          f'(single {rm1:.6f}), chain range of rank 0 {res["chain_range"]}')
+dist.barrier()
 dist.destroy_process_group()

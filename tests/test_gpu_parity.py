@@ -455,3 +455,42 @@ def test_producer_warps_fall_back_for_misaligned_chains(monkeypatch):
     for a, c in zip(res['0'], res['1']):
         assert np.array_equal(a, c)
     assert np.array_equal(res['1'][-1], offs + 303)
+
+
+def test_chain_moments_bit_exact_and_statistics_match_numpy():
+    """pb200_chain_moments: per-chain sums in row order are bit-identical to a sequential numpy loop; the flat
+    statistics vector equals its numpy restatement and yields np.cov of the pooled chains."""
+    from prospect_public_b200.run import convergence_from_statistics
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    b, cap, n = 37, 61, hp.n
+    rng = np.random.default_rng(8)
+    smp = engine.Samples(prob, b, cap, capi.RECORD_ACCEPTED, 1)
+    cnt = rng.integers(0, cap + 5, b).astype(np.int32)          # some empty, some "overflowed" (count > capacity)
+    cnt[3] = 0
+    x = np.zeros((b, cap, hp.npad))
+    mult = np.zeros((b, cap), dtype=np.int32)
+    for c in range(b):
+        r = min(cnt[c], cap)
+        x[c, :r, :n] = rng.normal(0.3, 1.0, (r, n))
+        mult[c, :r] = rng.integers(1, 9, r)
+    smp.x.copy_(torch.as_tensor(x))
+    smp.mult.copy_(torch.as_tensor(mult))
+    smp.count.copy_(torch.as_tensor(cnt))
+    sw, swx, scaled = (t.cpu().numpy() for t in engine.chain_moments(smp, n))
+    for c in range(b):
+        acc, w_acc = np.zeros(n), 0.0
+        for r in range(min(cnt[c], cap)):
+            w_acc = w_acc + float(mult[c, r])
+            acc = acc + float(mult[c, r]) * x[c, r, :n]
+        assert sw[c] == w_acc and np.array_equal(swx[c], acc)
+        assert np.array_equal(scaled[c], acc * (1.0 / np.sqrt(w_acc)) if w_acc > 0 else np.zeros(n))
+    stats = engine.chain_statistics(smp, n).cpu().numpy()
+    keep = [c for c in range(b) if cnt[c] > 0]
+    xs = [x[c, :min(cnt[c], cap), :n] for c in keep]
+    ws = [mult[c, :min(cnt[c], cap)].astype(np.float64) for c in keep]
+    allx, allw = np.concatenate(xs), np.concatenate(ws).astype(int)
+    rm1, mean, cov = convergence_from_statistics(stats, n)
+    assert stats[-1] == len(keep) and stats[0] == allw.sum()
+    assert np.allclose(cov, np.cov(allx, rowvar=False, bias=True, fweights=allw), rtol=1e-10, atol=1e-12)
+    assert np.allclose(mean, np.average(allx, axis=0, weights=allw), rtol=1e-12)

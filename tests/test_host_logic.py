@@ -268,6 +268,83 @@ def test_record_all_gather_world2_gloo(p, r):
     assert set(owners) == {0.0, 1.0}
 
 
+def _chain_statistics_numpy(xs, ws):
+    """numpy restatement of engine.chain_statistics for a list of chains (rows [r, n], integer weights [r])."""
+    n = xs[0].shape[1]
+    out = np.zeros(2 + n + 2 * n * n)
+    for x, w in zip(xs, ws):
+        sw, swx = w.sum(), (w[:, None] * x).sum(0)
+        out[0] += sw
+        out[1:1 + n] += swx
+        out[1 + n:1 + n + n * n] += ((w[:, None] * x).T @ x).ravel()
+        out[1 + n + n * n:1 + n + 2 * n * n] += np.outer(swx, swx).ravel() / sw
+        out[-1] += 1
+    return out
+
+
+def _fake_chains(n_chains, n, seed):
+    rng = np.random.default_rng(seed)
+    xs = [rng.normal(0.1 * c, 1.0 + 0.05 * c, (40 + 3 * c, n)) for c in range(n_chains)]
+    ws = [rng.integers(1, 6, len(x)).astype(np.float64) for x in xs]
+    return xs, ws
+
+
+def test_convergence_from_statistics_equals_per_chain_formula():
+    """The summed sufficient statistics give the same R-1, mean and covariance as the per-chain formulation, and
+    the pooled covariance equals np.cov(..., bias=True, fweights=mults) (prospect/mcmc.py:93-97)."""
+    from prospect_public_b200.run import convergence_from_statistics, gelman_rubin, shard_chains
+    xs, ws = _fake_chains(7, 5, seed=3)
+    rm1, mean, cov = convergence_from_statistics(_chain_statistics_numpy(xs, ws), 5)
+    means = np.array([np.average(x, axis=0, weights=w) for x, w in zip(xs, ws)])
+    covs = np.array([np.cov(x, rowvar=False, bias=True, fweights=w.astype(int)) for x, w in zip(xs, ws)])
+    assert rm1 == pytest.approx(gelman_rubin(means, covs, [w.sum() for w in ws]), rel=1e-10)
+    allx, allw = np.concatenate(xs), np.concatenate(ws).astype(int)
+    assert np.allclose(cov, np.cov(allx, rowvar=False, bias=True, fweights=allw), rtol=1e-11, atol=1e-13)
+    assert np.allclose(mean, np.average(allx, axis=0, weights=allw), rtol=1e-12)
+    assert convergence_from_statistics(_chain_statistics_numpy(xs[:1], ws[:1]), 5)[0] == 0.0
+    for b, world in ((7, 2), (3, 8), (65536, 8)):
+        blocks = [shard_chains(b, r, world) for r in range(world)]
+        assert blocks[0][0] == 0 and blocks[-1][1] == b
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+        assert max(hi - lo for lo, hi in blocks) - min(hi - lo for lo, hi in blocks) <= 1
+
+
+def _gloo_stats_worker(rank, world, port, q):
+    """jobtype mcmc for N > 1 on CPU tensors: every rank reduces the statistics of ITS chain block, one all-reduce
+    makes the global vector, and every rank derives the same R-1 (run.run_mcmc)."""
+    import torch
+    import torch.distributed as dist
+    from prospect_public_b200.run import convergence_from_statistics, shard_chains
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    xs, ws = _fake_chains(5, 4, seed=11)
+    lo, hi = shard_chains(5, rank, world)
+    stats = torch.as_tensor(_chain_statistics_numpy(xs[lo:hi], ws[lo:hi]))
+    dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    q.put((rank, convergence_from_statistics(stats.numpy(), 4)))
+    dist.destroy_process_group()
+
+
+def test_mcmc_statistics_all_reduce_world2_gloo():
+    import torch.multiprocessing as mp
+    from prospect_public_b200.run import convergence_from_statistics
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29950 + (os.getpid() % 40)
+    procs = [ctx.Process(target=_gloo_stats_worker, args=(rank, 2, port, q)) for rank in range(2)]
+    for pr in procs:
+        pr.start()
+    outs = dict(q.get(timeout=120) for _ in range(2))
+    for pr in procs:
+        pr.join(timeout=60)
+    xs, ws = _fake_chains(5, 4, seed=11)
+    rm1, mean, cov = convergence_from_statistics(_chain_statistics_numpy(xs, ws), 4)
+    for rank in range(2):
+        assert outs[rank][0] == pytest.approx(rm1, rel=1e-10)
+        assert np.allclose(outs[rank][1], mean, rtol=1e-12) and np.allclose(outs[rank][2], cov, rtol=1e-10)
+    assert outs[0][0] == outs[1][0]
+
+
 REFERENCE = '/root/reference'
 
 
