@@ -170,6 +170,22 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
                      const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream);
 
 /*
+ * pb200_anneal_run that also SIGNALS its progress: `progress` is a device array of n_iter uint32 counters, zeroed
+ * by the caller before the launch; counter k reaches *out_target (returned by this call) once every warp has made
+ * its records of the launch's k-th iteration globally visible (or will never run it because all its chains
+ * stopped).  A second stream can therefore ship iteration k's records -- pb200_stream_wait_geq(stream,
+ * progress + k, target), then the all-gather -- while later iterations are still running in the same launch.
+ * The kernel never waits on anything, so the scheme cannot dead-lock.  This is the iteration-boundary exchange of
+ * the sharded task farm without giving up the fused multi-iteration launch.
+ */
+int pb200_anneal_run_signalled(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                               const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
+                               uint32_t* progress, int32_t* out_target, void* stream);
+
+/* Enqueue on `stream` a wait until *counter >= value (cuStreamWaitValue32, CU_STREAM_WAIT_VALUE_GEQ). */
+int pb200_stream_wait_geq(void* stream, const uint32_t* counter, uint32_t value);
+
+/*
  * n_steps Metropolis-Hastings steps per chain at the chain's temperature / step size, optionally
  * recording the chain.  Replaces MCMCTask.run -> BaseMCMC.run_steps
  * (prospect/tasks/mcmc_task.py:17-23, prospect/mcmc.py:131-138).  accepted_out [B] device (may be NULL).

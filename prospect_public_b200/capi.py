@@ -55,6 +55,10 @@ SIGNATURES = {
     'pb200_loglkl_batch': (C.c_int, [C.POINTER(Problem), _vp, _vp, C.c_int32, _vp, _vp, _vp]),
     'pb200_anneal_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule), C.POINTER(Records),
                                    C.c_int32, C.c_uint64, C.c_int32, _vp]),
+    'pb200_anneal_run_signalled': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule),
+                                             C.POINTER(Records), C.c_int32, C.c_uint64, C.c_int32, _vp,
+                                             C.POINTER(C.c_int32), _vp]),
+    'pb200_stream_wait_geq': (C.c_int, [_vp, _vp, C.c_uint32]),
     'pb200_mh_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_int32, C.c_uint64, C.POINTER(Samples),
                                _vp, C.c_int32, _vp]),
     'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),

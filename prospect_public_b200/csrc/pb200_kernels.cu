@@ -410,7 +410,7 @@ template <int LPC, int CPL, int SRC>
 __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_chains& ch, const pb200_schedule& s,
                                             const pb200_records& rec, int n_iter, uint32_t k0, uint32_t k1,
                                             const float4* __restrict__ zbuf, int nb, uint32_t t_stream, int warp_slot,
-                                            double* stage_warp, Ring& ring) {
+                                            double* stage_warp, Ring& ring, uint32_t* __restrict__ progress) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     constexpr bool ZBUF = SRC == kSrcStream;
     const int lane = threadIdx.x & 31, gi = lane / LPC, gl = lane % LPC;
@@ -449,7 +449,8 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
     anchor<LPC, CPL>(p, pt, gl, x, c, qs);                 // loglkl of the start point (optimiser.py:55)
     RecCursor rc{};
 
-    for (int it = 0; it < n_iter && __any_sync(kFull, live); ++it) {
+    int it = 0;
+    for (; it < n_iter && __any_sync(kFull, live); ++it) {
         c.best_ll = c.ll;
         c.nacc = 0;
 #pragma unroll
@@ -490,6 +491,14 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
             schedule_next(s, st, nacc, best_exact);
             live = st.status == PB200_ACTIVE;
         }
+        if (progress) {          // this warp's records of launch-iteration `it` are globally visible: count it
+            __threadfence();
+            __syncwarp();
+            if (lane == 0) atomicAdd(progress + it, 1u);
+        }
+    }
+    if (progress && lane == 0) {  // iterations this warp will never run (all its chains stopped) count as done
+        for (int k = it; k < n_iter; ++k) atomicAdd(progress + k, 1u);
     }
     if (was_live) {
 #pragma unroll
@@ -513,13 +522,14 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
 template <int LPC, int CPL, bool ZBUF>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
 anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream) {
+              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream, uint32_t* __restrict__ progress) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
     const int wib = threadIdx.x >> 5;
     Ring none{};
     anneal_body<LPC, CPL, ZBUF ? kSrcStream : kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, zbuf, nb, t_stream,
-                                                          blockIdx.x * kWarpsPerCta + wib, &stage[wib][0][0], none);
+                                                          blockIdx.x * kWarpsPerCta + wib, &stage[wib][0][0], none,
+                                                          progress);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -562,7 +572,7 @@ __device__ __forceinline__ void produce_variates(int n, int n_iter, uint32_t ste
 template <int LPC, int CPL>
 __global__ void __launch_bounds__(64 * kWsPairs, ws_min_ctas(LPC * CPL))
 anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-                 uint32_t k1) {
+                 uint32_t k1, uint32_t* __restrict__ progress) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) unsigned char slots[kWsPairs][kRingDepth][ring_slot_bytes<CPL>()];
     __shared__ __align__(16) double stage[kWsPairs][G][NPAD];
@@ -602,10 +612,10 @@ anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_recor
     }
     if (paired)
         anneal_body<LPC, CPL, kSrcRing>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot, &stage[pair][0][0],
-                                        ring);
+                                        ring, progress);
     else
         anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot,
-                                          &stage[pair][0][0], ring);
+                                          &stage[pair][0][0], ring, progress);
     __syncwarp();
     if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ring.stop), "r"(1u) : "memory");
 }
@@ -1039,8 +1049,9 @@ int pb200_uses_producer_warps(int32_t lanes_per_chain, int32_t n_chains) {
     return use_producer_warps(lanes_per_chain, n_chains) ? 1 : 0;
 }
 
-int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
-                     const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream) {
+static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                         const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
+                         uint32_t* progress, void* stream) {
     if (validate(prob)) return 1;
     if (!chains || !sched || !rec) return fail("anneal_run: NULL argument");
     if (chains->n_chains <= 0 || n_iter <= 0) return 0;
@@ -1059,12 +1070,49 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
         const int pairs = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);
         const int ws_blocks = (pairs + kWsPairs - 1) / kWsPairs;
         PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_ws_kernel<LPC, CPL><<<ws_blocks, 64 * kWsPairs, 0, st>>>(
-                                                        *prob, *chains, *sched, *rec, n_iter, k0, k1)));
+                                                        *prob, *chains, *sched, *rec, n_iter, k0, k1, progress)));
         return check_cuda(cudaGetLastError(), "anneal_ws_kernel launch");
     }
     PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, false><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
-                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u)));
+                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u,
+                                                    progress)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");
+}
+
+int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                     const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream) {
+    return anneal_launch(prob, chains, sched, rec, n_iter, seed, lanes_per_chain, nullptr, stream);
+}
+
+int pb200_anneal_run_signalled(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                               const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
+                               uint32_t* progress, int32_t* out_target, void* stream) {
+    if (!progress || !out_target) return fail("anneal_run_signalled: NULL progress / out_target");
+    int lanes;
+    if (!prob || !chains) return fail("anneal_run_signalled: NULL argument");
+    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
+    *out_target = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);      // warps that own chains
+    return anneal_launch(prob, chains, sched, rec, n_iter, seed, lanes_per_chain, progress, stream);
+}
+
+// cuStreamWaitValue32 through the runtime's driver entry point lookup: no link-time dependency on libcuda, so
+// the library still loads (and exports every symbol) on a machine without a driver.
+int pb200_stream_wait_geq(void* stream, const uint32_t* counter, uint32_t value) {
+    typedef int (*wait_fn)(void*, unsigned long long, unsigned int, unsigned int);
+    static wait_fn fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (check_cuda(cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &status),
+                       "cudaGetDriverEntryPoint(cuStreamWaitValue32)"))
+            return 1;
+        if (status != cudaDriverEntryPointSuccess || !ptr) return fail("cuStreamWaitValue32 is not available");
+        fn = (wait_fn)ptr;
+    }
+    if (!counter) return fail("stream_wait_geq: NULL counter");
+    const int rc = fn(stream, (unsigned long long)(uintptr_t)counter, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
+    if (rc != 0) return fail("cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
+    return 0;
 }
 
 int64_t pb200_variates_bytes(int32_t npad, int32_t n_chains, uint32_t step_begin, int32_t n_steps) {
@@ -1108,7 +1156,7 @@ int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* cha
     const int nb = (int)(((step_begin + (uint32_t)sched->steps_per_iteration - 1u) >> 2) - blk0 + 1u);
     PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, true><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
                                                     *prob, *chains, *sched, *rec, 1, 0u, 0u, (const float4*)zbuf, nb,
-                                                    step_begin)));
+                                                    step_begin, nullptr)));
     return check_cuda(cudaGetLastError(), "anneal_kernel (streamed) launch");
 }
 

@@ -170,6 +170,24 @@ def anneal_run(problem, chains: ChainBatch, schedule, records: Records, n_iter, 
                                            _stream_ptr(stream)))
 
 
+def anneal_run_signalled(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, progress, stream=None,
+                         lanes=0):
+    """anneal_run whose kernel counts finished iterations in `progress` (zeroed int32 device tensor [n_iter]).
+    Returns the value every counter reaches (see pb200_anneal_run_signalled)."""
+    target = C.c_int32(0)
+    _count()
+    capi.check(capi.lib().pb200_anneal_run_signalled(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
+                                                     C.byref(records.c), int(n_iter), C.c_uint64(seed), int(lanes),
+                                                     capi.ptr(progress), C.byref(target), _stream_ptr(stream)))
+    return target.value
+
+
+def stream_wait_geq(stream, counter, index, value):
+    """Make `stream` wait until counter[index] >= value (a device-side wait; the host does not block)."""
+    capi.check(capi.lib().pb200_stream_wait_geq(_stream_ptr(stream), C.c_void_p(counter.data_ptr() + 4 * int(index)),
+                                                int(value)))
+
+
 def variates_buffer(problem, n_chains, n_steps):
     """Device buffer large enough for the variate stream of `n_steps` steps of `n_chains` chains at any alignment."""
     nbytes = capi.lib().pb200_variates_bytes(int(problem.npad), int(n_chains), 3, int(n_steps))

@@ -108,6 +108,7 @@ class SimulatedAnnealing:
         self.iterations_done = int(s.get('iteration_number', 0))
         self.bestfit = None
         self._gatherer = None
+        self.signalled = True
 
     @property
     def n_chains(self):
@@ -191,11 +192,13 @@ class SimulatedAnnealing:
 
     # --- whole schedules ---------------------------------------------------------------------------
     def run_schedule(self, n_iterations, iterations_per_launch=None, gather=True):
-        """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: one
-        launch per iteration and an all-gather of that iteration's per-chain scalars (bestfit chi^2, last chi^2,
-        temperature, step size, accepted count) on a side stream, overlapping the next iteration's compute (there is
-        no dependency between them); the bestfit positions of all iterations follow in one all-gather at the end
-        (global_records), which keeps the per-boundary collective latency-sized."""
+        """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: still ONE
+        fused launch; the kernel counts finished iterations in device memory and a side stream all-gathers every
+        iteration's per-chain scalars (bestfit chi^2, last chi^2, temperature, step size, accepted count) as soon as
+        its counter is complete -- the iteration-boundary exchange overlaps the following iterations' compute
+        instead of cutting the launch into pieces (run_signalled).  The bestfit positions of all iterations follow
+        in one all-gather at the end (global_records), which keeps the per-boundary collective latency-sized.
+        `self.signalled = False` (or the streamed generator) falls back to one launch + one gather per iteration."""
         import torch
         if self.world == 1 or not gather:
             if self.streamed and iterations_per_launch is None:
@@ -215,6 +218,13 @@ class SimulatedAnnealing:
             self._comm_stream = torch.cuda.Stream(device=self.problem.device)
             self.gathered = torch.zeros((self.max_rows, self.world, self.records.scalar_len), dtype=torch.float64,
                                         device=self.problem.device)
+
+        def ship(k):
+            dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k, :self.records.scalar_len])
+
+        if self.signalled and not self.streamed:
+            self.run_signalled(n_iterations, ship, self._comm_stream)
+            return self.gathered
         compute = torch.cuda.current_stream()
         iterate = self.optimise_streamed(n_iterations) if self.streamed else None
         for _ in range(n_iterations):
@@ -227,9 +237,33 @@ class SimulatedAnnealing:
             ev.record(compute)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(ev)
-                dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k, :self.records.scalar_len])
+                ship(k)
         compute.wait_stream(self._comm_stream)
         return self.gathered
+
+    def run_signalled(self, n_iterations, ship, side_stream):
+        """One fused launch of `n_iterations` iterations whose kernel signals each finished iteration; for every
+        iteration, in order, `ship(row)` is issued on `side_stream` behind a device-side wait on that iteration's
+        counter (pb200_anneal_run_signalled / pb200_stream_wait_geq).  All chains of a batch share the iteration
+        counter here, so launch-iteration i is record row iterations_done + i."""
+        import torch
+        from . import engine
+        compute = torch.cuda.current_stream()
+        progress = torch.zeros(n_iterations, dtype=torch.int32, device=self.problem.device)
+        zeroed = torch.cuda.Event()
+        zeroed.record(compute)
+        k0 = self.iterations_done
+        target = engine.anneal_run_signalled(self.problem, self.batch, self.schedule, self.records, n_iterations,
+                                             self.seed, progress, None, self.lanes)
+        self.iterations_done += n_iterations
+        self.step_counter += n_iterations * self.schedule.steps_per_iteration
+        with torch.cuda.stream(side_stream):
+            side_stream.wait_event(zeroed)
+            for i in range(n_iterations):
+                engine.stream_wait_geq(side_stream, progress, i, target)
+                ship(k0 + i)
+        compute.wait_stream(side_stream)
+        self._progress = progress            # keep alive until the streams are done with it
 
     def global_records(self):
         """Host arrays over ALL chains of the job in global order c = rep * P + point:

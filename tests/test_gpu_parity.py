@@ -494,3 +494,44 @@ def test_chain_moments_bit_exact_and_statistics_match_numpy():
     assert stats[-1] == len(keep) and stats[0] == allw.sum()
     assert np.allclose(cov, np.cov(allx, rowvar=False, bias=True, fweights=allw), rtol=1e-10, atol=1e-12)
     assert np.allclose(mean, np.average(allx, axis=0, weights=allw), rtol=1e-12)
+
+
+@pytest.mark.parametrize('lanes,tol', [(32, None), (8, None), (8, 0.02), (16, 1e9)])
+def test_signalled_launch_ships_complete_iterations(lanes, tol):
+    """pb200_anneal_run_signalled + pb200_stream_wait_geq: a side stream that waits on iteration i's counter sees
+    that iteration's complete record block while the launch is still running; results equal the plain launch; the
+    counters also complete when chains stop early (chi2_tolerance), so the side stream can never be left waiting."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[2, 6, 7])
+    prob = DeviceProblem(hp, DEV)
+    reps, n_iter = 5, 6
+    b = reps * hp.n_points
+    point = np.tile(np.arange(hp.n_points), reps).astype(np.int32)
+    sched = engine.make_schedule(250, 0.7, capi.STEP_ADAPTIVE_FIXED, 1.0, (0.19, 0.21), 0.3, tol)
+    out = {}
+    for mode in ('plain', 'signalled'):
+        chains = engine.ChainBatch(prob, np.tile(starts, (reps, 1)), point, temperature=0.01 if tol else 0.1,
+                                   step_size=0.1, current_best=np.tile(init_ll, reps))
+        recs = engine.Records(prob, b, n_iter)
+        if mode == 'plain':
+            engine.anneal_run(prob, chains, sched, recs, n_iter, SEED, lanes=lanes)
+            torch.cuda.synchronize()
+        else:
+            side = torch.cuda.Stream()
+            progress = torch.zeros(n_iter, dtype=torch.int32, device=DEV)
+            snap = torch.zeros_like(recs.buf)
+            torch.cuda.synchronize()
+            target = engine.anneal_run_signalled(prob, chains, sched, recs, n_iter, SEED, progress, lanes=lanes)
+            with torch.cuda.stream(side):
+                for i in range(n_iter):
+                    engine.stream_wait_geq(side, progress, i, target)
+                    snap[i].copy_(recs.buf[i], non_blocking=True)
+            torch.cuda.synchronize()
+            assert np.all(progress.cpu().numpy() == target)
+            assert target == -(-b // (32 // lanes))
+            assert torch.equal(snap.view(torch.int64), recs.buf.view(torch.int64))    # bit patterns (-1 counts are NaNs)
+        out[mode] = (recs.buf.clone(), chains.x.clone(), chains.status.clone(), chains.iteration.clone())
+    for a, c in zip(out['plain'], out['signalled']):
+        assert torch.equal(a.view(torch.int64) if a.dtype == torch.float64 else a,
+                           c.view(torch.int64) if c.dtype == torch.float64 else c)
+    if tol == 0.02:
+        assert len(np.unique(out['plain'][3].cpu().numpy())) > 1        # chains stopped at different iterations
