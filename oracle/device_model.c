@@ -326,16 +326,17 @@ static int block_steps(dm_run *R, dm_state *s, const float *zb[4], const float e
     delta[3] = sf * ((S[3] + S[7]) + x3);
     acc[3] = delta[3] < Tf * e[3];
     const int any = acc[0] || acc[1] || acc[2] || acc[3];
-    const float bnd = sqrtf(S[15]) + (sf + sf) * sqrtf(S[14]);
-    if (any && !(bnd * bnd <= s->m2)) return 1;
+    const float s2 = sf + sf;
+    const float half_bnd2 = fmaf(s2 * s2, S[14], S[15]);
+    if (any && !((half_bnd2 + half_bnd2) <= s->m2)) return 1;
     for (int k = 0; k < 4; ++k) {
+        s->ll = s->ll + (acc[k] ? (double)delta[k] : 0.0);      /* the kernel adds +0.0 for a rejected step */
         if (!acc[k]) continue;
         for (int c = 0; c < np; ++c) {
             const float zc = c < n ? zb[k][c] : 0.0f;
             s->w[c] = fmaf(sf, zc, s->w[c]);
             R->gf[c] = fmaf(R->hl[c] + R->hl[c], zc, R->gf[c]);
         }
-        s->ll = s->ll + (double)delta[k];
         s->nacc += 1;
         if (s->ll < s->best_ll) {
             s->best_ll = s->ll;

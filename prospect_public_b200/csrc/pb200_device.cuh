@@ -175,7 +175,7 @@ __device__ __forceinline__ void ring_fetch(Ring& rg, int lane, int gi, float (&z
     if (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
         const long long t0 = clock64();
         while (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
-            if (clock64() - t0 > 8000000000LL) __trap();
+            if (clock64() - t0 > 40000000000LL) __trap();      // ~20 s
         }
     }
     const uint32_t base = rg.data + slot * (uint32_t)ring_slot_bytes<CPL>();

@@ -196,8 +196,8 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
 // 16 independent values in flight instead of four dependent reduce -> compare -> branch chains -- and the four
 // accept decisions are then resolved with scalar arithmetic.  This is what keeps a small batch (few warps per
 // SM) from being latency-bound.  Box safety for every intermediate point: |w_k| <= |w_0| + step * sum_j |z_j|
-// <= sqrt(R0) + 2 step sqrt(E).  Returns true, with nothing committed, when the group must replay the block
-// step by step (bound not provably inside the safe radius).
+// <= sqrt(R0) + 2 step sqrt(E), hence |w_k|^2 <= 2 (R0 + 4 step^2 E).  Returns true, with nothing committed, when
+// the group must replay the block step by step (bound not provably inside the safe radius).
 // ----------------------------------------------------------------------------------------------
 template <int LPC, int CPL>
 __device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const float (&z)[CPL][4],
@@ -245,19 +245,22 @@ __device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const 
     delta[3] = __fmul_rn(sf, __fadd_rn(__fadd_rn(v[3], v[7]), x3));
     acc[3] = live && (delta[3] < __fmul_rn(Tf, e[3]));
     const bool any = acc[0] || acc[1] || acc[2] || acc[3];
-    const float bnd = __fadd_rn(__fsqrt_rn(v[15]), __fmul_rn(__fadd_rn(sf, sf), __fsqrt_rn(v[14])));
-    if (any && !(__fmul_rn(bnd, bnd) <= c.m2)) return true;
-    // scalar pass: running loglkl, accept count, and which step (if any) sets a new best
+    // (sqrt(R0) + 2 s sqrt(E))^2 <= 2 (R0 + 4 s^2 E): no square roots (each would be a MUFU + a slow-path branch)
+    const float s2 = __fadd_rn(sf, sf);
+    const float half_bnd2 = __fmaf_rn(__fmul_rn(s2, s2), v[14], v[15]);
+    if (any && !(__fadd_rn(half_bnd2, half_bnd2) <= c.m2)) return true;
+    // scalar pass, branch-free: running loglkl (+0.0 for a rejected step), accept count, and which step (if any)
+    // sets a new best
     int kb = -1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-        if (acc[k]) {
-            c.ll = __dadd_rn(c.ll, (double)delta[k]);
-            c.nacc += 1;
-            if (c.ll < c.best_ll) { c.best_ll = c.ll; kb = k; }
-        }
+        c.ll = __dadd_rn(c.ll, acc[k] ? (double)delta[k] : 0.0);
+        c.nacc += acc[k] ? 1 : 0;
+        const bool better = acc[k] && (c.ll < c.best_ll);
+        c.best_ll = better ? c.ll : c.best_ll;
+        kb = better ? k : kb;
     }
-    if (kb >= 0) c.best_rel = true;
+    c.best_rel = c.best_rel || (kb >= 0);
     // vector pass: predicated, branch-free
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
@@ -1001,12 +1004,12 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
 
 // lanes per chain: small groups serve several chains per warp instruction, large groups give more warps.
 static int choose_lanes(int npad, int n_chains) {
-    // Measured on B200 (30-D toy, profiles/): fewer lanes per chain = fewer warp instructions per chain-step; the
-    // 8-lane geometry (four steps per reduction) is best from 4096 chains up, below that more warps matter more.
+    // Measured on B200 (30-D toy, profiles/README.md): fewer lanes per chain = fewer warp instructions per chain-step.
+    // npad = 32: the 8-lane geometry (four steps per reduction) wins at every batch size once small batches get
+    // producer warps (use_producer_warps); wider problems keep more lanes per chain.
     if (npad > 64) return 32;
-    if (npad == 32 && n_chains >= 4096) return 8;
-    if (n_chains >= 4096) return 16;
-    return 32;
+    if (npad == 32) return 8;
+    return n_chains >= 4096 ? 16 : 32;
 }
 
 static int resolve_lanes(int requested, int npad, int n_chains, int* out) {
@@ -1021,9 +1024,10 @@ static int resolve_lanes(int requested, int npad, int n_chains, int* out) {
 }
 
 // Producer warps (anneal_ws_kernel) pay while the chain warps alone leave the schedulers idle: measured on B200 for the
-// 8-lane geometry up to kWsMaxChains chains.  PB200_WS=0 / 1 forces the choice (A/B runs, tests).
+// 8-lane geometry, +10 % at 1024 chains, +19 % at 3072, break-even at 4096, slower above (profiles/README.md).
+// PB200_WS=0 / 1 forces the choice (A/B runs, tests).
 #ifndef PB200_WS_MAX_CHAINS
-#define PB200_WS_MAX_CHAINS 6144
+#define PB200_WS_MAX_CHAINS 4095
 #endif
 static bool use_producer_warps(int lanes, int n_chains) {
     if (const char* env = std::getenv("PB200_WS")) {

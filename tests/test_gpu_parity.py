@@ -380,12 +380,11 @@ def test_misaligned_chains_in_one_warp_take_the_generic_path():
 
 
 def test_lane_choice_follows_batch_size():
-    assert engine.choose_lanes(32, 1000) == 32
-    assert engine.choose_lanes(32, 4096) == 8
-    assert engine.choose_lanes(32, 8192) == 8
-    assert engine.choose_lanes(32, 65536) == 8
+    assert engine.choose_lanes(32, 10) == 8 and engine.choose_lanes(32, 4096) == 8 and engine.choose_lanes(32, 65536) == 8
     assert engine.choose_lanes(64, 65536) == 16 and engine.choose_lanes(64, 100) == 32
     assert engine.choose_lanes(256, 65536) == 32
+    assert engine.uses_producer_warps(8, 1024) and not engine.uses_producer_warps(8, 4096)
+    assert not engine.uses_producer_warps(32, 1024)
 
 
 def test_mh_sample_overflow_is_reported():
