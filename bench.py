@@ -304,7 +304,15 @@ def main():
                     'kernel_ms': k_ms, 'peak_source': src,
                     'algorithmic_bytes_per_chain_step': stream_bytes,
                     'note': 'streaming-formulation bound; the kernel keeps chain state in registers, so DRAM '
-                            'traffic is ~0 and the binding resource is FP32/MUFU issue (DESIGN.md)'}
+                            'traffic is ~0 and the binding resource is the FMA pipe / instruction issue (DESIGN.md)'}
+        if sa.problem.npad == 32:
+            # measured instruction-pipe bound of this kernel (ncu opcode mix x the per-scheduler
+            # throughputs of scripts/pipe_probe.cu -> ~50 FMA-pipe cycles per chain-step) at the 1965 MHz these
+            # B200s run at under this load (see "clocks")
+            pipe_peak = 148 * 4 * 1.965e9 / 50.0
+            steps_per_s = b_local * n_iter * steps / (k_ms * 1e-3)
+            roofline['pipe_bound'] = {'fma_pipe_cycles_per_chain_step': 50, 'peak_chain_steps_per_s': pipe_peak,
+                                      'achieved_chain_steps_per_s': steps_per_s, 'frac': steps_per_s / pipe_peak}
 
     # ---------------- end-to-end arm: host arrays in, host arrays out, every step ----------------
     e2e_steps, e2e_warm = max(3, min(args.steps, 10)), 2

@@ -200,7 +200,7 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
 // the group must replay the block step by step (bound not provably inside the safe radius).
 // ----------------------------------------------------------------------------------------------
 template <int LPC, int CPL>
-__device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const float (&z)[CPL][4],
+__device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf, const float (&z)[CPL][4],
                                            const float (&e)[4], ChainState<CPL>& c) {
     float v[16];
 #pragma unroll
@@ -224,10 +224,30 @@ __device__ __forceinline__ bool block_step(bool live, float Tf, float sf, const 
         v[13] = __fmaf_rn(hz[2], z[r][3], v[13]);                // C23
         v[15] = __fmaf_rn(c.w[r], c.w[r], v[15]);                // R0 = |w|^2
     }
+    if constexpr (LPC == 8) {
+        // reduce-scatter + broadcast instead of 16 full butterflies: at every level a lane keeps the half of the
+        // values selected by its lane bit and ships the other half (8 + 4 + 2 exchanges), then each of the 16 sums
+        // is broadcast from the lane that owns it: 30 SHFL + 14 FADD instead of 48 + 48.  Every sum is formed by the
+        // same additions in the same order as the plain xor butterfly (own + partner, distances 4, 2, 1).
+        const bool b4 = (gl & 4) != 0, b2 = (gl & 2) != 0, b1 = (gl & 1) != 0;
+        float a8[8], a4[4], a2[2];
 #pragma unroll
-    for (int m = LPC / 2; m >= 1; m >>= 1) {
+        for (int i = 0; i < 8; ++i)
+            a8[i] = __fadd_rn(b4 ? v[i + 8] : v[i], __shfl_xor_sync(kFull, b4 ? v[i] : v[i + 8], 4));
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(kFull, v[i], m));
+        for (int i = 0; i < 4; ++i)
+            a4[i] = __fadd_rn(b2 ? a8[i + 4] : a8[i], __shfl_xor_sync(kFull, b2 ? a8[i] : a8[i + 4], 2));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            a2[i] = __fadd_rn(b1 ? a4[i + 2] : a4[i], __shfl_xor_sync(kFull, b1 ? a4[i] : a4[i + 2], 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(kFull, a2[j & 1], j >> 1, 8);
+    } else {
+#pragma unroll
+        for (int m = LPC / 2; m >= 1; m >>= 1) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fadd_rn(v[i], __shfl_xor_sync(kFull, v[i], m));
+        }
     }
     float delta[4];
     bool acc[4];
@@ -335,7 +355,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             for (int r = 0; r < CPL; ++r) c.w[r] += (z[r][0] + z[r][1]) * (z[r][2] + z[r][3]) * e[r & 3];
             todo = false;
 #else
-            todo = block_step<LPC, CPL>(live, Tf, sf, z, e, c);
+            todo = block_step<LPC, CPL>(gl, live, Tf, sf, z, e, c);
 #endif
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }

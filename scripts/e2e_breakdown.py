@@ -34,9 +34,9 @@ for s in range(12):
 print({k: round(1e3 * v / 10, 3) for k, v in acc.items()}, 'ms per step')
 import cProfile, pstats
 pr = cProfile.Profile(); pr.enable()
-for s in range(5):
+for s in range(20):
     sa = SimulatedAnnealing(cfg, kernel, settings(s)); sync()
-pr.disable(); pstats.Stats(pr).sort_stats("tottime").print_stats(22)
+pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(45)
 
 # the same loop without intermediate syncs (what bench.py's e2e arm does)
 sync(); t0 = time.perf_counter()
