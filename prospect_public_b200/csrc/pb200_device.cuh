@@ -106,20 +106,9 @@ __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t ch
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {
         const int coord = gl + LPC * r;
-#ifdef PB200_EXPERIMENT_FAKE_RNG   /* timing experiment only: cheap stand-in variates, results are meaningless */
-        {
-            const uint32_t hsh = blk * 2654435761u + (uint32_t)coord * 40503u + chain_id * 97u + k0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                w[k] = (hsh >> k) * 0x9E3779B9u | 0x01000000u;
-                z[r][k] = __uint_as_float(0x3f800000u | ((hsh * (2u * k + 3u)) & 0x7fffffu)) - 1.5f;
-            }
-        }
-#else
         philox4x32_10(blk, coord == n ? kAcceptSlot : (uint32_t)coord, chain_id, 0u, k0, k1, w);
         box_muller(w[0], w[1], z[r][0], z[r][1]);
         box_muller(w[2], w[3], z[r][2], z[r][3]);
-#endif
         if (coord >= n) { z[r][0] = z[r][1] = z[r][2] = z[r][3] = 0.0f; }
         if (r == acc_r) {
 #pragma unroll

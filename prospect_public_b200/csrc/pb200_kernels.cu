@@ -350,13 +350,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
         bool todo = live, cnt_done = false;
         if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && off == 0u && cnt == 4u) {
-#ifdef PB200_EXPERIMENT_FAKE_UPDATE   /* timing experiment only: consume the variates with no chain update */
-#pragma unroll
-            for (int r = 0; r < CPL; ++r) c.w[r] += (z[r][0] + z[r][1]) * (z[r][2] + z[r][3]) * e[r & 3];
-            todo = false;
-#else
             todo = block_step<LPC, CPL>(gl, live, Tf, sf, z, e, c);
-#endif
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }
 #pragma unroll 1
