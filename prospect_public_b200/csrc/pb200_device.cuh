@@ -129,6 +129,9 @@ __device__ __forceinline__ void draw_block(uint32_t k0, uint32_t k1, uint32_t ch
 // variates.  full[slot] / empty[slot] are mbarriers with 32 arrivals (every lane arrives for its own accesses).
 // ----------------------------------------------------------------------------------------------
 constexpr int kRingDepth = 4;
+#ifndef PB200_MBAR_SUSPEND_NS
+#define PB200_MBAR_SUSPEND_NS 20000u      // suspend-time hint of a pending mbarrier wait
+#endif
 
 __device__ __forceinline__ uint32_t smem_addr(const void* ptr) { return (uint32_t)__cvta_generic_to_shared(ptr); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -141,9 +144,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"     // suspends up to the hint, no busy spin
         "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+        : "=r"(ok) : "r"(bar), "r"(parity), "r"(PB200_MBAR_SUSPEND_NS) : "memory");
     return ok != 0u;
 }
 
