@@ -534,3 +534,47 @@ def test_signalled_launch_ships_complete_iterations(lanes, tol):
                            c.view(torch.int64) if c.dtype == torch.float64 else c)
     if tol == 0.02:
         assert len(np.unique(out['plain'][3].cpu().numpy())) > 1        # chains stopped at different iterations
+
+
+@pytest.mark.parametrize('lanes', [32, 8])
+def test_buffers_are_never_written_out_of_bounds(lanes):
+    """Canary check (compute-sanitizer is not available on this pool): sample and record buffers sit inside larger
+    allocations filled with a sentinel; chains overflow the sample capacity and run more iterations than the
+    records have rows; 5 chains leave the last warp of every geometry partly empty.  Nothing outside the buffers
+    changes and the overflow is reported through the counters."""
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    b, cap, npad, pad, mark = 5, 7, hp.npad, 96, 777
+    for mode in (capi.RECORD_ACCEPTED, capi.RECORD_THINNED):
+        xs = torch.full((pad + b * cap * npad + pad,), float(mark), dtype=torch.float64, device=DEV)
+        ll = torch.full((pad + b * cap + pad,), float(mark), dtype=torch.float64, device=DEV)
+        mu = torch.full((pad + b * cap + pad,), mark, dtype=torch.int32, device=DEV)
+        cn = torch.full((pad + b + pad,), mark, dtype=torch.int32, device=DEV)
+        cn[pad:pad + b] = 0
+        smp = engine.Samples(prob, b, cap, mode, 1)
+        smp.c = capi.Samples(mode, 1, cap, capi.C.c_void_p(xs.data_ptr() + 8 * pad), capi.C.c_void_p(ll.data_ptr() + 8 * pad),
+                             capi.C.c_void_p(mu.data_ptr() + 4 * pad), capi.C.c_void_p(cn.data_ptr() + 4 * pad))
+        chains = engine.ChainBatch(prob, np.zeros((b, 20)), 0, temperature=1.0, step_size=0.5)
+        engine.mh_run(prob, chains, 60, SEED, smp, lanes=lanes)
+        torch.cuda.synchronize()
+        for buf, n_in in ((xs, b * cap * npad), (ll, b * cap), (mu, b * cap), (cn, b)):
+            assert torch.all(buf[:pad] == mark) and torch.all(buf[pad + n_in:] == mark)
+        assert torch.all(cn[pad:pad + b] > cap)                  # rows were dropped and counted, not written
+    # records: 2 rows allocated, 5 iterations run
+    tmpl = engine.Records(prob, b, 2)
+    stride = tmpl.stride
+    big = torch.full(((2 + 2) * stride,), float(mark), dtype=torch.float64, device=DEV)
+    big_last = torch.full(((2 + 2) * stride,), float(mark), dtype=torch.float64, device=DEV)
+    base = big.data_ptr() + 8 * stride
+    addr = lambda name: capi.C.c_void_p(base + 8 * tmpl.offsets[name])
+    tmpl.c = capi.Records(2, stride, addr('best_loglkl'), addr('last_loglkl'), addr('temperature'), addr('step_size'),
+                          addr('accepted'), addr('best_x'), capi.C.c_void_p(big_last.data_ptr() + 8 * stride))
+    chains = engine.ChainBatch(prob, np.zeros((b, 20)), 0, temperature=1.0, step_size=0.5)
+    sched = engine.make_schedule(37, 0.9, capi.STEP_ADAPTIVE_FIXED, 1.0, (0.19, 0.21), 0.3, None)
+    engine.anneal_run(prob, chains, sched, tmpl, 5, SEED, lanes=lanes)
+    torch.cuda.synchronize()
+    for buf in (big, big_last):
+        assert torch.all(buf[:stride] == mark) and torch.all(buf[3 * stride:] == mark)
+    rows = big[stride:3 * stride].view(2, stride)
+    assert torch.all(rows[:, :b] != mark)                        # both allocated rows were filled
+    assert np.all(chains.iteration.cpu().numpy() == 5) and np.all(chains.steps_done.cpu().numpy() == 5 * 37)
