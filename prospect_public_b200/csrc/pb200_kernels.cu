@@ -353,13 +353,15 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             todo = block_step<LPC, CPL>(gl, live, Tf, sf, z, e, c);
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }
-#pragma unroll 1
-        for (uint32_t q = 0; q < (cnt_done ? 0u : cnt); ++q) {
-            const uint32_t k = off + q;
+        // the (up to) four steps of this block, step index k static so that z[.][k] are plain registers (a dynamic
+        // k costs a select ladder per coordinate and step); off / cnt are warp-uniform
 #pragma unroll
-            for (int r = 0; r < CPL; ++r) zk[r] = k == 0 ? z[r][0] : (k == 1 ? z[r][1] : (k == 2 ? z[r][2] : z[r][3]));
-            const float ek = k == 0 ? e[0] : (k == 1 ? e[1] : (k == 2 ? e[2] : e[3]));
-            one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, todo, t + q, Tf, sf, zk, ek, c, ws, rc);
+        for (uint32_t k = 0; k < 4u; ++k) {
+            if (!cnt_done && k >= off && k < off + cnt) {
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
+                one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, todo, t + (k - off), Tf, sf, zk, e[k], c, ws, rc);
+            }
         }
         i += cnt;
         if constexpr (ZBUF) {
