@@ -210,6 +210,37 @@ __device__ __forceinline__ bool ring_store(Ring& rg, int lane, int gi, int gl, c
     return true;
 }
 
+// acc[r] += sum_j m[j][gl + LPC r] * qs[j], j ascending, one FMA per term (the order the oracle uses).  The loads of
+// four rows are issued before their FMAs: the loop is bound by the latency of the L2-resident matrix rows (one
+// 8 * npad byte row per j), not by FP64 throughput, so memory-level parallelism is what counts.
+template <int LPC, int CPL>
+__device__ __forceinline__ void matvec_rows(const double* __restrict__ m, const double* qs, int n, double (&acc)[CPL]) {
+    // (measured: pays for the wide geometries, 256-D profile 4.55 -> 4.40 ms; costs 4 % at npad = 32, where the 30
+    // short rows are L1 hits and the extra live registers hurt the step loop -- so exact_eval only uses it for
+    // rows of >= 1 KB)
+    constexpr int NPAD = LPC * CPL, UN = 4;
+    int j = 0;
+    for (; j + UN <= n; j += UN) {
+        double a[UN][CPL];
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) a[u][r] = __ldg(m + (size_t)(j + u) * NPAD + LPC * r);
+        }
+#pragma unroll
+        for (int u = 0; u < UN; ++u) {
+            const double qj = qs[j + u];
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) acc[r] = fma(a[u][r], qj, acc[r]);
+        }
+    }
+    for (; j < n; ++j) {
+        const double qj = qs[j];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) acc[r] = fma(__ldg(m + (size_t)j * NPAD + LPC * r), qj, acc[r]);
+    }
+}
+
 // ----------------------------------------------------------------------------------------------
 // Exact FP64 evaluation at a position: loglkl = sum_i q_i (1/2 (S_aa q)_i + f s_ab_i) + c0 and,
 // optionally, the whitened gradient gt = G q + h.  `qs` is this group's [npad] double staging row.
@@ -228,14 +259,19 @@ __device__ __forceinline__ double exact_eval(const pb200_problem& p, int pt, con
         g[r] = 0.0;
     }
     __syncwarp();
-    const double* __restrict__ saa = p.saa + gl;
-    const double* __restrict__ gtm = p.g_t + (size_t)pt * NPAD * NPAD + gl;
-    for (int j = 0; j < p.n; ++j) {
-        const double qj = qs[j];
+    if constexpr (NPAD >= 128) {      // long rows: batched loads, one matrix at a time (matvec_rows)
+        matvec_rows<LPC, CPL>(p.saa + gl, qs, p.n, v);
+        if (WITH_GRAD) matvec_rows<LPC, CPL>(p.g_t + (size_t)pt * NPAD * NPAD + gl, qs, p.n, g);
+    } else {                          // short rows (L1 hits): both matrices in one pass
+        const double* __restrict__ saa = p.saa + gl;
+        const double* __restrict__ gtm = p.g_t + (size_t)pt * NPAD * NPAD + gl;
+        for (int j = 0; j < p.n; ++j) {
+            const double qj = qs[j];
 #pragma unroll
-        for (int r = 0; r < CPL; ++r) {
-            v[r] = fma(__ldg(saa + j * NPAD + LPC * r), qj, v[r]);
-            if (WITH_GRAD) g[r] = fma(__ldg(gtm + j * NPAD + LPC * r), qj, g[r]);
+            for (int r = 0; r < CPL; ++r) {
+                v[r] = fma(__ldg(saa + j * NPAD + LPC * r), qj, v[r]);
+                if (WITH_GRAD) g[r] = fma(__ldg(gtm + j * NPAD + LPC * r), qj, g[r]);
+            }
         }
     }
     __syncwarp();
