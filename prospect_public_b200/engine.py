@@ -33,8 +33,11 @@ class ChainBatch:
             'secant_prev_ar')
     _i32 = ('point', 'iteration', 'status', 'secant_stage')
 
+    STATE_KEYS = ('x', 'loglkl', 'temperature', 'step_size', 'current_best', 'secant_prev_mult', 'secant_cur_mult',
+                  'secant_prev_ar', 'steps_done', 'iteration', 'status', 'secant_stage')
+
     def __init__(self, problem: DeviceProblem, x0, point, chain_id=None, temperature=1.0, step_size=1.0,
-                 current_best=math.inf, steps_done=0):
+                 current_best=math.inf, steps_done=0, state=None):
         from .problem import upload_packed
         dev = problem.device
         self.problem = problem
@@ -53,6 +56,12 @@ class ChainBatch:
             'steps_done': full(steps_done, np.int32), 'iteration': np.zeros(b, dtype=np.int32),
             'status': np.zeros(b, dtype=np.int32), 'secant_stage': np.zeros(b, dtype=np.int32),
         }
+        if state is not None:                 # resume: every per-chain quantity of an earlier run (host_state())
+            for key in self.STATE_KEYS:
+                if key == 'x':
+                    host['x'][:, :problem.n] = np.asarray(state['x'], dtype=np.float64)[:, :problem.n]
+                else:
+                    host[key] = np.asarray(state[key], dtype=host[key].dtype).reshape(b).copy()
         t = upload_packed(host, dev)          # one pinned staging buffer, one H2D copy
         self._storage = t.pop('_storage')
         for name, tensor in t.items():
@@ -60,6 +69,12 @@ class ChainBatch:
         self.c = capi.Chains(b, *(capi.ptr(getattr(self, k)) for k in (
             'x', 'loglkl', 'temperature', 'step_size', 'current_best', 'point', 'chain_id', 'steps_done',
             'iteration', 'status', 'secant_stage', 'secant_prev_mult', 'secant_cur_mult', 'secant_prev_ar')))
+
+    def host_state(self):
+        """Everything needed to continue these chains later (ChainBatch(..., state=...)): host arrays per chain."""
+        out = {key: getattr(self, key).cpu().numpy() for key in self.STATE_KEYS}
+        out['x'] = out['x'][:, :self.problem.n]
+        return out
 
     def positions(self):
         return self.x[:, :self.problem.n].cpu().numpy()

@@ -80,9 +80,12 @@ class SimulatedAnnealing:
         fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
         self.problem = kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covs[self.local_points])
         cb = np.broadcast_to(np.asarray(s.get('current_best_loglkl', math.inf), dtype=np.float64), (self.n_points,))
-        self.batch = engine.ChainBatch(self.problem, starts[pt], point_local,
-                                       chain_id=global_chain_index(pt, rep, self.n_points),
-                                       temperature=s['temperature'], step_size=s['step_size'], current_best=cb[pt])
+        gid = global_chain_index(pt, rep, self.n_points)
+        resumed = s.get('chain_state')            # global-order per-chain state of an interrupted run (run.resume)
+        self.batch = engine.ChainBatch(self.problem, starts[pt], point_local, chain_id=gid,
+                                       temperature=s['temperature'], step_size=s['step_size'], current_best=cb[pt],
+                                       state=None if resumed is None else {k: np.asarray(v)[gid]
+                                                                           for k, v in resumed.items()})
         change = s.get('step_size_change')
         interval = prof.step_size_adaptive_interval or (0.0, 1.0)
         mult = prof.step_size_adaptive_multiplier
@@ -316,6 +319,37 @@ class SimulatedAnnealing:
         for rank in range(self.world):
             pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
             out[global_chain_index(pt, rep, self.n_points)] = allst[rank, :len(pt)]
+        return out
+
+    def global_chain_state(self):
+        """Per-chain state of every chain of the job in global order (what run.resume needs to continue the run):
+        position, loglkl, temperature, step size, current best, step-size history, step / iteration counters,
+        status.  One small all-gather for N > 1."""
+        import torch
+        from .engine import ChainBatch
+        local = self.batch.host_state()
+        if self.world == 1:
+            return local
+        import torch.distributed as dist
+        n = self.problem.n
+        keys = [k for k in ChainBatch.STATE_KEYS if k != 'x']
+        pack = np.zeros((self.b_alloc, n + len(keys)))
+        pack[:self.n_chains, :n] = local['x']
+        for i, k in enumerate(keys):
+            pack[:self.n_chains, n + i] = local[k]          # counters are small integers: exact in FP64
+        mine = torch.as_tensor(pack, device=self.problem.device)
+        allp = torch.empty((self.world,) + tuple(mine.shape), dtype=torch.float64, device=self.problem.device)
+        dist.all_gather_into_tensor(allp.view(-1), mine.view(-1))
+        allp = allp.cpu().numpy()
+        b_glob = self.n_points * self.reps
+        out = {'x': np.zeros((b_glob, n))}
+        out.update({k: np.zeros(b_glob, dtype=local[k].dtype) for k in keys})
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            ids = global_chain_index(pt, rep, self.n_points)
+            out['x'][ids] = allp[rank, :len(ids), :n]
+            for i, k in enumerate(keys):
+                out[k][ids] = allp[rank, :len(ids), n + i].astype(local[k].dtype)
         return out
 
     def reduce_over_iterations(self):

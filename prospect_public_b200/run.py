@@ -44,21 +44,26 @@ def _barrier():
         dist.barrier()
 
 
-def run(user_inp, quiet=True):
-    """Run a job.  Returns a dict with the records, the analysis products and timings."""
+def run(user_inp, quiet=True, stop_after=None):
+    """Run a job (a .yaml file or dict) or resume one (the folder of an earlier run, prospect/io.py:15-24).  Returns
+    a dict with the records, the analysis products and timings.  `stop_after` ends an annealing job after that
+    many iterations with a complete snapshot, as an interrupted run would leave it."""
     t_start = time.perf_counter()
-    config_yaml, resume = pio.read_user_input(user_inp) if isinstance(user_inp, str) else (user_inp, False)
+    config_yaml, is_folder = pio.read_user_input(user_inp) if isinstance(user_inp, str) else (user_inp, False)
     rank, world, _ = init_from_env('nccl') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else dist_info()
-    if resume:
-        raise NotImplementedError('Resuming a run folder is not part of this round (SURVEY.md section 8f, N2).')
     config = Configuration(config_yaml)
+    if is_folder:
+        out = resume(config, user_inp)
+        out['time_to_result_s'] = time.perf_counter() - t_start
+        out['config'] = config
+        return out
     if rank == 0:
         pio.prepare_run(config)
     _barrier()
     if config.run.jobtype == 'mcmc':
         out = run_mcmc(config)
     else:
-        out = run_annealing(config)
+        out = run_annealing(config, stop_after=stop_after)
     out['time_to_result_s'] = time.perf_counter() - t_start          # incl. the snapshot pickles
     if 't_results_written' in out:
         out['time_to_profile_s'] = out['t_results_written'] - t_start  # yaml read -> result files written (SURVEY M1)
@@ -66,8 +71,10 @@ def run(user_inp, quiet=True):
     return out
 
 
-def run_annealing(config, keep_positions=True, starts=None, values=None, seed=None, write=True):
-    """jobtype profile / global_optimisation.  `starts` / `values` / `seed` let reanneal() supply the start points."""
+def run_annealing(config, keep_positions=True, starts=None, values=None, seed=None, write=True, stop_after=None,
+                  resume_from=None):
+    """jobtype profile / global_optimisation.  `starts` / `values` / `seed` let reanneal() supply the start points;
+    `resume_from` = (state dict, RunRecord) of an interrupted run continues its chains where they stopped."""
     import torch
     rank, world, _ = dist_info()
     device = _device()
@@ -86,6 +93,10 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
         kernel.set_fixed_parameters({prof.parameter: float(values[0])})
     n_iter = int(prof.max_iterations)
     reps = int(prof.repetitions)
+    done, old_rec = 0, None
+    if resume_from is not None:
+        done, old_rec = int(resume_from[0]['iterations_done']), resume_from[1]
+    to_run = max(0, n_iter - done) if stop_after is None else max(0, min(n_iter - done, int(stop_after)))
     settings = {
         'current_best_loglkl': starts.initial_loglkl,
         'initial_position': starts.positions,
@@ -94,34 +105,64 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
         'temperature_change': get_temperature_change(config),
         'step_size': prof.step_size_range[0],
         'step_size_change': get_initial_step_size_change(config),
-        'iteration_number': 0,
+        'iteration_number': done,
         'repetitions': reps,
         'fixed_param_val': values if config.run.jobtype == 'profile' else None,
         'max_rows': n_iter,
         'seed': config.seed if seed is None else seed,
     }
+    if resume_from is not None:
+        settings['chain_state'] = resume_from[0]['chain_state']
     sa = SimulatedAnnealing(config, kernel, settings, keep_positions=keep_positions)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    gathered = sa.run_schedule(n_iter)
+    if to_run > 0:
+        sa.run_schedule(to_run)
     torch.cuda.synchronize()
     loop_s = time.perf_counter() - t0
     g = sa.global_records()
     best_ll, acc, step, temperature, best_x = g['best_loglkl'], g['accepted'], g['step_size'], g['temperature'], g['best_x']
+    chain_steps = int((acc >= 0).sum()) * int(prof.steps_per_iteration)    # global (records are gathered)
+    if old_rec is not None:                     # rows of the iterations that ran before the interruption
+        k_old = min(done, old_rec.best_loglkl.shape[0], n_iter)
+        best_ll[:k_old], acc[:k_old] = old_rec.best_loglkl[:k_old], old_rec.accepted[:k_old]
+        step[:k_old], temperature[:k_old] = old_rec.step_size[:k_old], old_rec.temperature[:k_old]
+        if best_x is not None and old_rec.best_x is not None:
+            best_x[:k_old] = old_rec.best_x[:k_old]
     status = sa.global_status()
-    ran = acc >= 0
-    chain_steps = int(ran.sum()) * int(prof.steps_per_iteration) * 1       # global (records are gathered)
     rec = analysis.RunRecord(values, reps, starts.names, best_ll, acc, best_x, status == capi.CONVERGED,
                              starts.initial_loglkl, starts.positions, starts.covmats, temperature, step)
     result = {'record': rec, 'chain_steps': chain_steps, 'loop_seconds': loop_s, 'optimiser': sa,
-              'status': status, 'values': values, 'seed': sa.seed}
+              'status': status, 'values': values, 'seed': sa.seed, 'iterations_done': sa.iterations_done}
+    chain_state = sa.global_chain_state()
     if rank == 0 and write:
-        result.update(write_outputs(config, rec, sa if world == 1 else None))
+        result.update(write_outputs(config, rec, sa if world == 1 and old_rec is None else None,
+                                    resume_state={'chain_state': chain_state, 'iterations_done': sa.iterations_done,
+                                                  'seed': sa.seed}))
     _barrier()
     return result
 
 
-def write_outputs(config, rec, sa=None):
+def resume(config, prospect_folder):
+    """`prospect <folder>` (prospect/io.py:15-24, prospect/communication.py:30-36): continue the chains of an
+    interrupted annealing run from the state in its snapshot -- position, temperature, step size and step-size
+    history, Philox step counter -- until every chain has run `profile.max_iterations` iterations (read from the
+    folder's log.yaml, so raising it there extends a finished run).  The continued run is step for step the run
+    that was never interrupted: same random streams, same records, same output files."""
+    if config.run.jobtype == 'mcmc':
+        raise NotImplementedError('Resuming jobtype mcmc: start a new job with start_from_position / covmat instead.')
+    config.io.dir = config.config_dict['io']['dir'] = prospect_folder
+    _, rec_old = load_record(prospect_folder)
+    state = pio.load_pickle(prospect_folder, 'pb200_state')
+    if 'chain_state' not in state:
+        raise ValueError(f'{prospect_folder}/pb200_state.pkl holds no chain state to resume from.')
+    from .initialise import StartingPoints
+    starts = StartingPoints(rec_old.names, rec_old.initial_position, rec_old.initial_covmat, rec_old.initial_loglkl)
+    return run_annealing(config, starts=starts, values=rec_old.values, seed=int(state['seed']),
+                         resume_from=(state, rec_old))
+
+
+def write_outputs(config, rec, sa=None, resume_state=None):
     """Analysis + result files + snapshot of a finished (or re-annealed) run; returns the analysis products."""
     prof = config.profile
     result = {}
@@ -147,11 +188,11 @@ def write_outputs(config, rec, sa=None):
             result['bestfits'] = {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}
     result['t_results_written'] = time.perf_counter()      # profile/<p>.txt (or results.txt) is on disk here
     if config.io.write:
-        dump_snapshot(config, rec)
+        dump_snapshot(config, rec, resume_state=resume_state)
     return result
 
 
-def dump_snapshot(config, rec, reference_compatible=True):
+def dump_snapshot(config, rec, reference_compatible=True, resume_state=None):
     """Snapshot of a finished run:
       pb200_config.pkl / pb200_state.pkl   this package's own dense records (a few MB);
       config.pkl / state.pkl               PROSPECT's own pickle layout (compat.export_reference_snapshot), so that
@@ -164,6 +205,9 @@ def dump_snapshot(config, rec, reference_compatible=True):
              'record': {k: getattr(rec, k) for k in ('values', 'reps', 'names', 'best_loglkl', 'accepted', 'best_x',
                                                      'converged', 'initial_loglkl', 'initial_position',
                                                      'initial_covmat', 'temperature', 'step_size')}}
+    if resume_state is not None:            # per-chain state: `prospect_public_b200 <folder>` continues from here
+        state.update(chain_state=resume_state['chain_state'], iterations_done=int(resume_state['iterations_done']),
+                     seed=int(resume_state['seed']))
     pio.dump_pickle(state, config.io.dir, 'pb200_state')
     if reference_compatible:
         n_tasks = int((rec.accepted >= 0).sum())
@@ -393,7 +437,7 @@ def run_mcmc(config, max_rounds=64):
 def run_from_shell(argv=None):
     import argparse
     parser = argparse.ArgumentParser(prog='prospect_public_b200')
-    parser.add_argument('input_file', help='input .yaml')
+    parser.add_argument('input_file', help='input .yaml, or the folder of an earlier run to resume it')
     parser.add_argument('--analyse', action='store_true', help='re-analyse an existing run folder')
     parser.add_argument('--reanneal', metavar='YAML', help='re-anneal the run folder with the schedule in YAML')
     args = parser.parse_args(argv)

@@ -32,6 +32,20 @@ for label, kw in (('points sharded (10 values x 6 reps)', dict(repetitions=6)),
               f'chain_steps {res["chain_steps"]}')
         assert err <= 1e-3 and ran and files
     dist.barrier()
+# interrupted + resumed run (per-chain state gathered over the ranks) == uninterrupted run
+kw = dict(repetitions=6, max_iterations=8)
+full = run(annealing_yaml(paths, os.path.join(base, 'out_full'), **kw))
+run(annealing_yaml(paths, os.path.join(base, 'out_part'), **kw), stop_after=3)
+dist.barrier()
+res = run(os.path.join(base, 'out_part'))
+if dist_info()[0] == 0:
+    same = all(np.array_equal(getattr(res['record'], key), getattr(full['record'], key))
+               for key in ('best_loglkl', 'accepted', 'best_x', 'step_size'))
+    a = open(os.path.join(base, 'out_part', 'profile', 'x2.txt'), 'rb').read()
+    b = open(os.path.join(base, 'out_full', 'profile', 'x2.txt'), 'rb').read()
+    print(f'resume: world {dist_info()[1]} records identical {same}, profile/x2.txt identical {a == b}')
+    assert same and a == b
+dist.barrier()
 # jobtype mcmc sharded over the ranks: chain files and statistics must not depend on the number of GPUs
 from prospect_public_b200.config import Configuration
 from prospect_public_b200.kernels import initialise_kernel

@@ -258,6 +258,31 @@ def test_reanneal_continues_from_the_best_points(tmp_path):
     assert np.allclose(prof['-loglkl'], ll_second, rtol=1e-9)
 
 
+@pytest.mark.parametrize('multiplier', [0.3, 'adaptive'])
+def test_interrupted_run_resumes_to_identical_outputs(tmp_path, multiplier):
+    """N2 resume (`prospect <folder>`, prospect/io.py:15-24, communication.py:30-36): a run stopped after 4 of 9
+    iterations leaves a complete snapshot; running the FOLDER continues every chain (position, temperature, step
+    size and its secant history, Philox step counter) and ends with byte-identical result files and bit-identical
+    records to the run that was never interrupted.  Resuming a finished folder runs nothing."""
+    paths, k = _inputs(tmp_path, 20)
+    kw = dict(values=[-0.5, 0.3, 1.1], repetitions=3, max_iterations=9, temperature_range=[0.1, 1.0e-4],
+              step_size_adaptive_multiplier=multiplier, step_size_adaptive_interval=[0.2, 0.3])
+    full = run(annealing_yaml(paths, str(tmp_path / 'full'), **kw))
+    part = run(annealing_yaml(paths, str(tmp_path / 'part'), **kw), stop_after=4)
+    assert part['iterations_done'] == 4 and np.all(part['record'].accepted[4:] == -1)
+    assert np.array_equal(part['record'].best_loglkl[:4], full['record'].best_loglkl[:4])
+    res = run(str(tmp_path / 'part'))
+    assert res['iterations_done'] == 9
+    assert res['chain_steps'] == 250 * int((full['record'].accepted[4:] >= 0).sum()) > 0     # only the new rows ran
+    for key in ('best_loglkl', 'accepted', 'best_x', 'temperature', 'step_size', 'converged'):
+        assert np.array_equal(getattr(res['record'], key), getattr(full['record'], key)), key
+    for name in ('x2.txt', 'x2_status.txt', 'x2_intervals.txt'):
+        with open(tmp_path / 'part' / 'profile' / name, 'rb') as fa, open(tmp_path / 'full' / 'profile' / name, 'rb') as fb:
+            assert fa.read() == fb.read(), name
+    again = run(str(tmp_path / 'part'))
+    assert again['chain_steps'] == 0 and np.array_equal(again['record'].best_loglkl, full['record'].best_loglkl)
+
+
 def test_start_from_profile_and_explicit_gaussian_kernel(tmp_path):
     """N4: `start_from_profile` (+ covmat from the MCMC) starts every value from the nearest old bestfit
     (initialise_optimiser_task.py:39-62); and the explicit `function: gaussian` kernel-settings file
