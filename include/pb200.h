@@ -170,6 +170,39 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
                      const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream);
 
 /*
+ * Exchange buffers of the ranks of a sharded job, all mapped into this process (CUDA peer memory over NVLink /
+ * NVSwitch, e.g. torch symmetric memory).  With them the annealing kernel does the iteration-boundary all-gather
+ * ITSELF: next to its own record row it stores the per-chain scalars of iteration k into slot `rank` of row k of
+ * EVERY rank's buffer, then (after a system-scope fence) adds 1 to counter `it` of every rank.  On a rank, counter
+ * `it` therefore reaches the total number of chain warps of the whole job exactly when the gathered row of launch
+ * iteration `it` is complete there.  No collective call, no extra kernel, no packing.
+ *   buffer[r]   [rows][n_peers][rank_stride] doubles; block of (row k, rank q) at k * row_stride + q * rank_stride:
+ *               [best_loglkl | last_loglkl | temperature | step_size] (n_alloc doubles each), accepted (n_alloc int32)
+ *   progress[r] [>= n_iter] uint32, zeroed (on every rank, before any rank launches) by the caller
+ */
+#define PB200_MAX_PEERS 16
+typedef struct pb200_peers {
+    int32_t   n_peers;                      /* ranks (0: no exchange) */
+    int32_t   rank;                         /* this rank's slot */
+    int32_t   n_alloc;                      /* chains per block */
+    int32_t   rows;                         /* rows allocated in every buffer */
+    int64_t   row_stride;                   /* doubles */
+    int64_t   rank_stride;                  /* doubles, >= 4 * n_alloc + (n_alloc + 1) / 2 */
+    double*   buffer[PB200_MAX_PEERS];
+    uint32_t* progress[PB200_MAX_PEERS];
+} pb200_peers;
+
+/*
+ * pb200_anneal_run_signalled with the iteration-boundary all-gather fused into the kernel (see pb200_peers).
+ * `progress` / `out_target` as in pb200_anneal_run_signalled (local counters; may be NULL / NULL here).
+ * Replaces the per-task result hand-off of the reference's scheduler (prospect/communication.py:106-157) for jobs
+ * sharded over several GPUs.
+ */
+int pb200_anneal_run_shared(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                            const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
+                            const pb200_peers* peers, uint32_t* progress, int32_t* out_target, void* stream);
+
+/*
  * pb200_anneal_run that also SIGNALS its progress: `progress` is a device array of n_iter uint32 counters, zeroed
  * by the caller before the launch; counter k reaches *out_target (returned by this call) once every warp has made
  * its records of the launch's k-th iteration globally visible (or will never run it because all its chains

@@ -47,6 +47,15 @@ class Samples(C.Structure):
                 ('mult', _vp), ('count', _vp)]
 
 
+MAX_PEERS = 16
+
+
+class Peers(C.Structure):
+    _fields_ = [('n_peers', C.c_int32), ('rank', C.c_int32), ('n_alloc', C.c_int32), ('rows', C.c_int32),
+                ('row_stride', C.c_int64), ('rank_stride', C.c_int64), ('buffer', _vp * MAX_PEERS),
+                ('progress', _vp * MAX_PEERS)]
+
+
 # name -> (restype, argtypes); every name here must be declared in include/pb200.h
 SIGNATURES = {
     'pb200_last_error': (C.c_char_p, []),
@@ -59,6 +68,9 @@ SIGNATURES = {
                                              C.POINTER(Records), C.c_int32, C.c_uint64, C.c_int32, _vp,
                                              C.POINTER(C.c_int32), _vp]),
     'pb200_stream_wait_geq': (C.c_int, [_vp, _vp, C.c_uint32]),
+    'pb200_anneal_run_shared': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule),
+                                          C.POINTER(Records), C.c_int32, C.c_uint64, C.c_int32, C.POINTER(Peers), _vp,
+                                          C.POINTER(C.c_int32), _vp]),
     'pb200_mh_run': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_int32, C.c_uint64, C.POINTER(Samples),
                                _vp, C.c_int32, _vp]),
     'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),

@@ -429,7 +429,8 @@ template <int LPC, int CPL, int SRC>
 __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_chains& ch, const pb200_schedule& s,
                                             const pb200_records& rec, int n_iter, uint32_t k0, uint32_t k1,
                                             const float4* __restrict__ zbuf, int nb, uint32_t t_stream, int warp_slot,
-                                            double* stage_warp, Ring& ring, uint32_t* __restrict__ progress) {
+                                            double* stage_warp, Ring& ring, uint32_t* __restrict__ progress,
+                                            const pb200_peers& peers) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     constexpr bool ZBUF = SRC == kSrcStream;
     const int lane = threadIdx.x & 31, gi = lane / LPC, gl = lane % LPC;
@@ -507,6 +508,19 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
                     if (rec.last_x) rec.last_x[o + (size_t)chain * NPAD + gl + LPC * r] = x[r];
                 }
             }
+            // fused all-gather: the same scalars go into slot `rank` of row `row` of every rank's exchange buffer
+            if (peers.n_peers > 0 && gl == 0 && row < peers.rows) {
+                const size_t blk = (size_t)row * peers.row_stride + (size_t)peers.rank * peers.rank_stride;
+                const size_t na = (size_t)peers.n_alloc;
+                for (int q = 0; q < peers.n_peers; ++q) {
+                    double* dst = peers.buffer[q] + blk;
+                    dst[chain] = best_exact;
+                    dst[na + chain] = c.ll;
+                    dst[2 * na + chain] = st.temperature;
+                    dst[3 * na + chain] = st.step_size;
+                    reinterpret_cast<int32_t*>(dst + 4 * na)[chain] = nacc;
+                }
+            }
             schedule_next(s, st, nacc, best_exact);
             live = st.status == PB200_ACTIVE;
         }
@@ -515,9 +529,18 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
             __syncwarp();
             if (lane == 0) atomicAdd(progress + it, 1u);
         }
+        if (peers.n_peers > 0) { // ... and visible on every rank: count it there
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0)
+                for (int q = 0; q < peers.n_peers; ++q) atomicAdd_system(peers.progress[q] + it, 1u);
+        }
     }
-    if (progress && lane == 0) {  // iterations this warp will never run (all its chains stopped) count as done
-        for (int k = it; k < n_iter; ++k) atomicAdd(progress + k, 1u);
+    if (lane == 0) {             // iterations this warp will never run (all its chains stopped) count as done
+        if (progress)
+            for (int k = it; k < n_iter; ++k) atomicAdd(progress + k, 1u);
+        for (int q = 0; q < peers.n_peers; ++q)
+            for (int k = it; k < n_iter; ++k) atomicAdd_system(peers.progress[q] + k, 1u);
     }
     if (was_live) {
 #pragma unroll
@@ -541,14 +564,15 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
 template <int LPC, int CPL, bool ZBUF>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
 anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream, uint32_t* __restrict__ progress) {
+              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream, uint32_t* __restrict__ progress,
+              const __grid_constant__ pb200_peers peers) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
     const int wib = threadIdx.x >> 5;
     Ring none{};
     anneal_body<LPC, CPL, ZBUF ? kSrcStream : kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, zbuf, nb, t_stream,
                                                           blockIdx.x * kWarpsPerCta + wib, &stage[wib][0][0], none,
-                                                          progress);
+                                                          progress, peers);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -591,7 +615,7 @@ __device__ __forceinline__ void produce_variates(int n, int n_iter, uint32_t ste
 template <int LPC, int CPL>
 __global__ void __launch_bounds__(64 * kWsPairs, ws_min_ctas(LPC * CPL))
 anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-                 uint32_t k1, uint32_t* __restrict__ progress) {
+                 uint32_t k1, uint32_t* __restrict__ progress, const __grid_constant__ pb200_peers peers) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) unsigned char slots[kWsPairs][kRingDepth][ring_slot_bytes<CPL>()];
     __shared__ __align__(16) double stage[kWsPairs][G][NPAD];
@@ -631,10 +655,10 @@ anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_recor
     }
     if (paired)
         anneal_body<LPC, CPL, kSrcRing>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot, &stage[pair][0][0],
-                                        ring, progress);
+                                        ring, progress, peers);
     else
         anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot,
-                                          &stage[pair][0][0], ring, progress);
+                                          &stage[pair][0][0], ring, progress, peers);
     __syncwarp();
     if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ring.stop), "r"(1u) : "memory");
 }
@@ -1071,7 +1095,19 @@ int pb200_uses_producer_warps(int32_t lanes_per_chain, int32_t n_chains) {
 
 static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
                          const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
-                         uint32_t* progress, void* stream) {
+                         uint32_t* progress, void* stream, const pb200_peers* peers_in = nullptr) {
+    pb200_peers peers{};
+    if (peers_in && peers_in->n_peers > 0) {
+        peers = *peers_in;
+        if (peers.n_peers > PB200_MAX_PEERS || peers.rank < 0 || peers.rank >= peers.n_peers)
+            return fail("anneal_run_shared: need 1 <= n_peers <= PB200_MAX_PEERS and 0 <= rank < n_peers");
+        if (chains && peers.n_alloc < chains->n_chains) return fail("anneal_run_shared: n_alloc < n_chains");
+        if (peers.rank_stride < 4LL * peers.n_alloc + (peers.n_alloc + 1) / 2 ||
+            peers.row_stride < (int64_t)peers.n_peers * peers.rank_stride)
+            return fail("anneal_run_shared: exchange buffer strides too small");
+        for (int q = 0; q < peers.n_peers; ++q)
+            if (!peers.buffer[q] || !peers.progress[q]) return fail("anneal_run_shared: NULL peer buffer");
+    }
     if (validate(prob)) return 1;
     if (!chains || !sched || !rec) return fail("anneal_run: NULL argument");
     if (chains->n_chains <= 0 || n_iter <= 0) return 0;
@@ -1090,12 +1126,13 @@ static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, 
         const int pairs = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);
         const int ws_blocks = (pairs + kWsPairs - 1) / kWsPairs;
         PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_ws_kernel<LPC, CPL><<<ws_blocks, 64 * kWsPairs, 0, st>>>(
-                                                        *prob, *chains, *sched, *rec, n_iter, k0, k1, progress)));
+                                                        *prob, *chains, *sched, *rec, n_iter, k0, k1, progress,
+                                                        peers)));
         return check_cuda(cudaGetLastError(), "anneal_ws_kernel launch");
     }
     PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, false><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
                                                     *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u,
-                                                    progress)));
+                                                    progress, peers)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");
 }
 
@@ -1113,6 +1150,17 @@ int pb200_anneal_run_signalled(const pb200_problem* prob, const pb200_chains* ch
     if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
     *out_target = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);      // warps that own chains
     return anneal_launch(prob, chains, sched, rec, n_iter, seed, lanes_per_chain, progress, stream);
+}
+
+int pb200_anneal_run_shared(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
+                            const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
+                            const pb200_peers* peers, uint32_t* progress, int32_t* out_target, void* stream) {
+    if (!peers) return fail("anneal_run_shared: NULL peers");
+    if (!prob || !chains) return fail("anneal_run_shared: NULL argument");
+    int lanes;
+    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
+    if (out_target) *out_target = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);
+    return anneal_launch(prob, chains, sched, rec, n_iter, seed, lanes_per_chain, progress, stream, peers);
 }
 
 // cuStreamWaitValue32 through the runtime's driver entry point lookup: no link-time dependency on libcuda, so
@@ -1176,7 +1224,7 @@ int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* cha
     const int nb = (int)(((step_begin + (uint32_t)sched->steps_per_iteration - 1u) >> 2) - blk0 + 1u);
     PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, true><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
                                                     *prob, *chains, *sched, *rec, 1, 0u, 0u, (const float4*)zbuf, nb,
-                                                    step_begin, nullptr)));
+                                                    step_begin, nullptr, pb200_peers{})));
     return check_cuda(cudaGetLastError(), "anneal_kernel (streamed) launch");
 }
 

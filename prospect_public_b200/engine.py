@@ -197,6 +197,33 @@ def anneal_run_signalled(problem, chains: ChainBatch, schedule, records: Records
     return target.value
 
 
+def make_peers(rank, n_alloc, rows, rank_stride, buffer_ptrs, progress_ptrs):
+    """struct pb200_peers from the device addresses of every rank's exchange buffer / counters (peer memory)."""
+    n = len(buffer_ptrs)
+    if n > capi.MAX_PEERS:
+        raise capi.Pb200Error(f'at most {capi.MAX_PEERS} ranks can share exchange buffers')
+    peers = capi.Peers()
+    peers.n_peers, peers.rank, peers.n_alloc, peers.rows = n, int(rank), int(n_alloc), int(rows)
+    peers.row_stride, peers.rank_stride = int(n * rank_stride), int(rank_stride)
+    for q in range(n):
+        peers.buffer[q] = int(buffer_ptrs[q])
+        peers.progress[q] = int(progress_ptrs[q])
+    return peers
+
+
+def anneal_run_shared(problem, chains: ChainBatch, schedule, records: Records, n_iter, seed, peers, progress=None,
+                      stream=None, lanes=0):
+    """anneal_run whose kernel also stores every iteration's per-chain scalars into all ranks' exchange buffers and
+    counts arrivals there (pb200_anneal_run_shared).  Returns this rank's number of chain warps."""
+    target = C.c_int32(0)
+    _count()
+    capi.check(capi.lib().pb200_anneal_run_shared(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
+                                                  C.byref(records.c), int(n_iter), C.c_uint64(seed), int(lanes),
+                                                  C.byref(peers), capi.ptr(progress), C.byref(target),
+                                                  _stream_ptr(stream)))
+    return target.value
+
+
 def stream_wait_geq(stream, counter, index, value):
     """Make `stream` wait until counter[index] >= value (a device-side wait; the host does not block)."""
     capi.check(capi.lib().pb200_stream_wait_geq(_stream_ptr(stream), C.c_void_p(counter.data_ptr() + 4 * int(index)),

@@ -47,6 +47,32 @@ def step_mode_of(profile_cfg):
     return capi.STEP_ADAPTIVE_FIXED
 
 
+class ExchangeUnavailable(RuntimeError):
+    """Peer-mapped exchange buffers could not be set up (no symmetric memory / no peer access)."""
+
+
+_EXCHANGE = {}
+
+
+def _exchange_buffers(rows, world, scalar_len, device):
+    """Exchange buffer [rows, world, scalar_len] FP64 + arrival counters, allocated in torch symmetric memory and
+    mapped on every rank of the default group; cached per shape (they are scratch: results are copied out)."""
+    import torch
+    import torch.distributed as dist
+    key = (int(rows), int(world), int(scalar_len), str(device))
+    if key not in _EXCHANGE:
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            buf = symm_mem.empty((rows, world, scalar_len), dtype=torch.float64, device=device)
+            prog = symm_mem.empty(max(64, rows), dtype=torch.int32, device=device)
+            hb = symm_mem.rendezvous(buf, dist.group.WORLD)
+            hp = symm_mem.rendezvous(prog, dist.group.WORLD)
+        except Exception as exc:            # noqa: BLE001 -- any failure here means "use the NCCL path"
+            raise ExchangeUnavailable(f'{type(exc).__name__}: {exc}') from exc
+        _EXCHANGE[key] = {'buf': buf, 'prog': prog, 'hb': hb, 'hp': hp}
+    return _EXCHANGE[key]
+
+
 class SimulatedAnnealing:
     """optimise_settings (arrays over the P profile points; P = 1 for a global optimisation):
         initial_position [P, n] (varying order), covmat [P, n, n], current_best_loglkl [P],
@@ -112,6 +138,8 @@ class SimulatedAnnealing:
         self.bestfit = None
         self._gatherer = None
         self.signalled = True
+        import os
+        self.fused_exchange = os.environ.get('PB200_EXCHANGE', 'fused') == 'fused'
 
     @property
     def n_chains(self):
@@ -225,6 +253,14 @@ class SimulatedAnnealing:
         def ship(k):
             dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k, :self.records.scalar_len])
 
+        if self.fused_exchange and not self.streamed:
+            try:
+                self.run_fused_exchange(n_iterations, self._comm_stream)
+                return self.gathered
+            except ExchangeUnavailable as exc:        # no peer-mapped memory on this system: NCCL gathers instead
+                self.fused_exchange = False
+                if self.rank == 0:
+                    print(f'prospect_public_b200: fused exchange unavailable ({exc}); using NCCL all-gathers')
         if self.signalled and not self.streamed:
             self.run_signalled(n_iterations, ship, self._comm_stream)
             return self.gathered
@@ -267,6 +303,44 @@ class SimulatedAnnealing:
                 ship(k0 + i)
         compute.wait_stream(side_stream)
         self._progress = progress            # keep alive until the streams are done with it
+
+    def run_fused_exchange(self, n_iterations, side_stream):
+        """One fused launch whose kernel performs the iteration-boundary all-gather itself: every warp stores its
+        chains' per-iteration scalars straight into ALL ranks' exchange buffers (peer memory over NVLink / NVSwitch,
+        mapped through torch symmetric memory) and bumps an arrival counter on every rank (pb200_anneal_run_shared).
+        No collective call and no extra kernel sit on the path; the side stream only waits (device-side) for each
+        iteration's counter to reach the number of chain warps of the whole job and then copies the finished rows
+        into this optimiser's `gathered` tensor."""
+        import torch
+        from . import engine
+        ex = _exchange_buffers(self.max_rows, self.world, self.records.scalar_len, self.problem.device)
+        compute = torch.cuda.current_stream()
+        k0, b, n = self.iterations_done, self.b_alloc, n_iterations
+        rows = ex['buf'][k0:k0 + n]
+        rows[:, :, :2 * b] = math.inf                       # best / last loglkl of chains that do not run
+        rows[:, :, 2 * b:4 * b] = 0.0
+        rows[:, :, 4 * b:].view(torch.int32).fill_(-1)      # accepted = -1: did not run
+        ex['prog'][:n].zero_()
+        ex['hb'].barrier()                                  # every rank is prefilled before anyone stores remotely
+        ready = torch.cuda.Event()
+        ready.record(compute)                               # the side stream must not look at stale counters
+        peers = engine.make_peers(self.rank, b, self.max_rows, self.records.scalar_len, ex['hb'].buffer_ptrs,
+                                  ex['hp'].buffer_ptrs)
+        engine.anneal_run_shared(self.problem, self.batch, self.schedule, self.records, n, self.seed, peers, None,
+                                 None, self.lanes)
+        self.iterations_done += n
+        self.step_counter += n * self.schedule.steps_per_iteration
+        total = 0                                           # chain warps of the whole job
+        for r in range(self.world):
+            n_r = len(shard_grid(self.n_points, self.reps, r, self.world)[0])
+            lanes_r = self.lanes or engine.choose_lanes(self.problem.npad, n_r)
+            total += -(-n_r // (32 // lanes_r)) if n_r else 0
+        with torch.cuda.stream(side_stream):
+            side_stream.wait_event(ready)
+            for i in range(n):
+                engine.stream_wait_geq(side_stream, ex['prog'], i, total)
+            self.gathered[k0:k0 + n].copy_(rows, non_blocking=True)
+        compute.wait_stream(side_stream)
 
     def global_records(self):
         """Host arrays over ALL chains of the job in global order c = rep * P + point:

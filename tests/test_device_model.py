@@ -44,11 +44,12 @@ def test_struct_layouts_match_header():
         text = f.read()
     for cname, cls in (('pb200_problem', capi.Problem), ('pb200_chains', capi.Chains),
                        ('pb200_schedule', capi.Schedule), ('pb200_records', capi.Records),
-                       ('pb200_samples', capi.Samples)):
+                       ('pb200_samples', capi.Samples), ('pb200_peers', capi.Peers)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
-        fields = [re.findall(r'(\w+)\s*;', line)[0] for line in body.split('\n') if ';' in line]
+        fields = [re.findall(r'(\w+)\s*(?:\[\w+\])?\s*;', line)[0] for line in body.split('\n') if ';' in line]
         assert fields == [f[0] for f in cls._fields_], cname
+    assert f'#define PB200_MAX_PEERS {capi.MAX_PEERS}' in text
 
 
 @pytest.mark.parametrize('d', [20, 30])

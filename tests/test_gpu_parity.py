@@ -578,3 +578,43 @@ def test_buffers_are_never_written_out_of_bounds(lanes):
     rows = big[stride:3 * stride].view(2, stride)
     assert torch.all(rows[:, :b] != mark)                        # both allocated rows were filled
     assert np.all(chains.iteration.cpu().numpy() == 5) and np.all(chains.steps_done.cpu().numpy() == 5 * 37)
+
+
+@pytest.mark.parametrize('lanes', [8, 32])
+def test_fused_exchange_fills_every_ranks_buffer(lanes):
+    """pb200_anneal_run_shared with two emulated ranks on one GPU (both "peer" buffers are local tensors): every
+    rank's kernel stores its per-iteration scalars into slot `rank` of BOTH buffers and bumps BOTH arrival counters;
+    afterwards each buffer holds the all-gathered rows, equal to the ranks' own records, and every counter equals
+    the number of chain warps of the whole job -- also when chains stop early (chi2_tolerance)."""
+    hp, starts, init_ll, values, k = toy_profile_problem(20, points=[2, 6, 7])
+    prob = DeviceProblem(hp, DEV)
+    n_iter, world = 5, 2
+    shards = [(np.array([0, 1, 2, 0, 1], dtype=np.int32), 5), (np.array([2, 0, 1, 2], dtype=np.int32), 4)]   # ragged
+    n_alloc = 5
+    rank_stride = 4 * n_alloc + (n_alloc + 1) // 2
+    bufs = [torch.full((n_iter, world, rank_stride), 123.0, dtype=torch.float64, device=DEV) for _ in range(world)]
+    progs = [torch.zeros(64, dtype=torch.int32, device=DEV) for _ in range(world)]
+    sched = engine.make_schedule(101, 0.7, capi.STEP_ADAPTIVE_FIXED, 1.0, (0.19, 0.21), 0.3, 2.5)
+    recs, targets = [], []
+    for rank, (pts, b) in enumerate(shards):
+        chains = engine.ChainBatch(prob, starts[pts], pts, chain_id=np.arange(b) + 10 * rank, temperature=0.01,
+                                   step_size=0.1, current_best=init_ll[pts])
+        rec = engine.Records(prob, b, n_iter, n_alloc=n_alloc)
+        peers = engine.make_peers(rank, n_alloc, n_iter, rank_stride, [t.data_ptr() for t in bufs],
+                                  [t.data_ptr() for t in progs])
+        targets.append(engine.anneal_run_shared(prob, chains, sched, rec, n_iter, SEED, peers, lanes=lanes))
+        recs.append(rec)
+    torch.cuda.synchronize()
+    assert targets == [-(-5 // (32 // lanes)), -(-4 // (32 // lanes))]
+    for q in range(world):
+        assert np.all(progs[q][:n_iter].cpu().numpy() == sum(targets)) and np.all(progs[q][n_iter:].cpu().numpy() == 0)
+        g = bufs[q].cpu().numpy()
+        for rank, (pts, b) in enumerate(shards):
+            dec = engine.Records.decode(g[:, rank], b, n_alloc, hp.npad, False)
+            acc = recs[rank].accepted.cpu().numpy()
+            ran = acc >= 0
+            assert np.array_equal(dec['accepted'][ran], acc[ran])
+            for key in ('best_loglkl', 'last_loglkl', 'temperature', 'step_size'):
+                assert np.array_equal(dec[key][ran], getattr(recs[rank], key).cpu().numpy()[ran]), key
+            assert np.all(dec['best_loglkl'][~ran] == 123.0)        # rows of stopped chains are left to the prefill
+    assert any((r.accepted.cpu().numpy() < 0).any() for r in recs)   # the tolerance did stop some chains early
