@@ -173,9 +173,10 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
  * Exchange buffers of the ranks of a sharded job, all mapped into this process (CUDA peer memory over NVLink /
  * NVSwitch, e.g. torch symmetric memory).  With them the annealing kernel does the iteration-boundary all-gather
  * ITSELF: next to its own record row it stores the per-chain scalars of iteration k into slot `rank` of row k of
- * EVERY rank's buffer, then (after a system-scope fence) adds 1 to counter `it` of every rank.  On a rank, counter
- * `it` therefore reaches the total number of chain warps of the whole job exactly when the gathered row of launch
- * iteration `it` is complete there.  No collective call, no extra kernel, no packing.
+ * EVERY rank's buffer as soon as the iteration ends (posted stores that drain over NVLink while the next
+ * iterations compute).  When a warp has finished all its iterations it issues ONE system-scope fence and adds 1 to
+ * every counter of every rank: on a rank, the counters reach the total number of chain warps of the whole job
+ * exactly when all gathered rows are complete there.  No collective call, no extra kernel, no packing.
  *   buffer[r]   [rows][n_peers][rank_stride] doubles; block of (row k, rank q) at k * row_stride + q * rank_stride:
  *               [best_loglkl | last_loglkl | temperature | step_size] (n_alloc doubles each), accepted (n_alloc int32)
  *   progress[r] [>= n_iter] uint32, zeroed (on every rank, before any rank launches) by the caller

@@ -54,22 +54,36 @@ class ExchangeUnavailable(RuntimeError):
 _EXCHANGE = {}
 
 
-def _exchange_buffers(rows, world, scalar_len, device):
-    """Exchange buffer [rows, world, scalar_len] FP64 + arrival counters, allocated in torch symmetric memory and
-    mapped on every rank of the default group; cached per shape (they are scratch: results are copied out)."""
+def _exchange_buffers(rows, world, scalar_len, n_alloc, device):
+    """Two alternating sets of {exchange buffer [rows, world, scalar_len] FP64, arrival counters}, allocated in torch
+    symmetric memory and mapped on every rank of the default group; cached per shape (they are scratch: results are
+    copied out).  Invariant between uses: buffers hold the "did not run" pattern (loglkl = inf, accepted = -1),
+    counters are zero.  Sets alternate per call, which is what makes a start-of-call barrier unnecessary: a rank
+    can only begin call c + 2 (same set as call c) after every peer's kernel of call c + 1 has finished, i.e. after
+    every peer restored the set behind call c."""
     import torch
     import torch.distributed as dist
     key = (int(rows), int(world), int(scalar_len), str(device))
     if key not in _EXCHANGE:
         try:
             import torch.distributed._symmetric_memory as symm_mem
-            buf = symm_mem.empty((rows, world, scalar_len), dtype=torch.float64, device=device)
-            prog = symm_mem.empty(max(64, rows), dtype=torch.int32, device=device)
-            hb = symm_mem.rendezvous(buf, dist.group.WORLD)
-            hp = symm_mem.rendezvous(prog, dist.group.WORLD)
+            sets = []
+            for _ in range(2):
+                buf = symm_mem.empty((rows, world, scalar_len), dtype=torch.float64, device=device)
+                prog = symm_mem.empty(max(64, rows), dtype=torch.int32, device=device)
+                sets.append({'buf': buf, 'prog': prog, 'hb': symm_mem.rendezvous(buf, dist.group.WORLD),
+                             'hp': symm_mem.rendezvous(prog, dist.group.WORLD)})
         except Exception as exc:            # noqa: BLE001 -- any failure here means "use the NCCL path"
             raise ExchangeUnavailable(f'{type(exc).__name__}: {exc}') from exc
-        _EXCHANGE[key] = {'buf': buf, 'prog': prog, 'hb': hb, 'hp': hp}
+        blank = torch.zeros((rows, world, scalar_len), dtype=torch.float64, device=device)
+        blank[:, :, :2 * n_alloc] = math.inf
+        blank[:, :, 4 * n_alloc:].view(torch.int32).fill_(-1)
+        for st in sets:
+            st['buf'].copy_(blank)
+            st['prog'].zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()                       # every rank's buffers are blank before anyone stores remotely
+        _EXCHANGE[key] = {'sets': sets, 'blank': blank, 'calls': 0}
     return _EXCHANGE[key]
 
 
@@ -308,22 +322,17 @@ class SimulatedAnnealing:
         """One fused launch whose kernel performs the iteration-boundary all-gather itself: every warp stores its
         chains' per-iteration scalars straight into ALL ranks' exchange buffers (peer memory over NVLink / NVSwitch,
         mapped through torch symmetric memory) and bumps an arrival counter on every rank (pb200_anneal_run_shared).
-        No collective call and no extra kernel sit on the path; the side stream only waits (device-side) for each
-        iteration's counter to reach the number of chain warps of the whole job and then copies the finished rows
-        into this optimiser's `gathered` tensor."""
+        No collective call and no extra kernel sit on the path; the side stream only waits (device-side) for the
+        arrival counter to reach the number of chain warps of the whole job and then copies the finished rows into
+        this optimiser's `gathered` tensor."""
         import torch
         from . import engine
-        ex = _exchange_buffers(self.max_rows, self.world, self.records.scalar_len, self.problem.device)
+        pool = _exchange_buffers(self.max_rows, self.world, self.records.scalar_len, self.b_alloc,
+                                 self.problem.device)
+        ex = pool['sets'][pool['calls'] % 2]
+        pool['calls'] += 1
         compute = torch.cuda.current_stream()
         k0, b, n = self.iterations_done, self.b_alloc, n_iterations
-        rows = ex['buf'][k0:k0 + n]
-        rows[:, :, :2 * b] = math.inf                       # best / last loglkl of chains that do not run
-        rows[:, :, 2 * b:4 * b] = 0.0
-        rows[:, :, 4 * b:].view(torch.int32).fill_(-1)      # accepted = -1: did not run
-        ex['prog'][:n].zero_()
-        ex['hb'].barrier()                                  # every rank is prefilled before anyone stores remotely
-        ready = torch.cuda.Event()
-        ready.record(compute)                               # the side stream must not look at stale counters
         peers = engine.make_peers(self.rank, b, self.max_rows, self.records.scalar_len, ex['hb'].buffer_ptrs,
                                   ex['hp'].buffer_ptrs)
         engine.anneal_run_shared(self.problem, self.batch, self.schedule, self.records, n, self.seed, peers, None,
@@ -335,11 +344,13 @@ class SimulatedAnnealing:
             n_r = len(shard_grid(self.n_points, self.reps, r, self.world)[0])
             lanes_r = self.lanes or engine.choose_lanes(self.problem.npad, n_r)
             total += -(-n_r // (32 // lanes_r)) if n_r else 0
+        rows = ex['buf'][k0:k0 + n]
         with torch.cuda.stream(side_stream):
-            side_stream.wait_event(ready)
-            for i in range(n):
-                engine.stream_wait_geq(side_stream, ex['prog'], i, total)
+            # every warp bumps its counters in ascending order after its completion fence: the last one suffices
+            engine.stream_wait_geq(side_stream, ex['prog'], n - 1, total)
             self.gathered[k0:k0 + n].copy_(rows, non_blocking=True)
+            rows.copy_(pool['blank'][k0:k0 + n], non_blocking=True)      # leave the set blank for its next use
+            ex['prog'][:n].zero_()
         compute.wait_stream(side_stream)
 
     def global_records(self):
