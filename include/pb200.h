@@ -175,11 +175,12 @@ int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, cons
  * ITSELF: next to its own record row it stores the per-chain scalars of iteration k into slot `rank` of row k of
  * EVERY rank's buffer as soon as the iteration ends (posted stores that drain over NVLink while the next
  * iterations compute).  When a warp has finished all its iterations it issues ONE system-scope fence and adds 1 to
- * every counter of every rank: on a rank, the counters reach the total number of chain warps of the whole job
- * exactly when all gathered rows are complete there.  No collective call, no extra kernel, no packing.
+ * counter n_iter - 1 of every rank: on a rank, that counter reaches the total number of chain warps of the whole job
+ * exactly when all gathered rows of the launch are complete there.  No collective call, no extra kernel, no packing.
  *   buffer[r]   [rows][n_peers][rank_stride] doubles; block of (row k, rank q) at k * row_stride + q * rank_stride:
  *               [best_loglkl | last_loglkl | temperature | step_size] (n_alloc doubles each), accepted (n_alloc int32)
- *   progress[r] [>= n_iter] uint32, zeroed (on every rank, before any rank launches) by the caller
+ *   progress[r] [>= n_iter] uint32, zeroed (on every rank, before any rank launches) by the caller; only entry
+ *               n_iter - 1 is used
  */
 #define PB200_MAX_PEERS 16
 typedef struct pb200_peers {

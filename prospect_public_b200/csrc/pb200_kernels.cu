@@ -536,12 +536,12 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
     if (peers.n_peers > 0) {
         // The peer stores above are posted as each iteration ends and drain over NVLink while the next iterations
         // compute; their COMPLETION is established once, here: one system-scope fence per warp (a fence per
-        // iteration costs ~9 us each, 10 % of the kernel), then every arrival counter of every rank is bumped.
+        // iteration costs ~9 us each, 10 % of the kernel), then the launch's arrival counter (index n_iter - 1) of
+        // every rank is bumped -- one remote atomic per warp and rank.
         __threadfence_system();
         __syncwarp();
         if (lane == 0)
-            for (int q = 0; q < peers.n_peers; ++q)
-                for (int k = 0; k < n_iter; ++k) atomicAdd_system(peers.progress[q] + k, 1u);
+            for (int q = 0; q < peers.n_peers; ++q) atomicAdd_system(peers.progress[q] + (n_iter - 1), 1u);
     }
     if (was_live) {
 #pragma unroll

@@ -607,7 +607,8 @@ def test_fused_exchange_fills_every_ranks_buffer(lanes):
     torch.cuda.synchronize()
     assert targets == [-(-5 // (32 // lanes)), -(-4 // (32 // lanes))]
     for q in range(world):
-        assert np.all(progs[q][:n_iter].cpu().numpy() == sum(targets)) and np.all(progs[q][n_iter:].cpu().numpy() == 0)
+        pq = progs[q].cpu().numpy()
+        assert pq[n_iter - 1] == sum(targets) and pq.sum() == sum(targets)      # one arrival counter per launch
         g = bufs[q].cpu().numpy()
         for rank, (pts, b) in enumerate(shards):
             dec = engine.Records.decode(g[:, rank], b, n_alloc, hp.npad, False)
