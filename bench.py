@@ -377,7 +377,11 @@ def main():
                                        f'({b_local} per GPU) x {n_iter} iterations x {steps} steps',
                            'chain_steps_per_step': chain_steps_per_step, 'l2': 'flushed (192 MiB write) between steps',
                            'precision': 'FP32 proposal / acceptance arithmetic, FP64 chain state and reported chi^2',
-                           'wall_ms_per_step_incl_reset_and_flush': 1e3 * t_wall / args.steps},
+                           'wall_ms_per_step_incl_reset_and_flush': 1e3 * t_wall / args.steps,
+                           **({'exchange': 'per-iteration all-gather of the per-chain scalars ' + (
+                               'fused into the annealing kernel (NVLink peer-memory stores, no collective call)'
+                               if getattr(sa, 'fused_exchange', False) else 'over NCCL on a side stream')}
+                              if world > 1 else {})},
                 'clocks': sampler.summary(),
                 'e2e': {'value': e2e_value, 'unit': UNIT, 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                         'steps': e2e_steps, 'warmup': e2e_warm},

@@ -4,6 +4,9 @@
 //   anneal_kernel<LPC,CPL>    fused annealing iterations: Philox normals -> whitened quadratic form ->
 //                             accept/reject at the chain temperature -> (on accept) proposal matvec, box
 //                             test, state update, running bestfit -> set_bestfit + next settings.
+//   anneal_ws_kernel<LPC,CPL> the same with a producer warp per chain warp (variates through a shared-memory ring)
+//                             for batches too small to fill the schedulers.  Both can signal finished iterations
+//                             and perform the iteration-boundary all-gather themselves (peer-memory stores).
 //   mh_kernel<LPC,CPL,REC>    plain Metropolis-Hastings rounds with chain recording (jobtype mcmc).
 //   loglkl_kernel<CPL>        FP64 chi^2 quadratic form + prior box for a batch of positions.
 //   schedule_kernel           stand-alone adaptive step-size bookkeeping.

@@ -238,12 +238,12 @@ class SimulatedAnnealing:
     # --- whole schedules ---------------------------------------------------------------------------
     def run_schedule(self, n_iterations, iterations_per_launch=None, gather=True):
         """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: still ONE
-        fused launch; the kernel counts finished iterations in device memory and a side stream all-gathers every
-        iteration's per-chain scalars (bestfit chi^2, last chi^2, temperature, step size, accepted count) as soon as
-        its counter is complete -- the iteration-boundary exchange overlaps the following iterations' compute
-        instead of cutting the launch into pieces (run_signalled).  The bestfit positions of all iterations follow
-        in one all-gather at the end (global_records), which keeps the per-boundary collective latency-sized.
-        `self.signalled = False` (or the streamed generator) falls back to one launch + one gather per iteration."""
+        fused launch, and the iteration-boundary exchange of the per-chain scalars (bestfit chi^2, last chi^2,
+        temperature, step size, accepted count) is done by the kernel itself over peer memory (run_fused_exchange).
+        Fallbacks: the kernel counts finished iterations and a side stream all-gathers each one over NCCL behind a
+        device-side wait (run_signalled; PB200_EXCHANGE=nccl or no symmetric memory); one launch + one gather per
+        iteration (`self.signalled = False` or the streamed generator).  The bestfit positions of all iterations
+        follow in one all-gather at the end (global_records)."""
         import torch
         if self.world == 1 or not gather:
             if self.streamed and iterations_per_launch is None:
