@@ -27,7 +27,9 @@
 extern "C" {
 #endif
 
-#define PB200_ABI_VERSION 2
+/* 3: pb200_anneal_run_signalled / _shared, pb200_stream_wait_geq, pb200_chain_moments, pb200_uses_producer_warps,
+ *    struct pb200_peers (additions only; every version-2 entry point is unchanged) */
+#define PB200_ABI_VERSION 3
 
 /* chain status (pb200_chains.status) */
 #define PB200_ACTIVE     0
