@@ -27,8 +27,8 @@
 extern "C" {
 #endif
 
-/* 3: pb200_anneal_run_signalled / _shared, pb200_stream_wait_geq, pb200_chain_moments, pb200_uses_producer_warps,
- *    struct pb200_peers (additions only; every version-2 entry point is unchanged) */
+/* 3: additions only (signalled / shared annealing launches, stream wait, per-chain moments, producer-warp query,
+ *    the peers struct); every version-2 entry point is unchanged */
 #define PB200_ABI_VERSION 3
 
 /* chain status (pb200_chains.status) */
