@@ -42,7 +42,9 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'smsp__cycles_active.avg', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'smsp__warps_eligible.avg.per_cycle_active', 'smsp__average_warp_latency_issue_stalled_short_scoreboard',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct']
-out['metrics'] = {n: f'{vals[i]} {units[i]}' for i, n in enumerate(names) if n in want}
+out['metrics'] = {n: f'{vals[i]} {units[i]}' for i, n in enumerate(names)
+                  if n in want or ('issue_stalled' in n and n.endswith('_per_issue_active.ratio'))
+                  or n in ('smsp__warps_active.avg.per_cycle_active', 'smsp__warps_eligible.avg.per_cycle_active')}
 for key in ('dram__bytes_read.sum', 'dram__bytes_write.sum'):
     pass
 
