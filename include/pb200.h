@@ -45,6 +45,11 @@ extern "C" {
 #define PB200_RECORD_NONE      0
 #define PB200_RECORD_ACCEPTED  1   /* accepted points + multiplicities == prospect/mcmc.py Chain */
 #define PB200_RECORD_THINNED   2   /* current position every `thin` steps, weight 1 */
+/* OR-ed into pb200_samples.mode: test the prior box exactly at EVERY likelihood-accepted step (one n x n proposal
+ * mat-vec per accepted step) instead of deferring it behind the whitened safe radius.  Same decisions; faster when
+ * steps are a sizeable fraction of that radius (wide-step sampling at T = 1), where the deferred test would have to
+ * re-reference every few accepted steps anyway.  PB200_RECORD_ACCEPTED always works this way. */
+#define PB200_EXACT_BOX        0x100
 
 /*
  * The Gaussian target and the per-point proposal, precomputed on the host in FP64.
@@ -135,7 +140,7 @@ typedef struct pb200_records {
 
 /* Sample recording for jobtype mcmc (prospect/mcmc.py:69-73, tasks/mcmc_task.py:17-23). */
 typedef struct pb200_samples {
-    int32_t  mode;          /* PB200_RECORD_* */
+    int32_t  mode;          /* PB200_RECORD_* [| PB200_EXACT_BOX] */
     int32_t  thin;          /* PB200_RECORD_THINNED: keep every thin-th step */
     int32_t  capacity;      /* rows per chain */
     double*  x;             /* device [B][capacity][npad] */

@@ -198,6 +198,7 @@ static void rec_push(dm_recorder *r, const double *x, double ll, int mult) {
 typedef struct {
     const dm_problem *p;
     int pt, lpc;
+    int exact;              /* PB200_EXACT_BOX: every likelihood-accepted step is materialised and box-tested */
     float Tf, sf;
     float gf[MAXN], hl[MAXN];
 } dm_run;
@@ -209,7 +210,7 @@ static void seq_step(dm_run *R, dm_state *s, const float *zt, float ek, uint32_t
     const float sf = R->sf, Tf = R->Tf;
     float z[MAXN], wt[MAXN], lanes[32];
     double xt[MAXN];
-    const int always_exact = rec && rec->mode == 1;
+    const int always_exact = R->exact || (rec && rec->mode == 1);
     for (int c = 0; c < np; ++c) z[c] = c < n ? zt[c] : 0.0f;
     for (int gl = 0; gl < lpc; ++gl) {
         float tt = 0.0f;
@@ -349,11 +350,11 @@ static int block_steps(dm_run *R, dm_state *s, const float *zb[4], const float e
 
 static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain_id, uint32_t t_begin,
                       uint32_t n_steps, float Tf, float sf, int lpc, dm_state *s, const float *z_replay,
-                      const float *e_replay, uint32_t replay_step0, dm_recorder *rec) {
+                      const float *e_replay, uint32_t replay_step0, dm_recorder *rec, int exact) {
     const int np = p->npad, n = p->n;
     const float *lam = p->lam + (size_t)pt * np;
     dm_run R;
-    R.p = p; R.pt = pt; R.lpc = lpc; R.Tf = Tf; R.sf = sf;
+    R.p = p; R.pt = pt; R.lpc = lpc; R.Tf = Tf; R.sf = sf; R.exact = exact;
     const float half_s = 0.5f * sf;
     for (int c = 0; c < np; ++c) { R.gf[c] = (float)s->gt[c]; R.hl[c] = half_s * lam[c]; }
     float *zbuf = NULL, *ebuf = NULL;
@@ -368,7 +369,7 @@ static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain
     uint32_t i = 0;
     while (i < n_steps) {
         const uint32_t t = t_begin + i;
-        if (lpc == 8 && !recording && (t & 3u) == 0u && n_steps - i >= 4u) {   /* a whole Philox block (8-lane geometry) */
+        if (lpc == 8 && !recording && !exact && (t & 3u) == 0u && n_steps - i >= 4u) {   /* a whole Philox block (8-lane geometry) */
             const float *zb[4] = {zs + (size_t)i * n, zs + (size_t)(i + 1) * n, zs + (size_t)(i + 2) * n,
                                   zs + (size_t)(i + 3) * n};
             if (block_steps(&R, s, zb, es + i))
@@ -441,7 +442,7 @@ void dm_anneal_chain(const dm_problem *p, const dm_schedule *s, dm_chain *c, int
         memcpy(st.bref, st.xref, sizeof(double) * np);
         memset(st.bw, 0, sizeof(float) * np);
         run_steps(p, c->point, seed, c->chain_id, c->steps_done, (uint32_t)s->steps_per_iteration,
-                  (float)c->temperature, (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, NULL);
+                  (float)c->temperature, (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, NULL, 0);
         c->steps_done += s->steps_per_iteration;
         materialise(p, c->point, st.bref, st.bw, bx);
         materialise(p, c->point, st.xref, st.w, c->x);
@@ -462,6 +463,8 @@ int32_t dm_mh_chain(const dm_problem *p, dm_chain *c, int32_t n_steps, uint64_t 
                     const float *e_replay, int mode, int thin, int capacity, double *sx, double *sll, int32_t *smult,
                     int32_t *count) {
     const int np = p->npad;
+    const int exact = (mode & 0x100) != 0 || (mode & 0xff) == 1;      /* PB200_EXACT_BOX / RECORD_ACCEPTED */
+    mode &= 0xff;
     dm_state st;
     const uint32_t replay0 = c->steps_done;
     anchor(p, c->point, c->x, &st, lpc);
@@ -478,7 +481,7 @@ int32_t dm_mh_chain(const dm_problem *p, dm_chain *c, int32_t n_steps, uint64_t 
     while (done < (uint32_t)n_steps) {
         const uint32_t chunk = (uint32_t)n_steps - done < 256u ? (uint32_t)n_steps - done : 256u;
         run_steps(p, c->point, seed, c->chain_id, c->steps_done + done, chunk, (float)c->temperature,
-                  (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, mode ? &r : NULL);
+                  (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, mode ? &r : NULL, exact);
         done += chunk;
         materialise(p, c->point, st.xref, st.w, c->x);
         anchor(p, c->point, c->x, &st, lpc);

@@ -13,6 +13,7 @@ LIB_PATH = os.environ.get('PB200_LIB') or os.path.join(_PKG, '_lib', 'libpb200.s
 ACTIVE, CONVERGED, FAILED = 0, 1, 2
 STEP_EXPONENTIAL, STEP_ADAPTIVE_FIXED, STEP_ADAPTIVE_SECANT = 0, 1, 2
 RECORD_NONE, RECORD_ACCEPTED, RECORD_THINNED = 0, 1, 2
+EXACT_BOX = 0x100
 ABI_VERSION = 3
 
 _vp = C.c_void_p

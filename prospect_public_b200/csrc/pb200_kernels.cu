@@ -109,7 +109,7 @@ struct ChainState {
 // materialised (n x n matvec), tested exactly and becomes the new reference point.
 // Predicates are per group; everything containing a shuffle or __syncwarp runs under warp-uniform control.
 // ----------------------------------------------------------------------------------------------
-template <int LPC, int CPL, int REC>
+template <int LPC, int CPL, int REC, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
 __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
                                          ChainState<CPL>& c, float* ws, RecCursor& rc) {
@@ -127,8 +127,8 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
             wt[r] = __fmaf_rn(sf, zk[r], c.w[r]);
             rr = __fmaf_rn(wt[r], wt[r], rr);
         }
-        rr = group_sum<LPC>(rr);
-        const bool exact = lik && (REC == PB200_RECORD_ACCEPTED || !(rr <= c.m2));
+        if (!EXACT) rr = group_sum<LPC>(rr);      // EXACT: every accepted step is materialised, no radius test
+        const bool exact = lik && (EXACT || !(rr <= c.m2));
         acc = lik;
         if (__any_sync(kFull, exact)) {
             double xt[CPL];
@@ -151,8 +151,10 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
                 }
                 c.best_rel = false;
             }
-            const float m2n = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
-            if (reref) c.m2 = m2n;
+            if (!EXACT) {                          // the safe radius around the new reference point
+                const float m2n = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
+                if (reref) c.m2 = m2n;
+            }
         }
         if (acc) {
 #pragma unroll
@@ -325,7 +327,7 @@ constexpr int kSrcPhilox = 0;   // drawn in place by the warp that uses them
 constexpr int kSrcStream = 1;   // pre-generated by variates_kernel into global memory (one iteration per launch)
 constexpr int kSrcRing = 2;     // produced by the partner warp into a shared-memory ring (anneal_ws_kernel)
 
-template <int LPC, int CPL, int REC, int SRC>
+template <int LPC, int CPL, int REC, int SRC, bool EXACT>
 __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
                                                 int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
                                                 uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
@@ -352,7 +354,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
         }
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
         bool todo = live, cnt_done = false;
-        if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && off == 0u && cnt == 4u) {
+        if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && !EXACT && off == 0u && cnt == 4u) {
             todo = block_step<LPC, CPL>(gl, live, Tf, sf, z, e, c);
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }
@@ -363,7 +365,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             if (!cnt_done && k >= off && k < off + cnt) {
 #pragma unroll
                 for (int r = 0; r < CPL; ++r) zk[r] = z[r][k];
-                one_step<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, todo, t + (k - off), Tf, sf, zk, e[k], c, ws, rc);
+                one_step<LPC, CPL, REC, EXACT>(p, pt, lt_pt, gl, gi, todo, t + (k - off), Tf, sf, zk, e[k], c, ws, rc);
             }
         }
         i += cnt;
@@ -379,7 +381,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
     }
 }
 
-template <int LPC, int CPL, int REC, int SRC = kSrcPhilox>
+template <int LPC, int CPL, int REC, int SRC = kSrcPhilox, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
@@ -396,14 +398,14 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
     const uint32_t lead = __shfl_sync(kFull, t_begin, lm ? __ffs(lm) - 1 : 0) & 3u;
     if (SRC == kSrcRing || __all_sync(kFull, !live || (t_begin & 3u) == lead)) {
         // (ring: the kernel only pairs a producer with warps whose live chains share one alignment class)
-        run_steps_class<LPC, CPL, REC, SRC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
+        run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
                                             sf, c, ws, rc, zrow, ring);
     } else {
 #pragma unroll 1
         for (uint32_t a = 0; a < 4u; ++a) {
             const bool mine = live && (t_begin & 3u) == a;
             if (__any_sync(kFull, mine))
-                run_steps_class<LPC, CPL, REC, SRC>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
+                run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
                                                     n_steps, Tf, sf, c, ws, rc, zrow, ring);
         }
     }
@@ -673,7 +675,7 @@ anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_recor
 // ----------------------------------------------------------------------------------------------
 constexpr uint32_t kResync = 256;
 
-template <int LPC, int CPL, int REC>
+template <int LPC, int CPL, int REC, bool EXACT>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
 mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k1, pb200_samples smp,
           int32_t* accepted_out) {
@@ -728,7 +730,7 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
     Ring no_ring{};
     while (done < (uint32_t)n_steps) {
         const uint32_t chunk = min((uint32_t)n_steps - done, kResync);
-        run_steps<LPC, CPL, REC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc,
+        run_steps<LPC, CPL, REC, kSrcPhilox, EXACT>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc,
                                  no_ring);
         done += chunk;
         materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
@@ -1238,7 +1240,9 @@ int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t 
     if (!chains) return fail("mh_run: NULL chains");
     if (chains->n_chains <= 0 || n_steps <= 0) return 0;
     pb200_samples none{};
-    const pb200_samples smp = samples ? *samples : none;
+    pb200_samples smp = samples ? *samples : none;
+    const bool exact_box = (smp.mode & PB200_EXACT_BOX) != 0;
+    smp.mode &= ~PB200_EXACT_BOX;
     if (smp.mode != PB200_RECORD_NONE) {
         if (!smp.x || !smp.loglkl || !smp.mult || !smp.count || smp.capacity <= 0)
             return fail("mh_run: sample buffers missing");
@@ -1250,12 +1254,12 @@ int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t 
     const int per_cta = kWarpsPerCta * (32 / lanes);
     const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#define PB200_MH(REC)                                                                                                  \
-    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (mh_kernel<LPC, CPL, REC><<<blocks, 32 * kWarpsPerCta, 0, st>>>(      \
+#define PB200_MH(REC, EXACT)                                                                                           \
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (mh_kernel<LPC, CPL, REC, EXACT><<<blocks, 32 * kWarpsPerCta, 0, st>>>( \
                                                     *prob, *chains, n_steps, k0, k1, smp, accepted_out)))
-    if (smp.mode == PB200_RECORD_NONE) { PB200_MH(PB200_RECORD_NONE); }
-    else if (smp.mode == PB200_RECORD_ACCEPTED) { PB200_MH(PB200_RECORD_ACCEPTED); }
-    else if (smp.mode == PB200_RECORD_THINNED) { PB200_MH(PB200_RECORD_THINNED); }
+    if (smp.mode == PB200_RECORD_NONE) { if (exact_box) { PB200_MH(PB200_RECORD_NONE, true); } else { PB200_MH(PB200_RECORD_NONE, false); } }
+    else if (smp.mode == PB200_RECORD_ACCEPTED) { PB200_MH(PB200_RECORD_ACCEPTED, true); }
+    else if (smp.mode == PB200_RECORD_THINNED) { if (exact_box) { PB200_MH(PB200_RECORD_THINNED, true); } else { PB200_MH(PB200_RECORD_THINNED, false); } }
     else return fail("mh_run: unknown record mode");
 #undef PB200_MH
     return check_cuda(cudaGetLastError(), "mh_kernel launch");

@@ -252,11 +252,18 @@ def anneal_run_streamed(problem, chains: ChainBatch, schedule, records: Records,
                                                     _stream_ptr(stream)))
 
 
-def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None, lanes=0):
+def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None, lanes=0,
+           exact_box=False):
+    """`exact_box`: test the prior box at every likelihood-accepted step (PB200_EXACT_BOX) instead of deferring it
+    behind the whitened safe radius -- same decisions, faster for wide steps."""
     accepted = torch.zeros(chains.n_chains, dtype=torch.int32, device=problem.device)
+    smp = samples.c if samples is not None else None
+    if exact_box:
+        smp = capi.Samples(capi.EXACT_BOX, 1, 0, None, None, None, None) if smp is None else capi.Samples(
+            smp.mode | capi.EXACT_BOX, smp.thin, smp.capacity, smp.x, smp.loglkl, smp.mult, smp.count)
     _count()
     capi.check(capi.lib().pb200_mh_run(C.byref(problem.c), C.byref(chains.c), int(n_steps), C.c_uint64(seed),
-                                       C.byref(samples.c) if samples is not None else None, capi.ptr(accepted),
+                                       C.byref(smp) if smp is not None else None, capi.ptr(accepted),
                                        int(lanes), _stream_ptr(stream)))
     return accepted
 

@@ -129,6 +129,15 @@ class MetropolisHastings:
         self.batch = engine.ChainBatch(self.problem, x0, 0, chain_id=ids, temperature=config_mcmc.temperature,
                                        step_size=config_mcmc.step_size,
                                        steps_done=mcmc_args.get('steps_done', 0))
+        # Wide steps (a sizeable fraction of the whitened safe radius, e.g. 2.4 / sqrt(d) at T = 1): test the box at
+        # every accepted step instead of deferring it.  'auto' compares the block bound 8 s^2 (4 n) with the safe
+        # radius^2 at the start point, min_i (distance to the box / proposal sigma_i)^2.
+        exact = mcmc_args.get('exact_box', 'auto')
+        if exact == 'auto':
+            hp = self.problem.host
+            margin = np.minimum(x0[:, :n] - hp.lo[None, :n], hp.hi[None, :n] - x0[:, :n]) / hp.lt_norm[0][None, :n]
+            exact = bool(8.0 * float(config_mcmc.step_size) ** 2 * 4 * n > (0.999 * max(margin.min(), 0.0)) ** 2)
+        self.exact_box = bool(exact)
         self.record = mcmc_args.get('record', 'accepted')
         self.thin = int(mcmc_args.get('thin', 1))
         self._prior = prior
@@ -165,7 +174,7 @@ class MetropolisHastings:
     def run_steps(self, steps_per_iteration):
         from . import engine
         smp = self._ensure_samples(steps_per_iteration)
-        acc = engine.mh_run(self.problem, self.batch, steps_per_iteration, self.seed, smp)
+        acc = engine.mh_run(self.problem, self.batch, steps_per_iteration, self.seed, smp, exact_box=self.exact_box)
         self.accepted += acc.cpu().numpy()
         self.steps += steps_per_iteration
 

@@ -619,3 +619,40 @@ def test_fused_exchange_fills_every_ranks_buffer(lanes):
                 assert np.array_equal(dec[key][ran], getattr(recs[rank], key).cpu().numpy()[ran]), key
             assert np.all(dec['best_loglkl'][~ran] == 123.0)        # rows of stopped chains are left to the prefill
     assert any((r.accepted.cpu().numpy() < 0).any() for r in recs)   # the tolerance did stop some chains early
+
+
+@pytest.mark.parametrize('lanes', [32, 8])
+@pytest.mark.parametrize('mode', [capi.RECORD_NONE, capi.RECORD_THINNED])
+def test_exact_box_mode_bit_exact_and_same_decisions(mode, lanes):
+    """PB200_EXACT_BOX (box test at every accepted step instead of the deferred safe-radius test): bit-exact against
+    the model in the same mode, also for chains bouncing off the box edge; away from the box the accept / reject
+    sequence is the one of the deferred test and the positions agree to FP32 accumulation error."""
+    hp, k = toy_free_problem(20)
+    prob = DeviceProblem(hp, DEV)
+    b, n_steps, cap, thin = 6, 900, 200, 7
+    model = dm.Model(hp, lanes)
+    for start, step in ((0.0, 1.0), (2.45, 0.3)):
+        res = {}
+        for exact in (True, False):
+            chains = engine.ChainBatch(prob, np.full((b, 20), start), 0, temperature=1.0, step_size=step)
+            smp = engine.Samples(prob, b, cap, mode, thin) if mode else None
+            acc = engine.mh_run(prob, chains, n_steps, SEED, smp, lanes=lanes, exact_box=exact).cpu().numpy()
+            res[exact] = (acc, chains.x.cpu().numpy(), chains.loglkl.cpu().numpy())
+            if not exact:
+                continue
+            gx = smp.x.cpu().numpy() if mode else None
+            for c in range(b):
+                z, e = _gpu_variates(c, 0, n_steps, 20)
+                ch = model.new_chain(np.full(20, start), 0, chain_id=c, temperature=1.0, step_size=step)
+                m, smod = model.mh_chain(ch, n_steps, SEED, z, e, mode | capi.EXACT_BOX, thin, cap)
+                assert acc[c] == m
+                assert np.array_equal(res[True][1][c], np.ctypeslib.as_array(ch.x, (hp.npad,)))
+                assert res[True][2][c] == ch.loglkl
+                if mode:
+                    r = smod['count'][0]
+                    assert smp.count.cpu().numpy()[c] == r and np.array_equal(gx[c, :r], smod['x'][:r])
+        if start == 0.0:                                    # far from the box: identical decisions
+            assert np.array_equal(res[True][0], res[False][0])
+            assert np.max(np.abs(res[True][1] - res[False][1])) < 1e-5
+        else:
+            assert np.all(np.abs(res[True][1][:, :20]) <= 2.5)
