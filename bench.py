@@ -346,15 +346,20 @@ def main():
         from prospect_public_b200.run import run as run_job
         pkw = dict(workload_profile_kw('profile30', world)[1])
         ycfg = annealing_yaml(toy_inputs(tmp)[0], os.path.join(tmp, 'ttp'), jobtype='profile', write=True, **pkw)
-        barrier()
-        t0 = time.perf_counter()
-        res = run_job(ycfg)
-        barrier()
-        ttp = {'seconds': res.get('time_to_profile_s', time.perf_counter() - t0),
+        first = None
+        for attempt in range(2):       # the first run of a new job shape pays one-off set-up (kernel loading, pinned
+            barrier()                  # staging and, for N > 1, the peer-memory rendezvous of the exchange buffers)
+            t0 = time.perf_counter()
+            res = run_job(ycfg)
+            barrier()
+            took = res.get('time_to_profile_s', time.perf_counter() - t0)
+            first = took if first is None else first
+        ttp = {'seconds': took, 'seconds_first_run': first,
                'seconds_incl_snapshot': time.perf_counter() - t0, 'loop_seconds': res['loop_seconds'],
                'chain_steps': int(res['chain_steps']),
                'job': f'30-D toy profile, {32 * world} values x 256 repetitions x 20 iterations x 250 steps, '
-                      'seconds = yaml read to profile/x2.txt written; the PROSPECT-compatible config.pkl/state.pkl follow'}
+                      'seconds = yaml read to profile/x2.txt written (second run of the job; seconds_first_run includes '
+                      'one-off set-up); the PROSPECT-compatible config.pkl/state.pkl follow'}
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and rows is not None:
