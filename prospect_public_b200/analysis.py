@@ -120,20 +120,24 @@ def write_profile_results(rec: RunRecord, srt, profile, out_dir, parameter):
 def write_profile_status(rec: RunRecord, srt, out_dir, parameter):
     path = os.path.join(out_dir, f'{parameter}_status.txt')
     ran = rec.accepted >= 0
+    k_rows = ran.shape[0]
+    any_ran = ran.any(axis=0)                                             # per chain
+    last = k_rows - 1 - np.argmax(ran[::-1], axis=0)                      # last iteration that ran
+    cur_ll = rec.best_loglkl[last, np.arange(ran.shape[1])]
+    chain_iter, chain_best, conv = srt['chain_iter'], srt['chain_best'], np.asarray(rec.converged, dtype=bool)
+    out = [f'{parameter:14.10} ',
+           '\t\t | rep. no.  current iter \t current loglkl \t best iter \t best loglkl \t converged? ']
+    for p in np.argsort(rec.values, kind='stable'):
+        out.append(f'\n{rec.values[p]:14.10} ')
+        for rep in range(rec.reps):
+            c = rep * rec.n_points + p
+            if not any_ran[c]:
+                continue
+            line = (f"| rep {rep + 1} \t {int(last[c]):<13} \t {cur_ll[c]:.10e} \t "
+                    f"{chain_iter[rep, p]:<9} \t {chain_best[rep, p]:.10e} \t {bool(conv[c])} ")
+            out.append(f'\t {line}' if rep == 0 else f'\n\t\t\t\t {line}')
     with open(path, 'w') as f:
-        f.write(f'{parameter:14.10} ')
-        f.write('\t\t | rep. no.  current iter \t current loglkl \t best iter \t best loglkl \t converged? ')
-        for p in np.argsort(rec.values, kind='stable'):
-            f.write(f'\n{rec.values[p]:14.10} ')
-            for rep in range(rec.reps):
-                c = rep * rec.n_points + p
-                if not ran[:, c].any():
-                    continue
-                cur = int(np.nonzero(ran[:, c])[0][-1])
-                line = (f"| rep {rep + 1} \t {cur:<13} \t {rec.best_loglkl[cur, c]:.10e} \t "
-                        f"{srt['chain_iter'][rep, p]:<9} \t {srt['chain_best'][rep, p]:.10e} \t "
-                        f"{bool(rec.converged[c])} ")
-                f.write(f'\t {line}' if rep == 0 else f'\n\t\t\t\t {line}')
+        f.write(''.join(out))
     return path
 
 
