@@ -268,6 +268,39 @@ def test_record_all_gather_world2_gloo(p, r):
     assert set(owners) == {0.0, 1.0}
 
 
+def test_status_file_with_ragged_and_empty_chains(tmp_path):
+    """<param>_status.txt (analyse_profile_task.py:62-89) when chains stopped at different iterations or never ran:
+    the vectorised writer gives the text of the plain per-chain loop."""
+    rng = np.random.default_rng(2)
+    p_count, reps, k_rows, n = 3, 4, 6, 5
+    b = p_count * reps
+    best = rng.uniform(1, 9, (k_rows, b))
+    acc = rng.integers(0, 50, (k_rows, b)).astype(np.int32)
+    stop = rng.integers(0, k_rows + 1, b)                    # chain c ran iterations [0, stop[c])
+    stop[[1, 7]] = 0                                         # two chains never ran
+    for c in range(b):
+        acc[stop[c]:, c] = -1
+    conv = rng.random(b) < 0.3
+    rec = analysis.RunRecord(np.array([0.5, -1.0, 2.0]), reps, [f'x{i}' for i in range(n)], best, acc,
+                             rng.normal(size=(k_rows, b, n)), conv, np.ones(p_count), np.zeros((p_count, n)),
+                             np.tile(np.eye(n), (p_count, 1, 1)))
+    srt = analysis.sort_bestfits(rec)
+    path = analysis.write_profile_status(rec, srt, str(tmp_path), 'x2')
+    ran = acc >= 0
+    expect = [f"{'x2':14.10} ", '\t\t | rep. no.  current iter \t current loglkl \t best iter \t best loglkl \t converged? ']
+    for p in np.argsort(rec.values, kind='stable'):
+        expect.append(f'\n{rec.values[p]:14.10} ')
+        for rep in range(reps):
+            c = rep * p_count + p
+            if not ran[:, c].any():
+                continue
+            cur = int(np.nonzero(ran[:, c])[0][-1])
+            line = (f"| rep {rep + 1} \t {cur:<13} \t {best[cur, c]:.10e} \t {srt['chain_iter'][rep, p]:<9} \t "
+                    f"{srt['chain_best'][rep, p]:.10e} \t {bool(conv[c])} ")
+            expect.append(f'\t {line}' if rep == 0 else f'\n\t\t\t\t {line}')
+    assert open(path).read() == ''.join(expect)
+
+
 def _chain_statistics_numpy(xs, ws):
     """numpy restatement of engine.chain_statistics for a list of chains (rows [r, n], integer weights [r])."""
     n = xs[0].shape[1]
