@@ -27,9 +27,10 @@
 extern "C" {
 #endif
 
-/* 3: additions only (signalled / shared annealing launches, stream wait, per-chain moments, producer-warp query,
- *    the peers struct); every version-2 entry point is unchanged */
-#define PB200_ABI_VERSION 3
+/* 4: struct pb200_problem gained lt_hi / lt_lo (tensor-core operands of the wide path); the stand-alone variate
+ *    generator entry points of version 3 (pb200_variates_*, pb200_anneal_run_streamed: measured slower than the fused
+ *    kernel at every batch size) were removed; pb200_exchange_arrivals and pb200_launch_status are new */
+#define PB200_ABI_VERSION 4
 
 /* chain status (pb200_chains.status) */
 #define PB200_ACTIVE     0
@@ -81,6 +82,10 @@ typedef struct pb200_problem {
                              |x_i - xref_i| <= lt_norm_i * |w| for a whitened displacement w (deferred box test) */
     const double* g_t;    /* device [P][npad*npad]  g_t[j*npad+i] = G[i][j] */
     const double* h;      /* device [P][npad] */
+    const float*  lt_hi;  /* device [P][npad*npad]  lt_hi[i*npad+j] = the TF32 part of Lt[i][j] (low 13 mantissa bits
+                             cleared), K-major: operand of the tcgen05 materialisation GEMM of the wide path
+                             (npad >= 128).  May be NULL (with lt_lo): that GEMM then runs on the FP32 SIMT pipe */
+    const float*  lt_lo;  /* device [P][npad*npad]  lt_lo[i*npad+j] = Lt[i][j] - lt_hi[i*npad+j] (exact) */
 } pb200_problem;
 
 /*
@@ -172,6 +177,15 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
  * OptimiseTask.run + emit_tasks (prospect/tasks/optimise_task.py:16-54),
  * SimulatedAnnealing.__init__/optimise/set_bestfit/get_next_iteration_settings
  * (prospect/optimiser.py:40-162) and MetropolisHastings.step/get_proposal (prospect/mcmc.py:163-190).
+ *
+ * Wide problems (npad >= 128): the dense contractions of an iteration boundary -- the proposal-factor product
+ * x = xref + Lt w (prospect/mcmc.py:187) and the chi^2 quadratic forms / gradients (analytical_kernel.py:65) -- are
+ * batched over the repetitions of a profile point: per iteration one launch of the Metropolis steps, one tcgen05
+ * (3xTF32, TMA-fed) GEMM for the positions and one FP64 shared-memory-tiled GEMM for the anchors, all enqueued by
+ * this one call.  That path addresses the repetitions of a point as chain = rep * n_points + point, i.e. it needs
+ * chains.point[c] == c % n_points (a batch laid out differently ends with every chain in status PB200_FAILED and no
+ * records).  PB200_WIDE=0 in the environment keeps the single fused kernel; PB200_WIDE_MMA=0 keeps the position GEMM
+ * on the FP32 SIMT pipe (bit-identical to the fused kernel).
  */
 int pb200_anneal_run(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
                      const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain, void* stream);
@@ -224,6 +238,22 @@ int pb200_anneal_run_signalled(const pb200_problem* prob, const pb200_chains* ch
                                const pb200_records* rec, int32_t n_iter, uint64_t seed, int32_t lanes_per_chain,
                                uint32_t* progress, int32_t* out_target, void* stream);
 
+/*
+ * Number of arrivals a rank with `n_chains` chains adds to an arrival counter of pb200_anneal_run_signalled /
+ * pb200_anneal_run_shared (= its number of chain warps for the geometry the library resolves `lanes_per_chain`
+ * to, environment overrides included).  A rank of a sharded job sums this over all ranks' chain counts to get the
+ * value the counters reach; 0 for n_chains <= 0, -1 (with pb200_last_error) for an invalid geometry.
+ */
+int pb200_exchange_arrivals(int32_t npad, int32_t n_chains, int32_t lanes_per_chain);
+
+/*
+ * Device-side protocol faults (a producer-warp ring or a TMA / tensor-core pipeline stage that never delivered within
+ * its time-out) do not trap the context: the kernel records the fault, stops the affected chains (status
+ * PB200_FAILED) and ends.  This call waits for the work enqueued on `stream` so far, then returns non-zero -- with
+ * the description in pb200_last_error() -- if any launch since the previous call recorded a fault, and clears it.
+ */
+int pb200_launch_status(void* stream);
+
 /* Enqueue on `stream` a wait until *counter >= value (cuStreamWaitValue32, CU_STREAM_WAIT_VALUE_GEQ). */
 int pb200_stream_wait_geq(void* stream, const uint32_t* counter, uint32_t value);
 
@@ -234,23 +264,6 @@ int pb200_stream_wait_geq(void* stream, const uint32_t* counter, uint32_t value)
  */
 int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,
                  const pb200_samples* samples, int32_t* accepted_out, int32_t lanes_per_chain, void* stream);
-
-/*
- * Streamed variant: the variate stream of one iteration is produced by a separate, fully parallel generator
- * kernel (pb200_variates_fill) and the annealing kernel reads it back, so random-number generation (about 60 % of
- * the instructions of the fused kernel) overlaps the latency-bound chain updates of the previous iteration when the
- * two are issued on different streams.  All chains of the batch must share the step counter `step_begin`
- * (chains.steps_done is ignored on input and advanced by steps_per_iteration on output).  Numbers are bit-identical
- * to pb200_anneal_run.
- *   zbuf: device buffer of pb200_variates_bytes(npad, n_chains, step_begin, steps_per_iteration) bytes,
- *         layout [chain][block][npad + 1] float4 (slot npad = the four accept variates of the block).
- */
-int64_t pb200_variates_bytes(int32_t npad, int32_t n_chains, uint32_t step_begin, int32_t n_steps);
-int pb200_variates_fill(const pb200_problem* prob, const pb200_chains* chains, uint32_t step_begin, int32_t n_steps,
-                        uint64_t seed, void* zbuf, void* stream);
-int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
-                              const pb200_records* rec, uint32_t step_begin, const void* zbuf,
-                              int32_t lanes_per_chain, void* stream);
 
 /*
  * lanes_per_chain (both samplers): how many lanes of a warp cooperate on one chain -- 32, 16 or 8 (16 / 8 only

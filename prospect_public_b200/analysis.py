@@ -44,17 +44,18 @@ class RunRecord:
 
 
 def bestfit_parabola(x, f):
-    """Vertex (x*, f*) of the parabola through three points (Lagrange form; same quantity as
-    analyse_profile_task.py:300-307)."""
-    (xm, xj, xp), (fm, fj, fp) = x, f
-    num = fm * (xj - xp) * (xj + xp) + fj * (xp - xm) * (xp + xm) + fp * (xm - xj) * (xm + xj)
-    den = 2.0 * (fm * (xj - xp) + fj * (xp - xm) + fp * (xm - xj))
-    x_best = num / den
-    # value of the interpolating parabola at x_best
-    lm = (x_best - xj) * (x_best - xp) / ((xm - xj) * (xm - xp))
-    lj = (x_best - xm) * (x_best - xp) / ((xj - xm) * (xj - xp))
-    lp = (x_best - xm) * (x_best - xj) / ((xp - xm) * (xp - xj))
-    return x_best, fm * lm + fj * lj + fp * lp
+    """Vertex (x*, f*) of the parabola through three points.  The floating-point operations are those of
+    analyse_profile_task.py:300-307, term for term and in the same order (Python float arithmetic, `pow` for the
+    squares), because x* and f* are printed at full precision into <param>.txt / <param>_intervals.txt: a
+    mathematically equal form (e.g. Lagrange) differs in the last bits and breaks byte-identity of those files
+    (tests/test_host_logic.py compares randomised triples bit for bit with the pinned port)."""
+    xm, xj, xp = (float(v) for v in x)
+    fm, fj, fp = (float(v) for v in f)
+    x_num = fp*(xj - xm)*(xj + xm) + fj*(xm - xp)*(xm + xp) + fm*(-pow(xj, 2) + pow(xp, 2))
+    x_den = 2.*(fp*(xj - xm) + fj*(xm - xp) + fm*(-xj + xp))
+    f_num = pow(-(fp*pow(xj - xm, 2)) + fj*pow(xm - xp, 2) + fm*(xj - xp)*(xj - 2*xm + xp), 2)
+    f_den = 4.*(xj - xm)*(xj - xp)*(xm - xp)*(fp*(-xj + xm) + fm*(xj - xp) + fj*(-xm + xp))
+    return x_num/x_den, fm + f_num/f_den
 
 
 def sort_bestfits(rec: RunRecord, reduced=None):

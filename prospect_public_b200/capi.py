@@ -14,7 +14,7 @@ ACTIVE, CONVERGED, FAILED = 0, 1, 2
 STEP_EXPONENTIAL, STEP_ADAPTIVE_FIXED, STEP_ADAPTIVE_SECANT = 0, 1, 2
 RECORD_NONE, RECORD_ACCEPTED, RECORD_THINNED = 0, 1, 2
 EXACT_BOX = 0x100
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 _vp = C.c_void_p
 
@@ -22,7 +22,7 @@ _vp = C.c_void_p
 class Problem(C.Structure):
     _fields_ = [('d', C.c_int32), ('n', C.c_int32), ('npad', C.c_int32), ('n_points', C.c_int32),
                 ('saa', _vp), ('sab', _vp), ('mu', _vp), ('lo', _vp), ('hi', _vp), ('f', _vp), ('c0', _vp),
-                ('lt_t', _vp), ('lam', _vp), ('lt_norm', _vp), ('g_t', _vp), ('h', _vp)]
+                ('lt_t', _vp), ('lam', _vp), ('lt_norm', _vp), ('g_t', _vp), ('h', _vp), ('lt_hi', _vp), ('lt_lo', _vp)]
 
 
 class Chains(C.Structure):
@@ -76,11 +76,8 @@ SIGNATURES = {
                                _vp, C.c_int32, _vp]),
     'pb200_choose_lanes': (C.c_int, [C.c_int32, C.c_int32]),
     'pb200_uses_producer_warps': (C.c_int, [C.c_int32, C.c_int32]),
-    'pb200_variates_bytes': (C.c_int64, [C.c_int32, C.c_int32, C.c_uint32, C.c_int32]),
-    'pb200_variates_fill': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.c_uint32, C.c_int32, C.c_uint64, _vp,
-                                      _vp]),
-    'pb200_anneal_run_streamed': (C.c_int, [C.POINTER(Problem), C.POINTER(Chains), C.POINTER(Schedule),
-                                            C.POINTER(Records), C.c_uint32, _vp, C.c_int32, _vp]),
+    'pb200_exchange_arrivals': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
+    'pb200_launch_status': (C.c_int, [_vp]),
     'pb200_schedule_update': (C.c_int, [C.POINTER(Chains), C.POINTER(Schedule), _vp, _vp, _vp]),
     'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -232,8 +232,29 @@ class Configuration:
 
     @property
     def seed(self):
-        """run.numpy_random_seed doubles as the Philox key; None draws one from the OS."""
+        """run.numpy_random_seed doubles as the Philox key; None draws one from the OS -- ONCE per Configuration, so
+        that every use (the optimiser, the snapshot a resumed run replays from) sees the same key.  Under torchrun
+        `synchronise()` makes rank 0's value the job's."""
         s = self.run.numpy_random_seed
-        if s is None:
-            return int.from_bytes(os.urandom(8), 'little')
-        return int(s) & 0xFFFFFFFFFFFFFFFF
+        if s is not None:
+            return int(s) & 0xFFFFFFFFFFFFFFFF
+        if getattr(self, '_drawn_seed', None) is None:
+            self._drawn_seed = int.from_bytes(os.urandom(8), 'little')
+        return self._drawn_seed
+
+    def synchronise(self):
+        """Make rank 0's resolved output folder and Philox key those of every rank of a torch.distributed job (every
+        rank builds its own Configuration: a late rank could otherwise de-duplicate io.dir differently, and ranks
+        without a numpy_random_seed would each draw their own key).  No-op for a single process."""
+        try:
+            import torch.distributed as dist
+        except ImportError:
+            return self
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self
+        payload = [{'dir': self.io.dir, 'seed': self.seed}]
+        dist.broadcast_object_list(payload, src=0)
+        self.io.dir = self.config_dict['io']['dir'] = payload[0]['dir']
+        if self.run.numpy_random_seed is None:
+            self._drawn_seed = int(payload[0]['seed'])
+        return self

@@ -153,22 +153,43 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 struct Ring {
     uint32_t data, full, empty, stop;   // shared-space addresses: slots, mbarriers [kRingDepth] each, stop word
     uint32_t count;                     // blocks produced / consumed so far by this side
+    uint32_t dead;                      // consumer: the producer stopped delivering (fault recorded)
 };
+
+// Device-side protocol faults (pb200_launch_status reads and clears the word).
+constexpr uint32_t kFaultRing = 1u;     // a producer warp never filled its ring slot
+constexpr uint32_t kFaultPipe = 2u;     // a TMA / tcgen05 pipeline barrier of the wide path never completed
+__device__ uint32_t g_fault_word = 0u;
+#ifndef PB200_WAIT_TIMEOUT_CYCLES
+#define PB200_WAIT_TIMEOUT_CYCLES 4000000000LL      // ~2 s at 1.9 GHz
+#endif
 
 template <int CPL>
 __device__ __forceinline__ constexpr int ring_slot_bytes() { return (CPL + 1) * 32 * 16; }
 
-// Consumer side: wait for the next block, copy it to registers, hand the slot back.  A producer that never
-// delivers would hang the GPU, so the wait is bounded and traps (the launch then fails loudly).
+// Consumer side: wait for the next block, copy it to registers, hand the slot back.  A producer that never delivers
+// would hang the GPU, so the wait is bounded: on a time-out the fault is recorded (pb200_launch_status turns it into
+// an error on the host), the ring is marked dead and every later fetch returns variates that reject every proposal
+// (z = 0, e = 0 -> Delta = 0 is not < 0); the caller stops the chains with status PB200_FAILED.
 template <int LPC, int CPL>
 __device__ __forceinline__ void ring_fetch(Ring& rg, int lane, int gi, float (&z)[CPL][4], float (&e)[4]) {
     const uint32_t slot = rg.count % kRingDepth, parity = (rg.count / kRingDepth) & 1u;
     const uint32_t bar = rg.full + 8u * slot;
-    if (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
+    if (!rg.dead && !__all_sync(kFull, mbar_try_wait(bar, parity))) {
         const long long t0 = clock64();
         while (!__all_sync(kFull, mbar_try_wait(bar, parity))) {
-            if (clock64() - t0 > 40000000000LL) __trap();      // ~20 s
+            if (__any_sync(kFull, clock64() - t0 > PB200_WAIT_TIMEOUT_CYCLES)) {
+                if (lane == 0) atomicOr(&g_fault_word, kFaultRing);
+                rg.dead = 1u;
+                break;
+            }
         }
+    }
+    if (rg.dead) {
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) z[r][0] = z[r][1] = z[r][2] = z[r][3] = 0.0f;
+        e[0] = e[1] = e[2] = e[3] = 0.0f;
+        return;
     }
     const uint32_t base = rg.data + slot * (uint32_t)ring_slot_bytes<CPL>();
 #pragma unroll

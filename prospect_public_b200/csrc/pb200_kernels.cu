@@ -13,7 +13,8 @@
 //   chain_min_kernel + point_reduce_kernel   min over iterations / first-min repetition / mean (warp shuffles).
 //   moments_kernel            weighted first/second moments (covariance reduction), FP64.
 //   chain_moments_kernel      per-chain weighted first moments of recorded chains (Gelman-Rubin statistics).
-//   variates_kernel           stand-alone Philox + Box-Muller stream generator (feeds the streamed annealing path).
+//   wide_* (pb200_wide.cuh, pb200_umma.cuh)  the per-iteration pipeline of wide problems (npad >= 128): steps ->
+//                             tcgen05 position GEMM -> FP64 anchor GEMM.
 //   rng_kernel                test hook exposing the variates.
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
@@ -36,6 +37,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 namespace pb200 {
 
@@ -109,6 +111,44 @@ struct ChainState {
 // materialised (n x n matvec), tested exactly and becomes the new reference point.
 // Predicates are per group; everything containing a shuffle or __syncwarp runs under warp-uniform control.
 // ----------------------------------------------------------------------------------------------
+// The exact prior-box test of a proposal: materialise it, compare with the box, and (deferred mode) the safe radius
+// around the point that will be the reference afterwards.  In the deferred mode this is the RARE path of a step (only
+// when |w|^2 leaves the safe radius), so it is kept out of line: inlined into each of the four unrolled steps of a
+// Philox block it made the hot loop several times larger than the instruction cache (ncu: `no_instruction` stalls of
+// 0.5 per issue in the 256-D kernel).  Arguments and results travel by value, so the caller's arrays stay in registers.
+template <int CPL>
+struct BoxIn { double xref[CPL]; float wt[CPL]; };
+template <int CPL>
+struct BoxProbe { double xt[CPL]; float m2n; bool outside; };
+
+template <int LPC, int CPL, bool WITH_RADIUS>
+__device__ __forceinline__ BoxProbe<CPL> probe_box_body(const pb200_problem& p, int pt, const float* __restrict__ lt_pt,
+                                                        int gl, int gi, bool exact, const BoxIn<CPL>& in, float* ws) {
+    BoxProbe<CPL> o;
+    materialise<LPC, CPL>(lt_pt, gl, in.xref, in.wt, ws, o.xt);
+    bool outside = false;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) {
+        const int col = gl + LPC * r;
+        outside = outside || (o.xt[r] < __ldg(p.lo + col)) || (o.xt[r] > __ldg(p.hi + col));
+    }
+    o.outside = group_any<LPC>(outside, gi);
+    o.m2n = 0.0f;
+    if (WITH_RADIUS) {                         // the safe radius around the reference point after this step
+        const bool reref = exact && !o.outside;
+        double ref[CPL];
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) ref[r] = reref ? o.xt[r] : in.xref[r];
+        o.m2n = safe_radius2<LPC, CPL>(p, pt, gl, ref);
+    }
+    return o;
+}
+template <int LPC, int CPL>
+__device__ __noinline__ BoxProbe<CPL> probe_box_rare(const pb200_problem& p, int pt, const float* __restrict__ lt_pt,
+                                                     int gl, int gi, bool exact, BoxIn<CPL> in, float* ws) {
+    return probe_box_body<LPC, CPL, true>(p, pt, lt_pt, gl, gi, exact, in, ws);
+}
+
 template <int LPC, int CPL, int REC, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
 __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
@@ -131,29 +171,22 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
         const bool exact = lik && (EXACT || !(rr <= c.m2));
         acc = lik;
         if (__any_sync(kFull, exact)) {
-            double xt[CPL];
-            materialise<LPC, CPL>(lt_pt, gl, c.xref, wt, ws, xt);
-            bool outside = false;
+            BoxIn<CPL> in;
 #pragma unroll
-            for (int r = 0; r < CPL; ++r) {
-                const int col = gl + LPC * r;
-                outside = outside || (xt[r] < __ldg(p.lo + col)) || (xt[r] > __ldg(p.hi + col));
-            }
-            outside = group_any<LPC>(outside, gi);
-            const bool reref = exact && !outside;
-            acc = lik && !(exact && outside);
+            for (int r = 0; r < CPL; ++r) { in.xref[r] = c.xref[r]; in.wt[r] = wt[r]; }
+            const BoxProbe<CPL> probe = EXACT ? probe_box_body<LPC, CPL, false>(p, pt, lt_pt, gl, gi, exact, in, ws)
+                                              : probe_box_rare<LPC, CPL>(p, pt, lt_pt, gl, gi, exact, in, ws);
+            const bool reref = exact && !probe.outside;
+            acc = lik && !(exact && probe.outside);
             if (reref) {
 #pragma unroll
                 for (int r = 0; r < CPL; ++r) {
                     if (c.best_rel) c.bref[r] = c.xref[r];      // the best point stays where it was
-                    c.xref[r] = xt[r];
+                    c.xref[r] = probe.xt[r];
                     wt[r] = 0.0f;
                 }
                 c.best_rel = false;
-            }
-            if (!EXACT) {                          // the safe radius around the new reference point
-                const float m2n = safe_radius2<LPC, CPL>(p, pt, gl, c.xref);
-                if (reref) c.m2 = m2n;
+                if (!EXACT) c.m2 = probe.m2n;
             }
         }
         if (acc) {
@@ -306,48 +339,20 @@ __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf
 // modulo 4 (`live` is false for the others).  Whole Philox blocks go through block_step, the ragged head / tail of
 // the range and blocks that need the exact box test through one_step.  Which path a step takes depends only on
 // the chain's own step index and state, never on its warp neighbours.
-// Variates of one Philox block from the pre-generated stream (variates_kernel): one float4 (the 4 steps) per
-// coordinate, the accept variates in slot npad.  Eight lanes of a group read 128 contiguous bytes.
-template <int LPC, int CPL>
-__device__ __forceinline__ void fetch_block(const float4* __restrict__ row, int n, int gl, float (&z)[CPL][4],
-                                            float (&e)[4]) {
-    constexpr int NPAD = LPC * CPL;
-#pragma unroll
-    for (int r = 0; r < CPL; ++r) {
-        const int coord = gl + LPC * r;
-        const float4 v = coord < n ? __ldg(row + coord) : make_float4(0.f, 0.f, 0.f, 0.f);
-        z[r][0] = v.x; z[r][1] = v.y; z[r][2] = v.z; z[r][3] = v.w;
-    }
-    const float4 ev = __ldg(row + NPAD);
-    e[0] = ev.x; e[1] = ev.y; e[2] = ev.z; e[3] = ev.w;
-}
-
 // Where the variates of a Philox block come from.
 constexpr int kSrcPhilox = 0;   // drawn in place by the warp that uses them
-constexpr int kSrcStream = 1;   // pre-generated by variates_kernel into global memory (one iteration per launch)
 constexpr int kSrcRing = 2;     // produced by the partner warp into a shared-memory ring (anneal_ws_kernel)
 
 template <int LPC, int CPL, int REC, int SRC, bool EXACT>
 __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
                                                 int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
                                                 uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
-                                                ChainState<CPL>& c, float* ws, RecCursor& rc,
-                                                const float4* __restrict__ zrow, Ring& ring) {
-    constexpr int NPAD = LPC * CPL;
-    constexpr bool ZBUF = SRC == kSrcStream;
+                                                ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring) {
     float z[CPL][4], e[4], zk[CPL];
-    float zn[ZBUF ? CPL : 1][4], en[4];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
-    const uint32_t blk0 = t_begin >> 2;
-    if constexpr (ZBUF) fetch_block<LPC, CPL>(zrow, p.n, gl, z, e);
     while (i < n_steps) {
         const uint32_t t = t_begin + i;
-        if constexpr (ZBUF) {
-            // the next block's loads are issued before this block is processed (one block of latency cover)
-            const uint32_t nxt = (t >> 2) + 1u - blk0;
-            if (((t >> 2) + 1u) << 2 < t_begin + n_steps)
-                fetch_block<LPC, CPL>(zrow + (size_t)nxt * (NPAD + 1), p.n, gl, zn, en);
-        } else if constexpr (SRC == kSrcRing) {
+        if constexpr (SRC == kSrcRing) {
             ring_fetch<LPC, CPL>(ring, gi * LPC + gl, gi, z, e);
         } else {
             draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
@@ -369,15 +374,6 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
             }
         }
         i += cnt;
-        if constexpr (ZBUF) {
-#pragma unroll
-            for (int r = 0; r < CPL; ++r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) z[r][k] = zn[r][k];
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) e[k] = en[k];
-        }
     }
 }
 
@@ -385,8 +381,7 @@ template <int LPC, int CPL, int REC, int SRC = kSrcPhilox, bool EXACT = (REC == 
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
-                                          ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring,
-                                          const float4* __restrict__ zrow = nullptr) {
+                                          ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring) {
     asm volatile("" : "+f"(Tf), "+f"(sf));      // keep the FP32 copies live instead of re-converting the doubles
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
@@ -399,14 +394,14 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
     if (SRC == kSrcRing || __all_sync(kFull, !live || (t_begin & 3u) == lead)) {
         // (ring: the kernel only pairs a producer with warps whose live chains share one alignment class)
         run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
-                                            sf, c, ws, rc, zrow, ring);
+                                            sf, c, ws, rc, ring);
     } else {
 #pragma unroll 1
         for (uint32_t a = 0; a < 4u; ++a) {
             const bool mine = live && (t_begin & 3u) == a;
             if (__any_sync(kFull, mine))
                 run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
-                                                    n_steps, Tf, sf, c, ws, rc, zrow, ring);
+                                                    n_steps, Tf, sf, c, ws, rc, ring);
         }
     }
 }
@@ -426,18 +421,15 @@ __device__ __forceinline__ void anchor(const pb200_problem& p, int pt, int gl, c
 // ----------------------------------------------------------------------------------------------
 // Fused annealing: n_iter iterations x S steps per launch, one lane group per chain.  `warp_slot` is the index of
 // this warp among the warps that own chains, `stage_warp` its [G][NPAD] double staging rows in shared memory.
-// SRC = kSrcStream: ONE iteration whose variates were pre-generated by variates_kernel into `zbuf`
-// ([chain][nb][npad + 1] float4, first block = t_stream >> 2); all chains then share the step counter t_stream.
 // SRC = kSrcRing: the variates come from the partner warp through `ring` (anneal_ws_kernel).
 // ----------------------------------------------------------------------------------------------
 template <int LPC, int CPL, int SRC>
 __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_chains& ch, const pb200_schedule& s,
                                             const pb200_records& rec, int n_iter, uint32_t k0, uint32_t k1,
-                                            const float4* __restrict__ zbuf, int nb, uint32_t t_stream, int warp_slot,
+                                            int warp_slot,
                                             double* stage_warp, Ring& ring, uint32_t* __restrict__ progress,
                                             const pb200_peers& peers) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
-    constexpr bool ZBUF = SRC == kSrcStream;
     const int lane = threadIdx.x & 31, gi = lane / LPC, gl = lane % LPC;
     const int slot = warp_slot * G + gi;
     if (warp_slot * G >= ch.n_chains) return;         // whole warp idle
@@ -457,8 +449,7 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
     const bool was_live = live;
     const int pt = ch.point[chain];
     const uint32_t chain_id = ch.chain_id[chain];
-    uint32_t t = ZBUF ? t_stream : ch.steps_done[chain];
-    const float4* zrow = ZBUF ? zbuf + (size_t)chain * nb * (NPAD + 1) : nullptr;
+    uint32_t t = ch.steps_done[chain];
     const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
     double* qs = stage_warp + gi * NPAD;
     float* ws = reinterpret_cast<float*>(qs);
@@ -483,7 +474,7 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
         c.best_rel = true;
         run_steps<LPC, CPL, PB200_RECORD_NONE, SRC>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t,
                                                     (uint32_t)s.steps_per_iteration, (float)st.temperature,
-                                                    (float)st.step_size, lam, c, ws, rc, ring, zrow);
+                                                    (float)st.step_size, lam, c, ws, rc, ring);
         // set_bestfit: positions are materialised, the reported chi^2 is re-evaluated in FP64 at them
         if (c.best_rel) {
 #pragma unroll
@@ -535,6 +526,10 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
             if (lane == 0) atomicAdd(progress + it, 1u);
         }
     }
+    if (SRC == kSrcRing && ring.dead && live) {     // the producer stopped delivering: stop these chains, loudly
+        st.status = PB200_FAILED;
+        live = false;
+    }
     if (progress && lane == 0) { // iterations this warp will never run (all its chains stopped) count as done
         for (int k = it; k < n_iter; ++k) atomicAdd(progress + k, 1u);
     }
@@ -567,18 +562,17 @@ __device__ __forceinline__ void anneal_body(const pb200_problem& p, const pb200_
     }
 }
 
-template <int LPC, int CPL, bool ZBUF>
+template <int LPC, int CPL>
 __global__ void __launch_bounds__(32 * kWarpsPerCta, Geometry<LPC, CPL>::kMinCtas)
 anneal_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, int n_iter, uint32_t k0,
-              uint32_t k1, const float4* __restrict__ zbuf, int nb, uint32_t t_stream, uint32_t* __restrict__ progress,
+              uint32_t k1, uint32_t* __restrict__ progress,
               const __grid_constant__ pb200_peers peers) {
     constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     __shared__ __align__(16) double stage[kWarpsPerCta][G][NPAD];
     const int wib = threadIdx.x >> 5;
     Ring none{};
-    anneal_body<LPC, CPL, ZBUF ? kSrcStream : kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, zbuf, nb, t_stream,
-                                                          blockIdx.x * kWarpsPerCta + wib, &stage[wib][0][0], none,
-                                                          progress, peers);
+    anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, blockIdx.x * kWarpsPerCta + wib,
+                                      &stage[wib][0][0], none, progress, peers);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -653,6 +647,7 @@ anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_recor
     ring.empty = smem_addr(&bars[pair][kRingDepth]);
     ring.stop = smem_addr(&stop[pair]);
     ring.count = 0u;
+    ring.dead = 0u;
     if (producer) {
         if (paired)
             produce_variates<LPC, CPL>(p.n, n_iter, (uint32_t)s.steps_per_iteration, k0, k1, chain_id,
@@ -660,14 +655,19 @@ anneal_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_recor
         return;
     }
     if (paired)
-        anneal_body<LPC, CPL, kSrcRing>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot, &stage[pair][0][0],
-                                        ring, progress, peers);
+        anneal_body<LPC, CPL, kSrcRing>(p, ch, s, rec, n_iter, k0, k1, warp_slot, &stage[pair][0][0], ring, progress,
+                                        peers);
     else
-        anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, nullptr, 0, 0u, warp_slot,
-                                          &stage[pair][0][0], ring, progress, peers);
+        anneal_body<LPC, CPL, kSrcPhilox>(p, ch, s, rec, n_iter, k0, k1, warp_slot, &stage[pair][0][0], ring, progress,
+                                          peers);
     __syncwarp();
     if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ring.stop), "r"(1u) : "memory");
 }
+
+}  // namespace pb200
+#include "pb200_wide.cuh"
+#include "pb200_umma.cuh"
+namespace pb200 {
 
 // ----------------------------------------------------------------------------------------------
 // Metropolis-Hastings rounds (jobtype mcmc): fixed temperature / step size per chain, chain recording.
@@ -947,34 +947,6 @@ chain_moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ m
     if (lane == 0) out_sw[chain] = sw;
 }
 
-// Stand-alone generator of the samplers' variate stream: one thread per (chain, Philox block, slot) makes the one
-// Philox-4x32-10 call whose four words become the four normals of coordinate `slot` in steps 4*blk .. 4*blk+3 (or,
-// for slot == n, the four accept variates) and stores them as ONE float4.  Embarrassingly parallel, no idle lanes,
-// 16-byte coalesced stores; the annealing kernel then streams them back (fetch_block).  Same device functions as
-// the inline path, so the numbers are bit-identical.
-__global__ void __launch_bounds__(256)
-variates_kernel(const uint32_t* __restrict__ chain_id, int n_chains, int n, int npad, int nb, uint32_t blk0,
-                uint32_t k0, uint32_t k1, float4* __restrict__ out) {
-    const long long total = (long long)n_chains * nb * (n + 1);
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
-        const int slot = (int)(idx % (n + 1));
-        const long long rest = idx / (n + 1);
-        const int b = (int)(rest % nb), chain = (int)(rest / nb);
-        uint32_t w[4];
-        philox4x32_10(blk0 + (uint32_t)b, slot == n ? kAcceptSlot : (uint32_t)slot, __ldg(chain_id + chain), 0u, k0, k1,
-                      w);
-        float4 v;
-        if (slot < n) {
-            box_muller(w[0], w[1], v.x, v.y);
-            box_muller(w[2], w[3], v.z, v.w);
-        } else {
-            v = make_float4(exp_variate(w[0]), exp_variate(w[1]), exp_variate(w[2]), exp_variate(w[3]));
-        }
-        out[((size_t)chain * nb + b) * (npad + 1) + (slot == n ? npad : slot)] = v;
-    }
-}
-
 __global__ void rng_kernel(uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t step0, int n_steps, int n,
                            float* __restrict__ out_z, float* __restrict__ out_e) {
     // one warp; CPL = 8 covers every n <= 256 with the production draw_block
@@ -1004,6 +976,122 @@ static int validate(const pb200_problem* p) {
     if (!p->saa || !p->sab || !p->mu || !p->lo || !p->hi || !p->f || !p->c0 || !p->lt_t || !p->lam || !p->lt_norm || !p->g_t || !p->h)
         return fail("problem has NULL device pointers");
     return 0;
+}
+
+// Layout guard of the wide path: its GEMM tiles address the repetitions of a point as chain = rep * P + point (the
+// enumeration every entry point documents).  A batch laid out differently is stopped, loudly at the data level:
+// every chain gets status FAILED and no record is written.
+__global__ void wide_check_layout_kernel(pb200_chains ch, int n_points) {
+    __shared__ int bad;
+    if (threadIdx.x == 0) bad = 0;
+    __syncthreads();
+    for (int c = threadIdx.x; c < ch.n_chains; c += blockDim.x)
+        if (ch.point[c] != c % n_points) bad = 1;
+    __syncthreads();
+    if (bad)
+        for (int c = threadIdx.x; c < ch.n_chains; c += blockDim.x) ch.status[c] = PB200_FAILED;
+}
+
+static bool use_wide_path(const pb200_problem* prob, const pb200_chains* chains) {
+    if (prob->npad < 128 || chains->n_chains % prob->n_points != 0) return false;
+    if (const char* env = std::getenv("PB200_WIDE")) return env[0] != '0';
+    return true;
+}
+
+// Annealing iterations of a wide problem as three launches each (pb200_wide.cuh).  Scratch memory is stream-ordered
+// (cudaMallocAsync on `st`), so the call stays asynchronous and owns nothing afterwards.
+template <int NPAD>
+static int anneal_launch_wide(const pb200_problem& prob, const pb200_chains& chains, const pb200_schedule& sched,
+                              const pb200_records& rec, int n_iter, uint32_t k0, uint32_t k1, uint32_t* progress,
+                              cudaStream_t st, const pb200_peers& peers) {
+    constexpr int CPL = NPAD / 32;
+    const size_t b = (size_t)chains.n_chains;
+    const int P = prob.n_points, reps = chains.n_chains / P;
+    static bool pool_ready = false;
+    if (!pool_ready) {                     // keep freed scratch cached in the default pool between calls
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = UINT64_MAX;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_ready = true;
+    }
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
+    const size_t o_base = carve(2 * b * NPAD * 8), o_hi = carve(2 * b * NPAD * 4), o_lo = carve(2 * b * NPAD * 4),
+                 o_bx = carve(b * NPAD * 8), o_v = carve(3 * b * NPAD * 8), o_nacc = carve(b * 4), o_ran = carve(b * 4);
+    char* mem = nullptr;
+    if (check_cuda(cudaMallocAsync((void**)&mem, off, st), "cudaMallocAsync (wide workspace)")) return 1;
+    WideWs ws{(double*)(mem + o_base), (float*)(mem + o_hi), (float*)(mem + o_lo), (double*)(mem + o_bx),
+              (double*)(mem + o_v), (int32_t*)(mem + o_nacc), (int32_t*)(mem + o_ran)};
+    const int n_rt = (reps + kWideTileRows - 1) / kWideTileRows, n_at = (reps + kAnchorTileRows - 1) / kAnchorTileRows;
+    const int steps_blocks = (chains.n_chains + kWarpsPerCta - 1) / kWarpsPerCta;
+    const size_t anchor_smem = sizeof(double) * (kAnchorTileRows * NPAD + 2 * kWideKChunk * kAnchorTileCols);
+    static bool attr_set[2] = {false, false};
+    if (!attr_set[NPAD == 256]) {
+        if (check_cuda(cudaFuncSetAttribute(wide_anchor_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)anchor_smem), "cudaFuncSetAttribute (wide_anchor_kernel)"))
+            return 1;
+        attr_set[NPAD == 256] = true;
+    }
+    WideMma mma;
+    if (wide_mma_prepare<NPAD>(prob, chains, ws, reps, &mma)) return 1;
+    // PB200_WIDE_TIMING=1 (diagnostics): CUDA events between the launches, one synchronising report per call on stderr
+    static const bool timing = std::getenv("PB200_WIDE_TIMING") && std::getenv("PB200_WIDE_TIMING")[0] == '1';
+    std::vector<cudaEvent_t> marks;
+    auto mark = [&]() {
+        if (!timing) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        marks.push_back(e);
+    };
+    mark();
+    wide_check_layout_kernel<<<1, 256, 0, st>>>(chains, P);
+    wide_anchor_kernel<NPAD><<<2 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x3);
+    mark();
+    // producer warps pay while the chain warps alone leave the schedulers short of instruction streams (measured:
+    // profiles/README.md); PB200_WIDE_WS=0 / 1 forces the choice
+    bool ws_steps = chains.n_chains <= 148 * 16 / 2;
+    if (const char* env = std::getenv("PB200_WIDE_WS")) ws_steps = env[0] != '0';
+    const int ws_blocks = (chains.n_chains + kWideWsPairs - 1) / kWideWsPairs;
+    for (int it = 0; it < n_iter; ++it) {
+        const int flags = (it > 0 ? kWideFinish : 0) | kWideRun;
+        if (ws_steps)
+            wide_steps_ws_kernel<CPL><<<ws_blocks, 64 * kWideWsPairs, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
+                                                                               flags, it, n_iter, progress, peers);
+        else
+            wide_steps_kernel<CPL><<<steps_blocks, 32 * kWarpsPerCta, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
+                                                                               flags, it, n_iter, progress, peers);
+        mark();
+        if (mma.enabled) {
+            if (wide_mma_launch<NPAD>(prob, chains, ws, reps, mma, st)) return 1;
+        } else {
+            wide_materialise_simt_kernel<NPAD><<<2 * P * n_rt, NPAD, 0, st>>>(prob, chains, ws, reps);
+        }
+        mark();
+        wide_anchor_kernel<NPAD><<<3 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x7);
+        mark();
+    }
+    wide_steps_kernel<CPL><<<steps_blocks, 32 * kWarpsPerCta, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
+                                                                        kWideFinish | kWideLast, n_iter, n_iter,
+                                                                        progress, peers);
+    if (check_cuda(cudaGetLastError(), "wide annealing launches")) return 1;
+    if (timing && marks.size() >= 2) {
+        cudaStreamSynchronize(st);
+        double t_steps = 0, t_pos = 0, t_anchor = 0;
+        float ms = 0;
+        for (size_t i = 2; i + 0 < marks.size(); ++i) {      // marks: [start, after first anchor, (steps, pos, anchor)*]
+            cudaEventElapsedTime(&ms, marks[i - 1], marks[i]);
+            const size_t ph = (i - 2) % 3;
+            (ph == 0 ? t_steps : ph == 1 ? t_pos : t_anchor) += ms;
+        }
+        std::fprintf(stderr, "[pb200 wide timing] %d iterations: steps %.1f us, positions %.1f us, anchors %.1f us per iteration\n",
+                     n_iter, 1e3 * t_steps / n_iter, 1e3 * t_pos / n_iter, 1e3 * t_anchor / n_iter);
+        for (cudaEvent_t e : marks) cudaEventDestroy(e);
+    }
+    return check_cuda(cudaFreeAsync(mem, st), "cudaFreeAsync (wide workspace)");
 }
 
 }  // namespace pb200
@@ -1114,9 +1202,9 @@ static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, 
         for (int q = 0; q < peers.n_peers; ++q)
             if (!peers.buffer[q] || !peers.progress[q]) return fail("anneal_run_shared: NULL peer buffer");
     }
+    if (!prob || !chains || !sched || !rec) return fail("anneal_run: NULL argument");
+    if (chains->n_chains <= 0 || n_iter <= 0) return 0;      // a rank without chains (fewer chains than GPUs) is fine
     if (validate(prob)) return 1;
-    if (!chains || !sched || !rec) return fail("anneal_run: NULL argument");
-    if (chains->n_chains <= 0 || n_iter <= 0) return 0;
     if (sched->steps_per_iteration <= 0) return fail("anneal_run: steps_per_iteration must be > 0");
     if (sched->step_mode < 0 || sched->step_mode > 2) return fail("anneal_run: unknown step_mode");
     if (!rec->best_loglkl || !rec->last_loglkl || !rec->temperature || !rec->step_size || !rec->accepted)
@@ -1128,6 +1216,10 @@ static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, 
     const int per_cta = kWarpsPerCta * (32 / lanes);
     const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    if (use_wide_path(prob, chains)) {
+        if (prob->npad == 128) return anneal_launch_wide<128>(*prob, *chains, *sched, *rec, n_iter, k0, k1, progress, st, peers);
+        return anneal_launch_wide<256>(*prob, *chains, *sched, *rec, n_iter, k0, k1, progress, st, peers);
+    }
     if (use_producer_warps(lanes, chains->n_chains)) {
         const int pairs = (chains->n_chains + (32 / lanes) - 1) / (32 / lanes);
         const int ws_blocks = (pairs + kWsPairs - 1) / kWsPairs;
@@ -1136,9 +1228,8 @@ static int anneal_launch(const pb200_problem* prob, const pb200_chains* chains, 
                                                         peers)));
         return check_cuda(cudaGetLastError(), "anneal_ws_kernel launch");
     }
-    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, false><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
-                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1, nullptr, 0, 0u,
-                                                    progress, peers)));
+    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
+                                                    *prob, *chains, *sched, *rec, n_iter, k0, k1, progress, peers)));
     return check_cuda(cudaGetLastError(), "anneal_kernel launch");
 }
 
@@ -1169,69 +1260,45 @@ int pb200_anneal_run_shared(const pb200_problem* prob, const pb200_chains* chain
     return anneal_launch(prob, chains, sched, rec, n_iter, seed, lanes_per_chain, progress, stream, peers);
 }
 
+int pb200_exchange_arrivals(int32_t npad, int32_t n_chains, int32_t lanes_per_chain) {
+    if (n_chains <= 0) return 0;
+    int lanes;
+    if (resolve_lanes(lanes_per_chain, npad, n_chains, &lanes)) return -1;
+    return (n_chains + (32 / lanes) - 1) / (32 / lanes);      // warps that own chains (wide path: one per chain)
+}
+
+int pb200_launch_status(void* stream) {
+    uint32_t word = 0;
+    if (check_cuda(cudaMemcpyFromSymbolAsync(&word, g_fault_word, sizeof(word), 0, cudaMemcpyDeviceToHost,
+                                             (cudaStream_t)stream), "launch_status: read"))
+        return 1;
+    if (check_cuda(cudaStreamSynchronize((cudaStream_t)stream), "launch_status: synchronize")) return 1;
+    if (word == 0) return 0;
+    const uint32_t zero = 0;
+    cudaMemcpyToSymbol(g_fault_word, &zero, sizeof(zero));
+    std::string msg = "device-side protocol fault:";
+    if (word & kFaultRing) msg += " a producer-warp ring timed out (anneal_ws_kernel);";
+    if (word & kFaultPipe) msg += " a TMA / tcgen05 pipeline barrier timed out (wide_materialise_mma_kernel);";
+    return fail(msg + " the affected chains were stopped, results of this launch are incomplete");
+}
+
 // cuStreamWaitValue32 through the runtime's driver entry point lookup: no link-time dependency on libcuda, so
 // the library still loads (and exports every symbol) on a machine without a driver.
 int pb200_stream_wait_geq(void* stream, const uint32_t* counter, uint32_t value) {
     typedef int (*wait_fn)(void*, unsigned long long, unsigned int, unsigned int);
-    static wait_fn fn = nullptr;
-    if (!fn) {
+    static const wait_fn fn = []() -> wait_fn {          // initialised once, thread-safe (C++11 magic static)
         void* ptr = nullptr;
         cudaDriverEntryPointQueryResult status;
-        if (check_cuda(cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &status),
-                       "cudaGetDriverEntryPoint(cuStreamWaitValue32)"))
-            return 1;
-        if (status != cudaDriverEntryPointSuccess || !ptr) return fail("cuStreamWaitValue32 is not available");
-        fn = (wait_fn)ptr;
-    }
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &ptr, cudaEnableDefault, &status) != cudaSuccess ||
+            status != cudaDriverEntryPointSuccess)
+            return nullptr;
+        return (wait_fn)ptr;
+    }();
+    if (!fn) return fail("cuStreamWaitValue32 is not available");
     if (!counter) return fail("stream_wait_geq: NULL counter");
     const int rc = fn(stream, (unsigned long long)(uintptr_t)counter, value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
     if (rc != 0) return fail("cuStreamWaitValue32 failed with CUresult " + std::to_string(rc));
     return 0;
-}
-
-int64_t pb200_variates_bytes(int32_t npad, int32_t n_chains, uint32_t step_begin, int32_t n_steps) {
-    if (n_steps <= 0 || n_chains <= 0) return 0;
-    const int64_t nb = (int64_t)((step_begin + (uint32_t)n_steps - 1u) >> 2) - (int64_t)(step_begin >> 2) + 1;
-    return (int64_t)n_chains * nb * (npad + 1) * (int64_t)sizeof(float4);
-}
-
-int pb200_variates_fill(const pb200_problem* prob, const pb200_chains* chains, uint32_t step_begin, int32_t n_steps,
-                        uint64_t seed, void* zbuf, void* stream) {
-    if (validate(prob)) return 1;
-    if (!chains || !zbuf) return fail("variates_fill: NULL argument");
-    if (chains->n_chains <= 0 || n_steps <= 0) return 0;
-    const uint32_t blk0 = step_begin >> 2;
-    const int nb = (int)(((step_begin + (uint32_t)n_steps - 1u) >> 2) - blk0 + 1u);
-    const long long total = (long long)chains->n_chains * nb * (prob->n + 1);
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148LL * 64);
-    variates_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(chains->chain_id, chains->n_chains, prob->n, prob->npad,
-                                                             nb, blk0, (uint32_t)seed, (uint32_t)(seed >> 32),
-                                                             (float4*)zbuf);
-    return check_cuda(cudaGetLastError(), "variates_kernel launch");
-}
-
-int pb200_anneal_run_streamed(const pb200_problem* prob, const pb200_chains* chains, const pb200_schedule* sched,
-                              const pb200_records* rec, uint32_t step_begin, const void* zbuf,
-                              int32_t lanes_per_chain, void* stream) {
-    if (validate(prob)) return 1;
-    if (!chains || !sched || !rec || !zbuf) return fail("anneal_run_streamed: NULL argument");
-    if (chains->n_chains <= 0) return 0;
-    if (sched->steps_per_iteration <= 0) return fail("anneal_run_streamed: steps_per_iteration must be > 0");
-    if (sched->step_mode < 0 || sched->step_mode > 2) return fail("anneal_run_streamed: unknown step_mode");
-    if (!rec->best_loglkl || !rec->last_loglkl || !rec->temperature || !rec->step_size || !rec->accepted)
-        return fail("anneal_run_streamed: records have NULL device pointers");
-    if (rec->iter_stride < chains->n_chains) return fail("anneal_run_streamed: records iter_stride < n_chains");
-    int lanes;
-    if (resolve_lanes(lanes_per_chain, prob->npad, chains->n_chains, &lanes)) return 1;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int per_cta = kWarpsPerCta * (32 / lanes);
-    const int blocks = (chains->n_chains + per_cta - 1) / per_cta;
-    const uint32_t blk0 = step_begin >> 2;
-    const int nb = (int)(((step_begin + (uint32_t)sched->steps_per_iteration - 1u) >> 2) - blk0 + 1u);
-    PB200_DISPATCH_GEOMETRY(prob->npad, lanes, (anneal_kernel<LPC, CPL, true><<<blocks, 32 * kWarpsPerCta, 0, st>>>(
-                                                    *prob, *chains, *sched, *rec, 1, 0u, 0u, (const float4*)zbuf, nb,
-                                                    step_begin, nullptr, pb200_peers{})));
-    return check_cuda(cudaGetLastError(), "anneal_kernel (streamed) launch");
 }
 
 int pb200_mh_run(const pb200_problem* prob, const pb200_chains* chains, int32_t n_steps, uint64_t seed,

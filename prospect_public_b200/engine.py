@@ -230,26 +230,18 @@ def stream_wait_geq(stream, counter, index, value):
                                                 int(value)))
 
 
-def variates_buffer(problem, n_chains, n_steps):
-    """Device buffer large enough for the variate stream of `n_steps` steps of `n_chains` chains at any alignment."""
-    nbytes = capi.lib().pb200_variates_bytes(int(problem.npad), int(n_chains), 3, int(n_steps))
-    return torch.empty(int(nbytes), dtype=torch.uint8, device=problem.device)
+def exchange_arrivals(npad, n_chains, lanes=0):
+    """Arrivals a rank with `n_chains` chains adds to the counters of the signalled / shared launches."""
+    n = int(capi.lib().pb200_exchange_arrivals(int(npad), int(n_chains), int(lanes)))
+    if n < 0:
+        capi.check(1)
+    return n
 
 
-def variates_fill(problem, chains: ChainBatch, step_begin, n_steps, seed, zbuf, stream=None):
-    """Generate the normals / accept variates of steps [step_begin, step_begin + n_steps) of every chain into zbuf."""
-    _count()
-    capi.check(capi.lib().pb200_variates_fill(C.byref(problem.c), C.byref(chains.c), int(step_begin), int(n_steps),
-                                              C.c_uint64(seed), capi.ptr(zbuf), _stream_ptr(stream)))
-
-
-def anneal_run_streamed(problem, chains: ChainBatch, schedule, records: Records, step_begin, zbuf, stream=None,
-                        lanes=0):
-    """One annealing iteration reading its variates from zbuf (see pb200_anneal_run_streamed)."""
-    _count()
-    capi.check(capi.lib().pb200_anneal_run_streamed(C.byref(problem.c), C.byref(chains.c), C.byref(schedule),
-                                                    C.byref(records.c), int(step_begin), capi.ptr(zbuf), int(lanes),
-                                                    _stream_ptr(stream)))
+def launch_status(stream=None):
+    """Wait for the stream and raise Pb200Error if a launch recorded a device-side protocol fault (a producer-warp
+    ring or a TMA / tensor-core pipeline stage that timed out)."""
+    capi.check(capi.lib().pb200_launch_status(_stream_ptr(stream)))
 
 
 def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, stream=None, lanes=0,

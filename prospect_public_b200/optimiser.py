@@ -47,6 +47,16 @@ def step_mode_of(profile_cfg):
     return capi.STEP_ADAPTIVE_FIXED
 
 
+def blank_rows(rows, world, scalar_len, n_alloc, device):
+    """[rows, world, scalar_len] FP64 blocks in the "chain did not run this iteration" state: best / last loglkl = inf,
+    accepted = -1 (the layout of engine.Records' scalar prefix)."""
+    import torch
+    blank = torch.zeros((rows, world, scalar_len), dtype=torch.float64, device=device)
+    blank[:, :, :2 * n_alloc] = math.inf
+    blank[:, :, 4 * n_alloc:].view(torch.int32).fill_(-1)
+    return blank
+
+
 class ExchangeUnavailable(RuntimeError):
     """Peer-mapped exchange buffers could not be set up (no symmetric memory / no peer access)."""
 
@@ -75,9 +85,7 @@ def _exchange_buffers(rows, world, scalar_len, n_alloc, device):
                              'hp': symm_mem.rendezvous(prog, dist.group.WORLD)})
         except Exception as exc:            # noqa: BLE001 -- any failure here means "use the NCCL path"
             raise ExchangeUnavailable(f'{type(exc).__name__}: {exc}') from exc
-        blank = torch.zeros((rows, world, scalar_len), dtype=torch.float64, device=device)
-        blank[:, :, :2 * n_alloc] = math.inf
-        blank[:, :, 4 * n_alloc:].view(torch.int32).fill_(-1)
+        blank = blank_rows(rows, world, scalar_len, n_alloc, device)
         for st in sets:
             st['buf'].copy_(blank)
             st['prog'].zero_()
@@ -115,7 +123,9 @@ class SimulatedAnnealing:
         self.rank, self.world, _ = dist_info()
         pt, rep = shard_grid(self.n_points, self.reps, self.rank, self.world)
         self.point_global, self.rep = pt, rep
-        self.local_points = np.unique(pt)
+        # a rank without chains (fewer chains than GPUs) still builds a (dummy, one-point) problem and joins every
+        # collective; its launches are no-ops
+        self.local_points = np.unique(pt) if len(pt) else np.array([0])
         point_local = np.searchsorted(self.local_points, pt).astype(np.int32)
         fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
         self.problem = kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covs[self.local_points])
@@ -142,12 +152,6 @@ class SimulatedAnnealing:
         self.lanes = int(s.get('lanes_per_chain', 0))
         self.seed = int(s.get('seed', 0))
         self.step_counter = 0                 # MH steps taken so far by every live chain (they advance in lockstep)
-        # streamed=True generates each iteration's variates with the stand-alone generator kernel on a side stream.
-        # Measured on B200 (profiles/README.md) it is SLOWER than the fused kernel at every batch size tried: the fused
-        # kernel hides its RNG instructions in the stall cycles of the latency-bound chain updates, and per-iteration
-        # launches re-synchronise all chains.  Kept as a tested alternative (bit-identical results), off by default.
-        self.streamed = bool(s.get('streamed', False))
-        self._zbufs = None
         self.iterations_done = int(s.get('iteration_number', 0))
         self.bestfit = None
         self._gatherer = None
@@ -167,37 +171,6 @@ class SimulatedAnnealing:
                           self.lanes)
         self.iterations_done += n_iterations
         self.step_counter += n_iterations * self.schedule.steps_per_iteration
-
-    def optimise_streamed(self, n_iterations):
-        """`n_iterations` iterations, one launch each, with the variate stream of iteration k+1 generated on a side
-        stream (variates_kernel: fully parallel Philox + Box-Muller) while iteration k's chains advance: random-number
-        generation is ~60 % of the fused kernel's instructions but independent of the chain state, the chain
-        updates are latency-bound -- two kernels in flight fill the machine with either.  Double-buffered."""
-        import torch
-        from . import engine
-        steps = self.schedule.steps_per_iteration
-        if self._zbufs is None:
-            self._zbufs = [engine.variates_buffer(self.problem, self.n_chains, steps) for _ in range(2)]
-            self._gen_stream = torch.cuda.Stream(device=self.problem.device)
-            self._ev_gen = [torch.cuda.Event() for _ in range(2)]
-            self._ev_free = [torch.cuda.Event() for _ in range(2)]
-        comp = torch.cuda.current_stream()
-        self._gen_stream.wait_stream(comp)
-        for k in range(n_iterations):
-            b = k % 2
-            t0 = self.step_counter
-            with torch.cuda.stream(self._gen_stream):
-                if k >= 2:
-                    self._gen_stream.wait_event(self._ev_free[b])
-                engine.variates_fill(self.problem, self.batch, t0, steps, self.seed, self._zbufs[b])
-                self._ev_gen[b].record(self._gen_stream)
-            comp.wait_event(self._ev_gen[b])
-            engine.anneal_run_streamed(self.problem, self.batch, self.schedule, self.records, t0, self._zbufs[b],
-                                       lanes=self.lanes)
-            self._ev_free[b].record(comp)
-            self.iterations_done += 1
-            self.step_counter += steps
-            yield self.iterations_done - 1
 
     def set_bestfit(self, iteration=None):
         """Host view of one iteration's records: loglkl, acceptance_rate, accepted_steps, position per chain
@@ -238,18 +211,16 @@ class SimulatedAnnealing:
     # --- whole schedules ---------------------------------------------------------------------------
     def run_schedule(self, n_iterations, iterations_per_launch=None, gather=True):
         """All iterations.  Single GPU: `iterations_per_launch` (default: all) per launch.  Several GPUs: still ONE
-        fused launch, and the iteration-boundary exchange of the per-chain scalars (bestfit chi^2, last chi^2,
+        call, and the iteration-boundary exchange of the per-chain scalars (bestfit chi^2, last chi^2,
         temperature, step size, accepted count) is done by the kernel itself over peer memory (run_fused_exchange).
         Fallbacks: the kernel counts finished iterations and a side stream all-gathers each one over NCCL behind a
         device-side wait (run_signalled; PB200_EXCHANGE=nccl or no symmetric memory); one launch + one gather per
-        iteration (`self.signalled = False` or the streamed generator).  The bestfit positions of all iterations
-        follow in one all-gather at the end (global_records)."""
+        iteration (`self.signalled = False`).  The bestfit positions of all iterations follow in one all-gather at
+        the end (global_records)."""
         import torch
+        if self.n_chains == 0 and (self.world == 1 or not gather):
+            return None
         if self.world == 1 or not gather:
-            if self.streamed and iterations_per_launch is None:
-                for _ in self.optimise_streamed(n_iterations):
-                    pass
-                return None
             per = n_iterations if iterations_per_launch is None else iterations_per_launch
             done = 0
             while done < n_iterations:
@@ -261,13 +232,16 @@ class SimulatedAnnealing:
         if self._gatherer is None:
             self._gatherer = True
             self._comm_stream = torch.cuda.Stream(device=self.problem.device)
-            self.gathered = torch.zeros((self.max_rows, self.world, self.records.scalar_len), dtype=torch.float64,
-                                        device=self.problem.device)
+            # rows that were never shipped must read "did not run" (loglkl = inf, accepted = -1), exactly like the
+            # exchange buffers and a single-GPU Records: a partial run (stop_after, an interrupted snapshot) decodes
+            # every row of this tensor
+            self.gathered = blank_rows(self.max_rows, self.world, self.records.scalar_len, self.b_alloc,
+                                       self.problem.device)
 
         def ship(k):
             dist.all_gather_into_tensor(self.gathered[k].view(-1), self.records.buf[k, :self.records.scalar_len])
 
-        if self.fused_exchange and not self.streamed:
+        if self.fused_exchange:
             try:
                 self.run_fused_exchange(n_iterations, self._comm_stream)
                 return self.gathered
@@ -275,17 +249,13 @@ class SimulatedAnnealing:
                 self.fused_exchange = False
                 if self.rank == 0:
                     print(f'prospect_public_b200: fused exchange unavailable ({exc}); using NCCL all-gathers')
-        if self.signalled and not self.streamed:
+        if self.signalled:
             self.run_signalled(n_iterations, ship, self._comm_stream)
             return self.gathered
         compute = torch.cuda.current_stream()
-        iterate = self.optimise_streamed(n_iterations) if self.streamed else None
         for _ in range(n_iterations):
             k = self.iterations_done
-            if iterate is not None:
-                next(iterate)
-            else:
-                self.optimise(1)
+            self.optimise(1)
             ev = torch.cuda.Event()
             ev.record(compute)
             with torch.cuda.stream(self._comm_stream):
@@ -339,11 +309,11 @@ class SimulatedAnnealing:
                                  None, self.lanes)
         self.iterations_done += n
         self.step_counter += n * self.schedule.steps_per_iteration
-        total = 0                                           # chain warps of the whole job
-        for r in range(self.world):
-            n_r = len(shard_grid(self.n_points, self.reps, r, self.world)[0])
-            lanes_r = self.lanes or engine.choose_lanes(self.problem.npad, n_r)
-            total += -(-n_r // (32 // lanes_r)) if n_r else 0
+        # arrivals of the whole job: every rank's count for ITS number of chains, resolved by the library itself
+        # (same geometry rules and environment overrides as the launch)
+        total = sum(engine.exchange_arrivals(self.problem.npad, len(shard_grid(self.n_points, self.reps, r,
+                                                                              self.world)[0]), self.lanes)
+                    for r in range(self.world))
         rows = ex['buf'][k0:k0 + n]
         with torch.cuda.stream(side_stream):
             # every warp bumps its counters in ascending order after its completion fence: the last one suffices

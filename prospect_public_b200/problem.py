@@ -65,6 +65,8 @@ class HostProblem:
     lt_norm: np.ndarray  # [P, npad] f32, Euclidean row norms of the FP32 Lt, rounded up
     g_t: np.ndarray      # [P, npad, npad] f64, g_t[p, j, i] = G[i, j]
     h: np.ndarray        # [P, npad]
+    lt_hi: object        # [P, npad, npad] f32, lt_hi[p, i, j] = TF32 part of Lt[i, j] (npad >= 128 only, else None)
+    lt_lo: object        # [P, npad, npad] f32, the exact remainder Lt - lt_hi
     varying: list        # indices of the varying parameters in x1..xd
     fixed_index: object  # index of the profiled parameter or None
     fixed_values: np.ndarray  # [P] (empty for free runs)
@@ -134,8 +136,13 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
         lt_norm[p, :n] = np.nextafter(rows.astype(np.float32), np.float32(np.inf))
         g_t[p, :n, :n] = g.T
         h[p, :n] = lt.T @ sab[:n] * f[p]
-    return HostProblem(d, n, npad, n_points, saa, sab, sbb, mu, lo_p, hi_p, f, c0, lt_t, lam, lt_norm, g_t, h, varying,
-                       fixed_index, fixed_values)
+    lt_hi = lt_lo = None
+    if npad >= 128:       # operands of the tcgen05 (3xTF32) position GEMM of the wide path: K-major, hi + lo == Lt exactly
+        lt_rows = np.ascontiguousarray(lt_t.transpose(0, 2, 1))              # [P, i, j] = Lt[i][j]
+        lt_hi = (lt_rows.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+        lt_lo = lt_rows - lt_hi
+    return HostProblem(d, n, npad, n_points, saa, sab, sbb, mu, lo_p, hi_p, f, c0, lt_t, lam, lt_norm, g_t, h, lt_hi,
+                       lt_lo, varying, fixed_index, fixed_values)
 
 
 _TORCH_DTYPES = {'<f8': 'float64', '<f4': 'float32', '<i4': 'int32', '<u4': 'int32', '<i8': 'int64'}
@@ -175,11 +182,13 @@ class DeviceProblem:
         if self.device.type != 'cuda':
             raise capi.Pb200Error('prospect_public_b200 runs on CUDA devices only (no CPU fallback)')
         names = ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t', 'lam', 'lt_norm', 'g_t', 'h')
+        if host.lt_hi is not None:
+            names += ('lt_hi', 'lt_lo')
         self.t = upload_packed({name: getattr(host, name) for name in names}, self.device)
         self._storage = self.t.pop('_storage')
         self.c = capi.Problem(host.d, host.n, host.npad, host.n_points,
-                              *(capi.ptr(self.t[k]) for k in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t',
-                                                              'lam', 'lt_norm', 'g_t', 'h')))
+                              *(capi.ptr(self.t.get(k)) for k in ('saa', 'sab', 'mu', 'lo', 'hi', 'f', 'c0', 'lt_t',
+                                                                  'lam', 'lt_norm', 'g_t', 'h', 'lt_hi', 'lt_lo')))
 
     @property
     def n(self):

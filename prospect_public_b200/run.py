@@ -51,7 +51,7 @@ def run(user_inp, quiet=True, stop_after=None):
     t_start = time.perf_counter()
     config_yaml, is_folder = pio.read_user_input(user_inp) if isinstance(user_inp, str) else (user_inp, False)
     rank, world, _ = init_from_env('nccl') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else dist_info()
-    config = Configuration(config_yaml)
+    config = Configuration(config_yaml).synchronise()      # rank 0's output folder and Philox key for every rank
     if is_folder:
         out = resume(config, user_inp)
         out['time_to_result_s'] = time.perf_counter() - t_start
@@ -201,7 +201,7 @@ def dump_snapshot(config, rec, reference_compatible=True, resume_state=None):
       status.txt                           one-paragraph summary."""
     from . import compat
     pio.dump_pickle(config, config.io.dir, 'pb200_config')
-    state = {'format': STATE_FORMAT, 'jobtype': config.run.jobtype, 'seed': config.seed, 'epoch': 0,
+    state = {'format': STATE_FORMAT, 'jobtype': config.run.jobtype, 'seed': config.seed, 'epoch': 0,    # (cached draw)
              'record': {k: getattr(rec, k) for k in ('values', 'reps', 'names', 'best_loglkl', 'accepted', 'best_x',
                                                      'converged', 'initial_loglkl', 'initial_position',
                                                      'initial_covmat', 'temperature', 'step_size')}}

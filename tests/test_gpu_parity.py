@@ -92,8 +92,7 @@ def test_loglkl_batch_matches_reference(d):
     assert np.allclose(ll0.cpu().numpy(), init_ll, rtol=1e-12, atol=0)
 
 
-def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED, lanes=32,
-                   streamed=False):
+def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode=capi.STEP_ADAPTIVE_FIXED, lanes=32):
     """Run B = reps * P chains on the GPU and through the scalar model with the GPU's variates."""
     prob = DeviceProblem(hp, DEV)
     p_count = hp.n_points
@@ -108,14 +107,8 @@ def _replay_anneal(hp, starts, init_ll, reps, sched_args, n_iter, launches, mode
                                  s.get('tol'))
     recs = engine.Records(prob, b, n_iter)
     done = 0
-    zbuf = engine.variates_buffer(prob, b, s['S']) if streamed else None
     for chunk in launches:
-        if streamed:        # one launch per iteration, variates pre-generated by the stand-alone generator kernel
-            for it in range(done, done + chunk):
-                engine.variates_fill(prob, chains, it * s['S'], s['S'], SEED, zbuf)
-                engine.anneal_run_streamed(prob, chains, sched, recs, it * s['S'], zbuf, lanes=lanes)
-        else:
-            engine.anneal_run(prob, chains, sched, recs, chunk, SEED, lanes=lanes)
+        engine.anneal_run(prob, chains, sched, recs, chunk, SEED, lanes=lanes)
         done += chunk
     assert done == n_iter
     torch.cuda.synchronize()
@@ -166,19 +159,6 @@ def test_anneal_bit_exact_vs_model_replay(d, lanes, producer_warps, monkeypatch)
     assert 0.02 < ar.mean() < 0.8
 
 
-@pytest.mark.parametrize('lanes', [32, 16, 8])
-def test_streamed_variates_path_bit_exact(lanes):
-    """pb200_variates_fill + pb200_anneal_run_streamed == the fused kernel == the model (S = 250 is not a multiple of
-    4, so iterations start at every block alignment)."""
-    hp, starts, init_ll, values, k = toy_profile_problem(30, points=[0, 9, 17, 31])
-    a, fa = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 5, [5], lanes=lanes, streamed=True)
-    b, fb = _replay_anneal(hp, starts, init_ll, 3, _toy_sched(), 5, [5], lanes=lanes, streamed=False)
-    for key in a:
-        assert np.array_equal(a[key], b[key]), key
-    for key in fa:
-        assert np.array_equal(fa[key], fb[key]), key
-
-
 def test_anneal_launch_partitioning_is_invisible():
     """1 launch of 4 iterations == 1+2+1 launches (state round-trips through HBM losslessly)."""
     hp, starts, init_ll, values, k = toy_profile_problem(20, points=[0, 4, 9])
@@ -203,18 +183,128 @@ def test_anneal_exponential_secant_and_tolerance_modes():
     assert (fin['status'] == capi.CONVERGED).any()
 
 
-def test_anneal_wide_path_bit_exact_npad64_and_256():
-    """CPL > 1 kernels (n = 40 -> npad 64; n = 255 -> npad 256) on synthetic SPD targets."""
-    for d, reps, s_steps in ((41, 3, 60), (256, 2, 24)):
-        mu, cov = spd_target(d, seed=d)
-        vals = np.array([mu[1] - 0.05, mu[1] + 0.08])
-        prop = conditional_covariance(cov, 1)
-        hp = build_problem(mu, cov, [-2.5] * d, [2.5] * d, 1, vals, np.stack([prop, prop]))
-        starts = np.stack([np.delete(mu, 1) + 0.01, np.delete(mu, 1) - 0.01])
-        init_ll = np.array([hp.loglkl(starts[p], p) for p in range(2)])
+def _spd_profile_problem(d, n_points):
+    mu, cov = spd_target(d, seed=d)
+    sig = float(np.sqrt(cov[1, 1]))
+    vals = mu[1] + sig * np.linspace(-0.8, 0.9, n_points)
+    prop = conditional_covariance(cov, 1)
+    hp = build_problem(mu, cov, [-2.5] * d, [2.5] * d, 1, vals, np.stack([prop] * n_points))
+    starts = np.stack([np.delete(mu, 1) + 0.01 * (1 - 2 * (p % 2)) for p in range(n_points)])
+    init_ll = np.array([hp.loglkl(starts[p], p) for p in range(n_points)])
+    return hp, starts, init_ll
+
+
+@pytest.mark.parametrize('path', ['fused', 'wide_simt', 'wide_simt_producer_warps'])
+def test_anneal_wide_path_bit_exact_npad64_and_256(path, monkeypatch):
+    """CPL > 1 geometries (n = 40 -> npad 64; n = 127 -> npad 128; n = 255 -> npad 256) on synthetic SPD targets, bit for
+    bit against the scalar oracle: the single fused kernel (PB200_WIDE=0) and the per-iteration pipeline of the wide
+    path -- steps kernel, position GEMM on the SIMT pipe (PB200_WIDE_MMA=0), FP64 anchor GEMM -- which keeps every
+    summation order of the fused kernel; its steps kernel with the variates drawn in place and by producer warps."""
+    monkeypatch.setenv('PB200_WIDE', '0' if path == 'fused' else '1')
+    monkeypatch.setenv('PB200_WIDE_MMA', '0')
+    monkeypatch.setenv('PB200_WIDE_WS', '1' if path.endswith('producer_warps') else '0')
+    for d, reps, s_steps in ((41, 3, 60), (128, 3, 40), (256, 2, 24)):
+        hp, starts, init_ll = _spd_profile_problem(d, 2)
         _replay_anneal(hp, starts, init_ll, reps, _toy_sched(S=s_steps, s0=2.4 / np.sqrt(d)), 3, [2, 1])
         if d == 41:
             _replay_anneal(hp, starts, init_ll, reps, _toy_sched(S=s_steps, s0=2.4 / np.sqrt(d)), 3, [3], lanes=16)
+
+
+def test_wide_path_tile_edges_and_schedule_modes_bit_exact(monkeypatch):
+    """Wide pipeline with ragged GEMM tiles (19 repetitions: one full 16-row tile + 3 rows; 3 points), chains that stop
+    at different iterations (chi2_tolerance), and the secant multiplier -- all bit-exact against the oracle."""
+    monkeypatch.setenv('PB200_WIDE_MMA', '0')
+    hp, starts, init_ll = _spd_profile_problem(130, 3)
+    s0 = 2.4 / np.sqrt(130)
+    _replay_anneal(hp, starts, init_ll, 19, _toy_sched(S=30, s0=s0), 3, [1, 2])
+    _, fin = _replay_anneal(hp, starts, init_ll, 5, _toy_sched(S=40, s0=s0, tol=30.0, t0=0.01), 6, [6])
+    assert (fin['status'] == capi.CONVERGED).any() and len(np.unique(fin['iteration'])) > 1
+    _replay_anneal(hp, starts, init_ll, 4, _toy_sched(S=50, s0=s0, interval=(0.24, 0.26)), 5, [5],
+                   mode=capi.STEP_ADAPTIVE_SECANT)
+
+
+def _wide_mma_run(hp, starts, init_ll, reps, s, n_iter):
+    prob = DeviceProblem(hp, DEV)
+    b = reps * hp.n_points
+    point = np.tile(np.arange(hp.n_points), reps).astype(np.int32)
+    x0, cb = np.tile(starts, (reps, 1)), np.tile(init_ll, reps)
+    chains = engine.ChainBatch(prob, x0, point, temperature=s['t0'], step_size=s['s0'], current_best=cb)
+    sched = engine.make_schedule(s['S'], s['tc'], capi.STEP_ADAPTIVE_FIXED, 1.0, s['interval'], s['mult'])
+    recs = engine.Records(prob, b, n_iter)
+    engine.anneal_run(prob, chains, sched, recs, n_iter, SEED)
+    engine.launch_status()
+    out = {k: getattr(recs, k).cpu().numpy() for k in ('best_loglkl', 'last_loglkl', 'temperature', 'step_size',
+                                                        'accepted', 'best_x', 'last_x')}
+    return out, x0, point, cb
+
+
+def _check_against_per_iteration_replay(hp, out, x0, point, cb, s, n_iter, chains_to_check):
+    """Replay iteration k with the scalar oracle FROM THE GPU's own position after iteration k - 1 (GPU variates)."""
+    model = dm.Model(hp, 32)
+    msched = dm.DmSchedule(s['S'], capi.STEP_ADAPTIVE_FIXED, s['tc'], 1.0, s['interval'][0], s['interval'][1],
+                           s['mult'], 0.0)
+    scale = np.abs(np.asarray(hp.lt_t, dtype=np.float64)).sum(axis=1).max()      # bound of the |Lt| row sums
+    for c in chains_to_check:
+        ch = model.new_chain(x0[c], point[c], chain_id=c, temperature=s['t0'], step_size=s['s0'],
+                             current_best=cb[c])
+        for k in range(n_iter):
+            z, e = _gpu_variates(c, k * s['S'], s['S'], hp.n)
+            mo = model.anneal_chain(ch, msched, 1, SEED, z, e)
+            assert out['accepted'][k, c] == mo['accepted'][0], (c, k)
+            assert out['temperature'][k, c] == mo['temperature'][0] and out['step_size'][k, c] == mo['step_size'][0]
+            for key in ('best_x', 'last_x'):
+                err = np.abs(out[key][k, c] - mo[key][0]).max()
+                assert err <= 3e-6 * scale * (1.0 + np.abs(mo[key][0]).max()), (key, c, k, err)
+            assert out['best_loglkl'][k, c] == model.exact_eval(out['best_x'][k, c, :hp.n], point[c])
+            assert out['last_loglkl'][k, c] == model.exact_eval(out['last_x'][k, c, :hp.n], point[c])
+            xs = np.ctypeslib.as_array(ch.x, (hp.npad,))          # continue the oracle from where the GPU actually is
+            xs[:] = out['last_x'][k, c]
+            ch.current_best = out['best_loglkl'][k, c]
+
+
+@pytest.mark.parametrize('d,reps', [(256, 5), (128, 130)])
+def test_wide_path_tensor_core_positions(d, reps, monkeypatch):
+    """The tcgen05 (3xTF32, TMA-fed) position GEMM of the wide path.  Tensor-core accumulation order is not
+    specified, so positions cannot be bit-compared; everything else can: iteration k is replayed by the scalar oracle
+    FROM THE GPU's own position after iteration k - 1 with the GPU's variates --
+      * accept counts, temperatures and step sizes are bit-identical (the FP64 anchors at the GPU's positions are),
+      * the written chi^2 values are the exact FP64 values at the written positions,
+      * the GPU's positions agree with the oracle's FP32-SIMT ones to 3e-6 of the displacement scale (3xTF32 keeps
+        ~21 bits per product; tolerance stated here).
+    130 repetitions: a full 128-row MMA tile plus a 2-row one; 5 repetitions: a TMA box smaller than the tile."""
+    monkeypatch.setenv('PB200_WIDE_MMA', '1')
+    hp, starts, init_ll = _spd_profile_problem(d, 2)
+    s = _toy_sched(S=32, s0=2.4 / np.sqrt(d))
+    out, x0, point, cb = _wide_mma_run(hp, starts, init_ll, reps, s, 3)
+    b = reps * hp.n_points
+    _check_against_per_iteration_replay(hp, out, x0, point, cb, s, 3, list(range(0, b, max(1, b // 24))) + [b - 1])
+
+
+def test_k4_shape_256d_8_points_x_128_repetitions():
+    """BASELINE.json configs[3] at its per-GPU shape: 256-D synthetic SPD Gaussian profile, 8 points x 128
+    repetitions = 1024 chains, 20 iterations x 250 steps through the default path (wide pipeline, tensor-core
+    position GEMM).  32 chains spread over all points are replayed iteration by iteration against the scalar oracle;
+    for ALL chains the recorded chi^2 is the exact FP64 value at the recorded position (pb200_loglkl_batch), the
+    prior box is respected, and every point's best repetition closes in on the analytic profile minimum."""
+    d, n_points, reps, n_iter = 256, 8, 128, 20
+    hp, starts, init_ll = _spd_profile_problem(d, n_points)
+    s = _toy_sched(S=250, s0=0.15)
+    out, x0, point, cb = _wide_mma_run(hp, starts, init_ll, reps, s, n_iter)
+    b = reps * n_points
+    assert (out['accepted'] >= 0).all()
+    rng = np.random.default_rng(0)
+    _check_against_per_iteration_replay(hp, out, x0, point, cb, s, n_iter, sorted(rng.choice(b, 32, replace=False)))
+    prob = DeviceProblem(hp, DEV)
+    for k in (0, n_iter - 1):
+        ll, outside = engine.loglkl_batch(prob, torch.as_tensor(out['best_x'][k], device=DEV),
+                                          torch.as_tensor(point, device=DEV))
+        assert np.array_equal(ll.cpu().numpy(), out['best_loglkl'][k]) and not outside.cpu().numpy().any()
+    mu, cov = spd_target(d, seed=d)
+    best = out['best_loglkl'].min(axis=0).reshape(reps, n_points).min(axis=0)
+    t_final = s['t0'] * s['tc'] ** (n_iter - 1)
+    for p in range(n_points):
+        exact = closed_form.profile_minimum(mu, cov, 1, hp.fixed_values[p])[0]
+        assert 0.0 <= best[p] - exact <= 1.5 * hp.n * t_final, (p, best[p] - exact)      # a sample at T sits ~ n/2 T above the minimum
 
 
 @pytest.mark.parametrize('lanes', [32, 8])
