@@ -57,7 +57,11 @@ struct Geometry {
     static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
     // four-steps-per-reduction (block_step) pays where few lanes per chain make the butterfly short: measured on B200 it
     // wins for 8 lanes per chain (+14 % at 4096 chains) and loses for 16 / 32 (more shuffle instructions, issue-bound)
-    static constexpr bool kBlockMode = (LPC == 8);
+    // ... and for the wide geometries (32 lanes, >= 4 coordinates per lane: npad >= 128), which are latency-bound at
+    // every batch size that fits the register file (one chain per warp, <= 8 warps per SM): there the four dependent
+    // reduce -> compare -> branch chains of a block cost ~4 x 300 cycles of pure latency (ncu, 256-D) and the
+    // reduce-scatter form needs 32 shuffles per block instead of 20-40
+    static constexpr bool kBlockMode = (LPC == 8) || (LPC == 32 && CPL >= 4);
     // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
     static constexpr int kMinCtas =
         (NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8))) * 4 / kWarpsPerCta;
@@ -280,6 +284,25 @@ __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf
             a2[i] = __fadd_rn(b1 ? a4[i + 2] : a4[i], __shfl_xor_sync(kFull, b1 ? a4[i] : a4[i + 2], 1));
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(kFull, a2[j & 1], j >> 1, 8);
+    } else if constexpr (LPC == 32) {
+        // the same reduce-scatter over five levels (8 + 4 + 2 + 1 exchanges, then one full exchange): sum j ends up in
+        // lanes 2 j and 2 j + 1, one broadcast per sum -- 32 SHFL + 16 FADD, each sum formed by the butterfly's own
+        // additions (own + partner at distances 16, 8, 4, 2, 1)
+        const bool b16 = (gl & 16) != 0, b8 = (gl & 8) != 0, b4 = (gl & 4) != 0, b2 = (gl & 2) != 0;
+        float a8[8], a4[4], a2[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            a8[i] = __fadd_rn(b16 ? v[i + 8] : v[i], __shfl_xor_sync(kFull, b16 ? v[i] : v[i + 8], 16));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            a4[i] = __fadd_rn(b8 ? a8[i + 4] : a8[i], __shfl_xor_sync(kFull, b8 ? a8[i] : a8[i + 4], 8));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            a2[i] = __fadd_rn(b4 ? a4[i + 2] : a4[i], __shfl_xor_sync(kFull, b4 ? a4[i] : a4[i + 2], 4));
+        float a1 = __fadd_rn(b2 ? a2[1] : a2[0], __shfl_xor_sync(kFull, b2 ? a2[0] : a2[1], 2));
+        a1 = __fadd_rn(a1, __shfl_xor_sync(kFull, a1, 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(kFull, a1, 2 * j);
     } else {
 #pragma unroll
         for (int m = LPC / 2; m >= 1; m >>= 1) {
@@ -1020,14 +1043,15 @@ static int anneal_launch_wide(const pb200_problem& prob, const pb200_chains& cha
     size_t off = 0;
     auto carve = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) / 256 * 256; return o; };
     const size_t o_base = carve(2 * b * NPAD * 8), o_hi = carve(2 * b * NPAD * 4), o_lo = carve(2 * b * NPAD * 4),
-                 o_bx = carve(b * NPAD * 8), o_v = carve(3 * b * NPAD * 8), o_nacc = carve(b * 4), o_ran = carve(b * 4);
+                 o_bx = carve(b * NPAD * 8), o_q = carve(2 * b * NPAD * 8), o_v = carve(3 * b * NPAD * 8),
+                 o_nacc = carve(b * 4), o_ran = carve(b * 4);
     char* mem = nullptr;
     if (check_cuda(cudaMallocAsync((void**)&mem, off, st), "cudaMallocAsync (wide workspace)")) return 1;
     WideWs ws{(double*)(mem + o_base), (float*)(mem + o_hi), (float*)(mem + o_lo), (double*)(mem + o_bx),
-              (double*)(mem + o_v), (int32_t*)(mem + o_nacc), (int32_t*)(mem + o_ran)};
+              (double*)(mem + o_q), (double*)(mem + o_v), (int32_t*)(mem + o_nacc), (int32_t*)(mem + o_ran)};
     const int n_rt = (reps + kWideTileRows - 1) / kWideTileRows, n_at = (reps + kAnchorTileRows - 1) / kAnchorTileRows;
     const int steps_blocks = (chains.n_chains + kWarpsPerCta - 1) / kWarpsPerCta;
-    const size_t anchor_smem = sizeof(double) * (kAnchorTileRows * NPAD + 2 * kWideKChunk * kAnchorTileCols);
+    const size_t anchor_smem = sizeof(double) * kAnchorStages * (kAnchorTileRows * kWideKChunk + kWideKChunk * kAnchorTileCols);
     static bool attr_set[2] = {false, false};
     if (!attr_set[NPAD == 256]) {
         if (check_cuda(cudaFuncSetAttribute(wide_anchor_kernel<NPAD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1049,11 +1073,12 @@ static int anneal_launch_wide(const pb200_problem& prob, const pb200_chains& cha
     };
     mark();
     wide_check_layout_kernel<<<1, 256, 0, st>>>(chains, P);
+    wide_residual_kernel<NPAD><<<148 * 2, 256, 0, st>>>(prob, chains, ws);
     wide_anchor_kernel<NPAD><<<2 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x3);
     mark();
     // producer warps pay while the chain warps alone leave the schedulers short of instruction streams (measured:
     // profiles/README.md); PB200_WIDE_WS=0 / 1 forces the choice
-    bool ws_steps = chains.n_chains <= 148 * 16 / 2;
+    bool ws_steps = chains.n_chains <= 148 * 4;          // up to one pair per scheduler
     if (const char* env = std::getenv("PB200_WIDE_WS")) ws_steps = env[0] != '0';
     const int ws_blocks = (chains.n_chains + kWideWsPairs - 1) / kWideWsPairs;
     for (int it = 0; it < n_iter; ++it) {

@@ -73,7 +73,8 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 
 template <int NPAD>
 __global__ void __launch_bounds__(128, 1)
-wide_materialise_mma_kernel(pb200_chains ch, WideWs ws, int n_points, int reps, int box_rows,
+wide_materialise_mma_kernel(pb200_chains ch, WideWs ws, const double* __restrict__ mu, int n_points, int reps,
+                            int box_rows,
                             const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                             const __grid_constant__ CUtensorMap map_lt_hi,
                             const __grid_constant__ CUtensorMap map_lt_lo) {
@@ -158,17 +159,28 @@ wide_materialise_mma_kernel(pb200_chains ch, WideWs ws, int n_points, int reps, 
             : "r"(addr));
     }
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    const int rep = mt * kMmaTileM + 32 * warp + lane;
-    if (ok && rep < reps) {
-        const size_t b = (size_t)ch.n_chains;
-        const size_t row = ((size_t)rep * n_points + pt) * NPAD + (size_t)nt * kMmaTileN;
-        const double2* __restrict__ base = reinterpret_cast<const double2*>(ws.base + (size_t)which * b * NPAD + row);
-        double2* __restrict__ out = reinterpret_cast<double2*>((which == 0 ? ch.x : ws.bx) + row);
+    // accumulator rows -> shared memory (the pipeline stages are free now), then row-contiguous, coalesced global
+    // access: a warp handles one row per pass, lane l the columns 2 l, 2 l + 1 of the 64-column tile
+    float* tile = reinterpret_cast<float*>(umma_smem_raw + (smem0 - smem_addr(umma_smem_raw)));      // [128][65]
+    {
+        float* mine = tile + (32 * warp + lane) * (kMmaTileN + 1);
 #pragma unroll
-        for (int c = 0; c < kMmaTileN / 2; ++c) {
-            const double2 bv = base[c];
-            out[c] = make_double2(__dadd_rn(bv.x, (double)__uint_as_float(acc[2 * c])),
-                                  __dadd_rn(bv.y, (double)__uint_as_float(acc[2 * c + 1])));
+        for (int c = 0; c < kMmaTileN; ++c) mine[c] = __uint_as_float(acc[c]);
+    }
+    __syncthreads();
+    if (ok) {
+        const size_t b = (size_t)ch.n_chains;
+        const double2 m = __ldg(reinterpret_cast<const double2*>(mu + (size_t)nt * kMmaTileN) + lane);
+        for (int r = warp; r < kMmaTileM; r += 4) {
+            const int rep = mt * kMmaTileM + r;
+            if (rep >= reps) break;
+            const size_t row = ((size_t)rep * n_points + pt) * NPAD + (size_t)nt * kMmaTileN;
+            const double2 bv = reinterpret_cast<const double2*>(ws.base + (size_t)which * b * NPAD + row)[lane];
+            const float* a = tile + r * (kMmaTileN + 1) + 2 * lane;
+            const double2 x = make_double2(__dadd_rn(bv.x, (double)a[0]), __dadd_rn(bv.y, (double)a[1]));
+            reinterpret_cast<double2*>((which == 0 ? ch.x : ws.bx) + row)[lane] = x;
+            reinterpret_cast<double2*>(ws.q + (size_t)which * b * NPAD + row)[lane] =
+                make_double2(x.x - m.x, x.y - m.y);            // the anchor GEMM's A operand
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -249,7 +261,8 @@ static int wide_mma_launch(const pb200_problem& prob, const pb200_chains& chains
                            const WideMma& mma, cudaStream_t st) {
     const int n_mt = (reps + kMmaTileM - 1) / kMmaTileM;
     const int grid = 2 * prob.n_points * n_mt * (NPAD / kMmaTileN);
-    wide_materialise_mma_kernel<NPAD><<<grid, 128, kMmaSmemBytes, st>>>(chains, ws, prob.n_points, reps, mma.box_rows,
+    wide_materialise_mma_kernel<NPAD><<<grid, 128, kMmaSmemBytes, st>>>(chains, ws, prob.mu, prob.n_points, reps,
+                                                                        mma.box_rows,
                                                                         mma.w_hi, mma.w_lo, mma.lt_hi, mma.lt_lo);
     return check_cuda(cudaGetLastError(), "wide_materialise_mma_kernel launch");
 }

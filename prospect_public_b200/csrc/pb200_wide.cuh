@@ -38,6 +38,8 @@ struct WideWs {
     float*   w_hi;      // [2][B][npad]  whitened displacement from it, split w = hi + lo (hi: 10 mantissa bits = TF32)
     float*   w_lo;      // [2][B][npad]
     double*  bx;        // [B][npad]     materialised best position
+    double*  q;         // [2][B][npad]  residuals X - mu (0) and BX - mu (1): the A operand of the anchor GEMM, written by
+                        //               the position GEMM's epilogue
     double*  v;         // [3][B][npad]  anchor GEMM outputs: 0: (X - mu) S_aa, 1: (X - mu) G_pt^T, 2: (BX - mu) S_aa
     int32_t* nacc;      // [B]           accepted proposals of the iteration just run
     int32_t* ran;       // [B]           1: the chain ran that iteration
@@ -82,9 +84,13 @@ __device__ __forceinline__ void produce_variates_wide(int n, uint32_t steps, uin
             const int coord = lane + 32 * r;
             uint32_t w[4];
             float z0, z1, z2, z3;
+#ifdef PB200_DBG_NO_RNG          // timing experiments only: how long does the consumer take on its own?
+            w[0] = w[1] = w[2] = w[3] = blk + coord; z0 = z1 = z2 = z3 = 1e-3f * (float)coord;
+#else
             philox4x32_10(blk, coord == n ? kAcceptSlot : (uint32_t)coord, chain_id, 0u, k0, k1, w);
             box_muller(w[0], w[1], z0, z1);
             box_muller(w[2], w[3], z2, z3);
+#endif
             if (coord >= n) { z0 = z1 = z2 = z3 = 0.0f; }
             const uint32_t dst = base + (uint32_t)(r * 128 + lane) * 4u;      // [r][k][lane]: conflict-free both ways
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(dst), "f"(z0) : "memory");
@@ -140,8 +146,25 @@ __device__ __forceinline__ void wide_run_steps_ring(const pb200_problem& p, int 
             }
         }
         const uint32_t base = rg.data + slot * (uint32_t)ring_slot_bytes<CPL>();
+        bool todo = live, block_done = false;
+#ifdef PB200_DBG_NO_STEPS        // timing experiments only: how long does the producer take on its own?
+        block_done = true;
+#endif
+        if (off == 0u && cnt == 4u && !rg.dead && !block_done) {       // a whole Philox block: four steps per reduction (block_step)
+            float z[CPL][4], e[4];
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(z[r][k]) : "r"(base + (uint32_t)((r * 4 + k) * 32 + gl) * 4u));
+            }
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(e[0]), "=f"(e[1]), "=f"(e[2]), "=f"(e[3]) : "r"(base + (uint32_t)(CPL * 32) * 16u));
+            todo = block_step<32, CPL>(gl, live, Tf, sf, z, e, c);
+            block_done = !__any_sync(kFull, todo);      // else: replay the block step by step (exact box test needed)
+        }
 #pragma unroll 1
-        for (uint32_t k = off; k < off + cnt; ++k) {
+        for (uint32_t k = off; k < off + cnt && !block_done; ++k) {
             float zk[CPL], ek = 0.0f;
 #pragma unroll
             for (int r = 0; r < CPL; ++r) zk[r] = 0.0f;
@@ -151,7 +174,7 @@ __device__ __forceinline__ void wide_run_steps_ring(const pb200_problem& p, int 
                     asm volatile("ld.shared.f32 %0, [%1];" : "=f"(zk[r]) : "r"(base + (uint32_t)((r * 4 + k) * 32 + gl) * 4u));
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(ek) : "r"(base + (uint32_t)(CPL * 32) * 16u + 4u * k));
             }
-            one_step<32, CPL, PB200_RECORD_NONE, false>(p, pt, lt_pt, gl, 0, live, t_begin + i + (k - off), Tf, sf, zk, ek, c,
+            one_step<32, CPL, PB200_RECORD_NONE, false>(p, pt, lt_pt, gl, 0, todo, t_begin + i + (k - off), Tf, sf, zk, ek, c,
                                                         ws, rc);
         }
         if (!rg.dead) {
@@ -428,7 +451,16 @@ wide_materialise_simt_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int re
                                    (double)__fadd_rn(__fadd_rn(a[r][0], a[r][1]), __fadd_rn(a[r][2], a[r][3])));
         if (which == 0) ch.x[c] = x;
         else ws.bx[c] = x;
+        ws.q[half + c] = x - __ldg(p.mu + i);
     }
+}
+
+// Residuals of the start positions (the anchor GEMM before the first iteration of a call).
+template <int NPAD>
+__global__ void wide_residual_kernel(pb200_problem p, pb200_chains ch, WideWs ws) {
+    const size_t total = (size_t)ch.n_chains * NPAD;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x)
+        ws.q[idx] = ch.x[idx] - __ldg(p.mu + (idx % NPAD));
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -436,21 +468,24 @@ wide_materialise_simt_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int re
 //   0: V  = (X  - mu) S_aa        -> chi^2 at x            (the epilogue runs in the steps kernel: chi2_of)
 //   1: G  = (X  - mu) G_pt^T      -> whitened gradient gt = g + h_pt
 //   2: Vb = (BX - mu) S_aa        -> chi^2 of the bestfit
-// One CTA = kAnchorTileRows repetitions of one point x kAnchorTileCols outputs, 256 threads with 4 x 4 register tiles;
-// 96 KB of shared memory, so two CTAs share an SM (4 warps per scheduler hide the shared-memory latency) and the 192
-// tiles of the 8-point x 128-repetition batch cover all 148 SMs.  The matrix streams through shared memory in chunks
-// of kWideKChunk k-rows (cp.async, double-buffered); every output has ONE accumulator advanced in ascending k with one
-// FMA per term -- the order of exact_eval(), hence the same bits.  tcgen05 has no FP64 type: this stays on the DFMA pipe.
+// One CTA = kAnchorTileRows (32) repetitions of one point x kAnchorTileCols (64) outputs, 256 threads with 4 x 2 register
+// tiles; both operands -- the residual rows Q and the matrix -- stream through shared memory in chunks of kWideKChunk
+// k-values (cp.async, kAnchorStages-deep ring, one barrier per chunk).  Every output has ONE accumulator advanced in
+// ascending k with one FMA per term -- the order of exact_eval(), hence the same bits.  tcgen05 has no FP64 type and
+// DMMA's accumulation order is not specified, so this stays on the DFMA pipe, which is what bounds it: measured
+// ~1 warp-DFMA per clock and SM in steady state (= 32 lanes: 18.6 TFLOP/s per B200); the small tiles (384 for the
+// 8-point x 128-repetition batch, up to 4 resident per SM) are for load balance over the 148 SMs.
 // ----------------------------------------------------------------------------------------------
-constexpr int kAnchorTileCols = 128;
+constexpr int kAnchorTileCols = 64;
+constexpr int kAnchorStages = 4;
 
 template <int NPAD>
 __global__ void __launch_bounds__(256, 2)
 wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cls_mask) {
-    constexpr int TM = kAnchorTileRows, TN = kAnchorTileCols, KC = kWideKChunk, NCT = NPAD / TN;
+    constexpr int TM = kAnchorTileRows, TN = kAnchorTileCols, KC = kWideKChunk, NCT = NPAD / TN, ST = kAnchorStages;
+    constexpr int kStageDoubles = TM * KC + KC * TN;       // residual chunk [TM][KC] + matrix chunk [KC][TN]
     extern __shared__ __align__(16) unsigned char wide_smem[];
-    double* qs = reinterpret_cast<double*>(wide_smem);                   // [TM][NPAD]
-    double* bs = qs + TM * NPAD;                                          // [2][KC][TN]
+    double* stages = reinterpret_cast<double*>(wide_smem);
     const int n_rt = (reps + TM - 1) / TM, P = p.n_points;
     int bid = blockIdx.x;
     const int ct = bid % NCT; bid /= NCT;
@@ -462,52 +497,49 @@ wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cl
         if ((cls_mask >> cls) & 1) { if (seen == cls_idx) break; ++seen; }
     const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5, n = p.n;      // warp ty: rows 4 ty .. 4 ty + 3
     const size_t b = (size_t)ch.n_chains;
-    const double* __restrict__ xs = cls == 2 ? ws.bx : ch.x;
+    const double* __restrict__ qsrc = ws.q + (cls == 2 ? b * NPAD : 0);
     const double* __restrict__ mat = (cls == 1 ? p.g_t + (size_t)pt * NPAD * NPAD : p.saa) + (size_t)ct * TN;
-
-    for (int idx = tid; idx < TM * NPAD; idx += 256) {
-        const int r = idx / NPAD, c = idx % NPAD, rep = rt * TM + r;
-        qs[idx] = rep < reps ? xs[((size_t)rep * P + pt) * NPAD + c] - __ldg(p.mu + c) : 0.0;
-    }
-    auto load_chunk = [&](int k_begin, int buf) {       // KC rows x TN doubles, 16-byte pieces
-        const uint32_t dst = smem_addr(bs + (size_t)buf * KC * TN);
-        for (int piece = tid; piece < KC * TN / 2; piece += 256) {
-            const int kr = piece / (TN / 2), cc = piece % (TN / 2);
-            const double* src = mat + (size_t)(k_begin + kr) * NPAD + 2 * cc;
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * piece), "l"(src) : "memory");
+    // this thread's piece of a residual chunk: row tid / 8 of the tile, doubles 2 (tid % 8) .. + 1 of the chunk
+    const int q_row = tid >> 3, q_rep = min(rt * TM + q_row, reps - 1);      // rows past the batch re-read the last one
+    const double* q_piece = qsrc + ((size_t)q_rep * P + pt) * NPAD + 2 * (tid & 7);
+    auto load_chunk = [&](int ck) {
+        if (ck * KC < n) {
+            double* st = stages + (size_t)(ck % ST) * kStageDoubles;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr(st) + 16u * tid), "l"(q_piece + ck * KC)
+                         : "memory");
+            const uint32_t dst = smem_addr(st + TM * KC);
+            for (int piece = tid; piece < KC * TN / 2; piece += 256) {
+                const int kr = piece / (TN / 2), cc = piece % (TN / 2);
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * piece),
+                             "l"(mat + (size_t)(ck * KC + kr) * NPAD + 2 * cc) : "memory");
+            }
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");       // (an empty group keeps the group count uniform)
     };
-    double acc[4][4];
+    double acc[4][2];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = acc[r][2] = acc[r][3] = 0.0;
+    for (int r = 0; r < 4; ++r) acc[r][0] = acc[r][1] = 0.0;
     const int n_chunks = (n + KC - 1) / KC;        // rows >= n of the padded matrices are never used
-    load_chunk(0, 0);
+#pragma unroll
+    for (int ck = 0; ck < ST - 1; ++ck) load_chunk(ck);
     for (int ck = 0; ck < n_chunks; ++ck) {
-        if (ck + 1 < n_chunks) {
-            load_chunk((ck + 1) * KC, (ck + 1) & 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        }
-        __syncthreads();
-        const double* bb = bs + (size_t)(ck & 1) * KC * TN + 2 * tx;
-        const double* qq = qs + (size_t)(4 * ty) * NPAD + ck * KC;
+        asm volatile("cp.async.wait_group %0;" ::"n"(ST - 2) : "memory");     // chunk ck has landed (this thread's pieces)
+        __syncthreads();                                                        // ... everyone's; chunk ck - 1 is consumed
+        load_chunk(ck + ST - 1);                                                // refills the buffer of chunk ck - 1
+        const double* st = stages + (size_t)(ck % ST) * kStageDoubles;
+        const double* qq = st + (size_t)(4 * ty) * KC;
+        const double* bb = st + TM * KC + 2 * tx;
         const int kk_end = min(KC, n - ck * KC);
 #pragma unroll 4
         for (int kk = 0; kk < kk_end; ++kk) {
             const double2 b01 = *reinterpret_cast<const double2*>(bb + kk * TN);
-            const double2 b23 = *reinterpret_cast<const double2*>(bb + kk * TN + TN / 2);
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
-                const double q = qq[r * NPAD + kk];
+                const double q = qq[r * KC + kk];
                 acc[r][0] = fma(b01.x, q, acc[r][0]);
                 acc[r][1] = fma(b01.y, q, acc[r][1]);
-                acc[r][2] = fma(b23.x, q, acc[r][2]);
-                acc[r][3] = fma(b23.y, q, acc[r][3]);
             }
         }
-        __syncthreads();
     }
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -515,7 +547,6 @@ wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cl
         if (rep >= reps) continue;
         double* dst = ws.v + ((size_t)cls * b + (size_t)rep * P + pt) * NPAD + (size_t)ct * TN + 2 * tx;
         *reinterpret_cast<double2*>(dst) = make_double2(acc[r][0], acc[r][1]);
-        *reinterpret_cast<double2*>(dst + TN / 2) = make_double2(acc[r][2], acc[r][3]);
     }
 }
 
