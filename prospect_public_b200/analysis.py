@@ -92,11 +92,15 @@ def compute_profile(rec: RunRecord, srt):
 
 
 def _best_positions(rec, srt):
-    """[P, n] position of the best repetition's best iteration."""
+    """[P, n] position of the best repetition's best iteration (from the per-chain best positions when the record
+    carries them -- rec.best_positions [B, n] -- else from the dense per-iteration positions)."""
     p_idx = np.arange(rec.n_points)
     rep = srt['best_rep']
-    it = srt['chain_iter'][rep, p_idx]
     chain = rep * rec.n_points + p_idx
+    per_chain = getattr(rec, 'best_positions', None)
+    if per_chain is not None:
+        return per_chain[chain]
+    it = srt['chain_iter'][rep, p_idx]
     return rec.best_x[np.maximum(it, 0), chain]
 
 
@@ -171,15 +175,20 @@ def write_intervals(profile, intervals, out_dir, parameter):
     return path
 
 
-def analyse_profile(rec: RunRecord, out_dir, parameter, confidence_levels, reduced=None):
-    """The whole AnalyseProfileTask.run minus the plots.  Returns (sorted bestfits, profile, intervals)."""
+def analyse_profile(rec: RunRecord, out_dir, parameter, confidence_levels, reduced=None, stamp=None):
+    """The whole AnalyseProfileTask.run minus the plots.  Returns (sorted bestfits, profile, intervals).  The profile
+    and its intervals are written first (`stamp['t_results_written']` is taken when profile/<p>.txt is on disk), the
+    per-repetition status table -- one formatted line per chain -- after them."""
+    import time
     os.makedirs(out_dir, exist_ok=True)
     srt = sort_bestfits(rec, reduced)
     profile = compute_profile(rec, srt)
     write_profile_results(rec, srt, profile, out_dir, parameter)
-    write_profile_status(rec, srt, out_dir, parameter)
+    if stamp is not None:
+        stamp['t_results_written'] = time.perf_counter()
     intervals = compute_intervals_neyman(profile, confidence_levels)
     write_intervals(profile, intervals, out_dir, parameter)
+    write_profile_status(rec, srt, out_dir, parameter)
     return srt, profile, intervals
 
 
@@ -196,6 +205,7 @@ def analyse_global_optimisation(rec: RunRecord, out_dir):
                 f.write(f'{rep} \t --- no optimisations finished ---\n')
                 continue
             f.write(f'{rep} \t {cb[rep, 0]:.10e} \t {rec.initial_loglkl[0]:.10e} \t ')
-            pos = rec.best_x[ci[rep, 0], rep]
+            per_chain = getattr(rec, 'best_positions', None)
+            pos = per_chain[rep] if per_chain is not None else rec.best_x[ci[rep, 0], rep]
             f.write(' \t '.join(str(np.round(v, 10)) for v in pos) + '\n')
     return {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}

@@ -286,6 +286,23 @@ def profile_reduce(records: Records, n_iter, n_points, reps, stream=None):
     return out
 
 
+def chain_minimum(records: Records, n_iter, stream=None):
+    """Per chain: first minimum over the iterations that ran -> dict(chain_best [B], chain_iter [B]) device tensors
+    (the first pass of pb200_profile_reduce, with every chain as its own 'point')."""
+    dev = records.best_loglkl.device
+    b = records.n_chains
+    out = {'chain_best': torch.empty(b, dtype=torch.float64, device=dev),
+           'chain_iter': torch.empty(b, dtype=torch.int32, device=dev)}
+    scratch = {'pb': torch.empty(b, dtype=torch.float64, device=dev), 'pr': torch.empty(b, dtype=torch.int32, device=dev),
+               'pa': torch.empty(b, dtype=torch.float64, device=dev)}
+    _count(2)
+    capi.check(capi.lib().pb200_profile_reduce(
+        capi.ptr(records.best_loglkl), capi.ptr(records.accepted), int(records.stride), 2 * int(records.stride),
+        int(n_iter), b, b, 1, capi.ptr(out['chain_best']), capi.ptr(out['chain_iter']), capi.ptr(scratch['pb']),
+        capi.ptr(scratch['pr']), capi.ptr(scratch['pa']), _stream_ptr(stream)))
+    return out
+
+
 def weighted_moments(x, n, weights=None, stream=None):
     """x: [N, ld] float64 device tensor (first n columns used), weights [N] int32 or None.
     -> (sum_w, sum_wx [n], sum_wxx [n, n]) device tensors."""

@@ -20,14 +20,16 @@ import numpy as np
 from .mcmc import Chain
 
 
-def load_mcmc(mcmc_path, collapse=True):
+def load_mcmc(mcmc_path, collapse=True, indices=None):
     """Read an unpacked MCMC `<root>_<i>.txt` + `<root>.paramnames` (MontePython / cobaya / GetDist layout:
     multiplicity, -log L, parameters) without GetDist: every chain file in index order, no burn-in removal,
-    which is what reproduces the reference's own fixtures.  -> Chain or list[Chain]."""
+    which is what reproduces the reference's own fixtures.  -> Chain or list[Chain].
+    `indices`: only these chain indices (a rank of a sharded, resumed mcmc job reads its own chains)."""
     files = []
+    wanted = None if indices is None else set(int(i) for i in indices)
     for f in glob.glob(mcmc_path + '_*.txt'):
         m = re.search(r'_(\d+)\.txt$', f)
-        if m:
+        if m and (wanted is None or int(m.group(1)) in wanted):
             files.append((int(m.group(1)), f))
     if not files:
         raise FileNotFoundError(f"No chain files '{mcmc_path}_<i>.txt' found.")
@@ -66,11 +68,27 @@ def get_fraction_of_points_in_bin(chain, param_val, param_name, fraction):
 
 
 def _weighted_cov_gpu(x, mults, device):
+    return _weighted_covs_gpu([x], [mults], device)[0]
+
+
+def _weighted_covs_gpu(xs, mults, device):
+    """Multiplicity-weighted (bias=True) covariances of several row sets -- one per profile value -- with ONE
+    upload, one moments launch per set and ONE read-back (the launches are queued back to back; a synchronising
+    read per profile value was the bulk of the initialisation time for 32-256 values)."""
     import torch
     from . import engine
-    xt = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float64), device=device)
-    w = torch.as_tensor(np.asarray(mults).astype(np.int32), device=device)
-    return engine.covariance_from_moments(*engine.weighted_moments(xt, x.shape[1], w)).cpu().numpy()
+    if not xs:
+        return []
+    n = xs[0].shape[1]
+    sizes = [len(x) for x in xs]
+    xt = torch.as_tensor(np.ascontiguousarray(np.concatenate(xs, axis=0), dtype=np.float64), device=device)
+    wt = torch.as_tensor(np.concatenate([np.asarray(m) for m in mults]).astype(np.int32), device=device)
+    out = torch.empty((len(xs), n, n), dtype=torch.float64, device=device)
+    lo = 0
+    for i, size in enumerate(sizes):
+        out[i] = engine.covariance_from_moments(*engine.weighted_moments(xt[lo:lo + size], n, wt[lo:lo + size]))
+        lo += size
+    return list(out.cpu().numpy())
 
 
 class StartingPoints:
@@ -84,8 +102,12 @@ class StartingPoints:
         self.indices = indices                # list of int arrays or None
 
 
-def initialise_optimiser(config, kernel):
-    """`kernel` must not have its profile parameter fixed yet.  Returns (StartingPoints, values [P])."""
+def initialise_optimiser(config, kernel, shard=None):
+    """`kernel` must not have its profile parameter fixed yet.  Returns (StartingPoints, values [P]).
+
+    `shard` = (rank, world) of a torch.distributed job: the binning / covariance work of the profile values is split
+    over the ranks (contiguous blocks of values) and the per-value results are all-gathered, instead of every rank
+    repeating all of it (256 values on 8 GPUs)."""
     prof = config.profile
     is_profile = config.run.jobtype == 'profile'
     all_names = list(kernel.param['varying'].keys())
@@ -99,13 +121,15 @@ def initialise_optimiser(config, kernel):
     else:
         pidx, values, names = None, np.zeros(0), all_names
     n_pts = max(1, len(values))
+    rank, world = shard if shard is not None else (0, 1)
+    mine = np.array_split(np.arange(n_pts), world)[rank] if world > 1 else np.arange(n_pts)
 
     def drop(cov):
         if pidx is None:
             return cov
         return np.delete(np.delete(cov, [pidx], 0), [pidx], 1)
 
-    positions, covmats, indices = [], [], None
+    positions, covmats, indices = {}, {}, None
     if prof.start_from_position is not None and prof.start_from_covmat is not None:
         pos = np.asarray(kernel.read_initial_position(prof.start_from_position), dtype=np.float64)
         cov = np.asarray(kernel.read_covmat(prof.start_from_covmat), dtype=np.float64)
@@ -113,58 +137,74 @@ def initialise_optimiser(config, kernel):
             pos = np.delete(pos, pidx)
         if cov.shape[0] == len(all_names):
             cov = drop(cov)
-        positions = [pos] * n_pts
-        covmats = [cov] * n_pts
+        mine = np.arange(n_pts)                    # nothing to compute: every rank fills all values itself
+        positions = {p: pos for p in mine}
+        covmats = {p: cov for p in mine}
     elif prof.start_from_profile is not None:
         from .io import load_profile
         chain = None
         if prof.start_from_mcmc is not None:
             chain = _reduced_chain(load_mcmc(prof.start_from_mcmc), kernel)
         start_profile = load_profile(prof.start_from_profile, direct_txt=True)
-        for p in range(n_pts):
+        xs, ms = [], []
+        for p in mine:
             if chain is not None:
                 idx = (get_fraction_of_points_in_bin(chain, values[p], prof.parameter, prof.start_bin_fraction)
                        if is_profile else np.arange(len(chain.mults)))
-                x = np.stack([np.take(chain.positions[nm], idx) for nm in all_names], axis=1)
-                covmats.append(drop(_weighted_cov_gpu(x, np.take(chain.mults, idx), kernel.device)))
+                xs.append(np.stack([np.take(chain.positions[nm], idx) for nm in all_names], axis=1))
+                ms.append(np.take(chain.mults, idx))
             else:
-                covmats.append(drop(np.asarray(kernel.read_covmat(prof.start_from_covmat), dtype=np.float64)))
+                covmats[p] = drop(np.asarray(kernel.read_covmat(prof.start_from_covmat), dtype=np.float64))
             if is_profile:
                 closest = int(np.argmin(np.abs(start_profile[prof.parameter] - values[p])))
             else:
                 closest = int(np.argmin(start_profile['-loglkl']))
-            positions.append(np.array([start_profile[nm][closest] for nm in names]))
+            positions[p] = np.array([start_profile[nm][closest] for nm in names])
+        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, kernel.device)):
+            covmats[p] = drop(cov)
     elif prof.start_from_mcmc is not None:
         chain = _reduced_chain(load_mcmc(prof.start_from_mcmc), kernel)
-        indices = []
-        for p in range(n_pts):
+        indices, xs, ms = {}, [], []
+        for p in mine:
             if is_profile:
                 idx = get_fraction_of_points_in_bin(chain, values[p], prof.parameter, prof.start_bin_fraction)
             else:
                 idx = np.arange(len(chain.mults))
-            indices.append(idx)
+            indices[p] = idx
             x = np.stack([np.take(chain.positions[nm], idx) for nm in all_names], axis=1)
-            covmats.append(drop(_weighted_cov_gpu(x, np.take(chain.mults, idx), kernel.device)))
-            best = int(np.argmin(np.take(chain.loglkls, idx)))
-            start = x[best]
-            positions.append(np.delete(start, pidx) if pidx is not None else start)
+            xs.append(x)
+            ms.append(np.take(chain.mults, idx))
+            start = x[int(np.argmin(np.take(chain.loglkls, idx)))]
+            positions[p] = np.delete(start, pidx) if pidx is not None else start
+        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, kernel.device)):
+            covmats[p] = drop(cov)
     else:
         raise ValueError('InitialiseOptimiserTask could not construct an initial position and/or covariance '
                          'matrix. Make sure to supply either "start_from_mcmc" or "start_from_position" and '
                          '"start_from_covmat" in the profile section of the input.')
-    positions = np.array(positions, dtype=np.float64)
-    covmats = np.array(covmats, dtype=np.float64)
-    # initial_loglkl = kernel.loglkl(start) with the profile parameter fixed (initialise_optimiser_task.py:124)
+    if world > 1 and len(mine) < n_pts:           # every rank gets every value's start point / covariance
+        import torch.distributed as dist
+        parts = [None] * world
+        dist.all_gather_object(parts, (positions, covmats, indices))
+        for pos_r, cov_r, idx_r in parts:
+            positions.update(pos_r)
+            covmats.update(cov_r)
+            if indices is not None and idx_r is not None:
+                indices.update(idx_r)
+    positions = np.array([positions[p] for p in range(n_pts)], dtype=np.float64)
+    covmats = np.array([covmats[p] for p in range(n_pts)], dtype=np.float64)
+    indices = None if indices is None else [indices[p] for p in range(n_pts)]
+    # initial_loglkl = kernel.loglkl(start) with the profile parameter fixed (initialise_optimiser_task.py:124): one
+    # batched likelihood launch over all values on a likelihood-only device image (no per-point proposal factors --
+    # those are only built for the points a rank actually anneals)
     if is_profile:
         kernel.set_fixed_parameters({prof.parameter: float(values[0])})
-        prob = kernel.device_problem(fixed_values=values, proposal_covmats=covmats)
+        prob = kernel.device_problem(fixed_values=values, likelihood_only=True)
         init_ll = kernel.loglkl_batch(positions, points=np.arange(n_pts), problem=prob)
     else:
-        prob = kernel.device_problem(proposal_covmats=covmats)
+        prob = kernel.device_problem(likelihood_only=True)
         init_ll = kernel.loglkl_batch(positions, problem=prob)
-    sp = StartingPoints(names, positions, covmats, init_ll, indices)
-    sp.problem = prob
-    return sp, values
+    return StartingPoints(names, positions, covmats, init_ll, indices), values
 
 
 def _reduced_chain(chain, kernel):

@@ -145,6 +145,35 @@ class MetropolisHastings:
         self._names = names
         self.accepted = np.zeros(b, dtype=np.int64)
         self.steps = 0
+        if prior is not None and mcmc_args.get('preload', False):
+            self._preload(prior)
+
+    def _preload(self, prior):
+        """Continue chains in place (`prospect <folder>` for jobtype mcmc, tasks/mcmc_task.py:71-81): the rows of the
+        earlier segments go back into the device sample buffers, so the recording cursor picks up at each chain's open
+        last row and everything downstream (chain files, pooled covariance, R-1) sees ONE chain per index, exactly as
+        if the run had never been interrupted."""
+        import torch
+        from . import engine
+        if self.record != 'accepted':
+            raise ValueError("chains can only be continued in place with record='accepted'")
+        n, names = self.problem.n, self._names
+        rows = [len(ch.mults) for ch in prior]
+        cap = max(rows)
+        x = np.zeros((self.n_chains, cap, self.problem.npad))
+        ll = np.zeros((self.n_chains, cap))
+        mult = np.zeros((self.n_chains, cap), dtype=np.int32)
+        for c, ch in enumerate(prior):
+            x[c, :rows[c], :n] = np.stack([np.asarray(ch.positions[nm], dtype=np.float64) for nm in names], axis=1)
+            ll[c, :rows[c]] = ch.loglkls
+            mult[c, :rows[c]] = np.asarray(ch.mults, dtype=np.int64)
+        smp = engine.Samples(self.problem, self.n_chains, cap, capi.RECORD_ACCEPTED, self.thin)
+        dev = self.problem.device
+        smp.x.copy_(torch.as_tensor(x, device=dev))
+        smp.loglkl.copy_(torch.as_tensor(ll, device=dev))
+        smp.mult.copy_(torch.as_tensor(mult, device=dev))
+        smp.count.copy_(torch.as_tensor(np.asarray(rows, dtype=np.int32), device=dev))
+        self._samples, self._used, self._prior = smp, 0, None
 
     def _ensure_samples(self, n_steps):
         from . import engine

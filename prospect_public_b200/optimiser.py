@@ -359,6 +359,72 @@ class SimulatedAnnealing:
                 out['best_x'][:, ids] = gx[rank, :, :len(ids), :n]
         return out
 
+    def global_scalars(self):
+        """global_records() without the positions: best_loglkl / accepted / step_size / temperature [K, B] in global chain
+        order.  Several GPUs: decoded from the per-iteration exchange (`gathered`), no further communication."""
+        from . import engine
+        names = ('best_loglkl', 'accepted', 'step_size', 'temperature')
+        if self.world == 1:
+            return {name: getattr(self.records, name).cpu().numpy() for name in names}
+        g = self.gathered.cpu().numpy()
+        b_glob, k = self.n_points * self.reps, self.max_rows
+        out = {'best_loglkl': np.full((k, b_glob), np.inf), 'accepted': np.full((k, b_glob), -1, dtype=np.int32),
+               'step_size': np.zeros((k, b_glob)), 'temperature': np.zeros((k, b_glob))}
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            ids = global_chain_index(pt, rep, self.n_points)
+            dec = engine.Records.decode(g[:, rank], len(ids), self.b_alloc, self.problem.npad, False)
+            for name in names:
+                out[name][:, ids] = dec[name]
+        return out
+
+    def global_best_positions(self):
+        """Per chain of the job (global order): the position of its best iteration [B, n] -- what the result files
+        need, picked on the device (first-minimum iteration from the running-bestfit reduction, one gather) and
+        exchanged as B x n doubles, instead of moving every iteration's positions ([K, B, n]) to rank 0 first."""
+        import torch
+        from . import engine
+        n, b_loc = self.problem.n, self.n_chains
+        if b_loc:
+            red = engine.chain_minimum(self.records, self.max_rows)
+            it = red['chain_iter'].clamp(min=0).long()
+            local = self.records.best_x[it, torch.arange(b_loc, device=it.device)][:, :n].contiguous()
+        else:
+            local = torch.zeros((0, n), dtype=torch.float64, device=self.problem.device)
+        if self.world == 1:
+            return local.cpu().numpy()
+        import torch.distributed as dist
+        pad = torch.zeros((self.b_alloc, n), dtype=torch.float64, device=self.problem.device)
+        pad[:b_loc] = local
+        allx = torch.empty((self.world, self.b_alloc, n), dtype=torch.float64, device=self.problem.device)
+        dist.all_gather_into_tensor(allx.view(-1), pad.view(-1))
+        allx = allx.cpu().numpy()
+        out = np.zeros((self.n_points * self.reps, n))
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            out[global_chain_index(pt, rep, self.n_points)] = allx[rank, :len(pt)]
+        return out
+
+    def global_positions(self):
+        """best_x [K, B, n] of every iteration in global chain order (snapshots; one all-gather for N > 1)."""
+        n, k = self.problem.n, self.max_rows
+        r = self.records
+        if self.world == 1:
+            return r.best_x[:, :, :n].cpu().numpy()
+        import torch
+        import torch.distributed as dist
+        o, width = r.offsets['best_x'], r.n_alloc * r.npad
+        local = r.buf[:, o:o + width].contiguous()
+        allx = torch.empty((self.world,) + tuple(local.shape), dtype=torch.float64, device=local.device)
+        dist.all_gather_into_tensor(allx.view(-1), local.view(-1))
+        gx = allx.cpu().numpy().reshape(self.world, k, r.n_alloc, r.npad)
+        out = np.zeros((k, self.n_points * self.reps, n))
+        for rank in range(self.world):
+            pt, rep = shard_grid(self.n_points, self.reps, rank, self.world)
+            ids = global_chain_index(pt, rep, self.n_points)
+            out[:, ids] = gx[rank, :, :len(ids), :n]
+        return out
+
     def global_status(self):
         """status of every chain of the job in global order (one small all-gather)."""
         import torch

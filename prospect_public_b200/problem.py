@@ -112,18 +112,22 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
                 lo_p[k] = lo[i]
             if hi is not None and hi[i] is not None:
                 hi_p[k] = hi[i]
-    proposal_covmats = np.asarray(proposal_covmats, dtype=np.float64)
-    if proposal_covmats.ndim == 2:
-        proposal_covmats = proposal_covmats[None]
-    if proposal_covmats.shape != (n_points, n, n):
-        raise ValueError(f'proposal covmats must have shape {(n_points, n, n)}, got {proposal_covmats.shape}')
-    lt_t = np.zeros((n_points, npad, npad), dtype=np.float32)
-    lam = np.zeros((n_points, npad), dtype=np.float32)
-    lt_norm = np.zeros((n_points, npad), dtype=np.float32)
-    g_t = np.zeros((n_points, npad, npad))
-    h = np.zeros((n_points, npad))
+    if proposal_covmats is None:         # likelihood-only image (pb200_loglkl_batch): one zero proposal slot
+        slots = 1
+    else:
+        proposal_covmats = np.asarray(proposal_covmats, dtype=np.float64)
+        if proposal_covmats.ndim == 2:
+            proposal_covmats = proposal_covmats[None]
+        if proposal_covmats.shape != (n_points, n, n):
+            raise ValueError(f'proposal covmats must have shape {(n_points, n, n)}, got {proposal_covmats.shape}')
+        slots = n_points
+    lt_t = np.zeros((slots, npad, npad), dtype=np.float32)
+    lam = np.zeros((slots, npad), dtype=np.float32)
+    lt_norm = np.zeros((slots, npad), dtype=np.float32)
+    g_t = np.zeros((slots, npad, npad))
+    h = np.zeros((slots, npad))
     s_aa = saa[:n, :n]
-    for p in range(n_points):
+    for p in range(n_points if proposal_covmats is not None else 0):
         fac = proposal_factor(proposal_covmats[p])
         m = fac.T @ s_aa @ fac
         w, q = np.linalg.eigh(0.5 * (m + m.T))
@@ -137,7 +141,7 @@ def build_problem(means, covmat, lo, hi, fixed_index, fixed_values, proposal_cov
         g_t[p, :n, :n] = g.T
         h[p, :n] = lt.T @ sab[:n] * f[p]
     lt_hi = lt_lo = None
-    if npad >= 128:       # operands of the tcgen05 (3xTF32) position GEMM of the wide path: K-major, hi + lo == Lt exactly
+    if npad >= 128 and proposal_covmats is not None:       # operands of the tcgen05 (3xTF32) position GEMM of the wide path: K-major, hi + lo == Lt exactly
         lt_rows = np.ascontiguousarray(lt_t.transpose(0, 2, 1))              # [P, i, j] = Lt[i][j]
         lt_hi = (lt_rows.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
         lt_lo = lt_rows - lt_hi

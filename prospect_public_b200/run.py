@@ -44,16 +44,17 @@ def _barrier():
         dist.barrier()
 
 
-def run(user_inp, quiet=True, stop_after=None):
+def run(user_inp, quiet=True, stop_after=None, max_rounds=64):
     """Run a job (a .yaml file or dict) or resume one (the folder of an earlier run, prospect/io.py:15-24).  Returns
     a dict with the records, the analysis products and timings.  `stop_after` ends an annealing job after that
-    many iterations with a complete snapshot, as an interrupted run would leave it."""
+    many iterations (an mcmc job after that many rounds) with a complete snapshot, as an interrupted run would leave
+    it; `max_rounds` bounds the rounds of an mcmc job that does not reach convergence_Rm1."""
     t_start = time.perf_counter()
     config_yaml, is_folder = pio.read_user_input(user_inp) if isinstance(user_inp, str) else (user_inp, False)
     rank, world, _ = init_from_env('nccl') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else dist_info()
     config = Configuration(config_yaml).synchronise()      # rank 0's output folder and Philox key for every rank
     if is_folder:
-        out = resume(config, user_inp)
+        out = resume(config, user_inp, max_rounds=max_rounds)
         out['time_to_result_s'] = time.perf_counter() - t_start
         out['config'] = config
         return out
@@ -61,7 +62,7 @@ def run(user_inp, quiet=True, stop_after=None):
         pio.prepare_run(config)
     _barrier()
     if config.run.jobtype == 'mcmc':
-        out = run_mcmc(config)
+        out = run_mcmc(config, max_rounds=max_rounds, stop_after_rounds=stop_after)
     else:
         out = run_annealing(config, stop_after=stop_after)
     out['time_to_result_s'] = time.perf_counter() - t_start          # incl. the snapshot pickles
@@ -88,7 +89,7 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
     if rank != 0:
         kernel = initialise_kernel(config.kernel, out_dir, rank, device)
     if starts is None:
-        starts, values = initialise_optimiser(config, kernel)
+        starts, values = initialise_optimiser(config, kernel, shard=(rank, world))
     elif config.run.jobtype == 'profile':
         kernel.set_fixed_parameters({prof.parameter: float(values[0])})
     n_iter = int(prof.max_iterations)
@@ -120,37 +121,51 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
         sa.run_schedule(to_run)
     torch.cuda.synchronize()
     loop_s = time.perf_counter() - t0
-    g = sa.global_records()
-    best_ll, acc, step, temperature, best_x = g['best_loglkl'], g['accepted'], g['step_size'], g['temperature'], g['best_x']
-    chain_steps = int((acc >= 0).sum()) * int(prof.steps_per_iteration)    # global (records are gathered)
+    result = {'loop_seconds': loop_s, 'optimiser': sa, 'values': values, 'seed': sa.seed,
+              'iterations_done': sa.iterations_done}
+
+    # --- the result files first: they need the per-iteration scalars (already exchanged at the iteration boundaries)
+    # and ONE position per chain (its best iteration's), not every iteration's positions
+    scal = sa.global_scalars()
+    best_ll, acc, step, temperature = scal['best_loglkl'], scal['accepted'], scal['step_size'], scal['temperature']
+    chain_steps = int((acc >= 0).sum()) * int(prof.steps_per_iteration)    # global; only what THIS call ran
     if old_rec is not None:                     # rows of the iterations that ran before the interruption
         k_old = min(done, old_rec.best_loglkl.shape[0], n_iter)
         best_ll[:k_old], acc[:k_old] = old_rec.best_loglkl[:k_old], old_rec.accepted[:k_old]
         step[:k_old], temperature[:k_old] = old_rec.step_size[:k_old], old_rec.temperature[:k_old]
-        if best_x is not None and old_rec.best_x is not None:
-            best_x[:k_old] = old_rec.best_x[:k_old]
     status = sa.global_status()
-    rec = analysis.RunRecord(values, reps, starts.names, best_ll, acc, best_x, status == capi.CONVERGED,
+    rec = analysis.RunRecord(values, reps, starts.names, best_ll, acc, None, status == capi.CONVERGED,
                              starts.initial_loglkl, starts.positions, starts.covmats, temperature, step)
-    result = {'record': rec, 'chain_steps': chain_steps, 'loop_seconds': loop_s, 'optimiser': sa,
-              'status': status, 'values': values, 'seed': sa.seed, 'iterations_done': sa.iterations_done}
+    fast = old_rec is None and keep_positions          # (a resumed run needs the old rows' positions: dense path)
+    if fast:
+        rec.best_positions = sa.global_best_positions()
+        if rank == 0 and write:
+            result.update(write_result_files(config, rec, sa if world == 1 else None))
+    # --- then everything a snapshot / the caller may want: every iteration's positions, the per-chain state
+    best_x = sa.global_positions() if keep_positions else None
+    if old_rec is not None and best_x is not None and old_rec.best_x is not None:
+        best_x[:k_old] = old_rec.best_x[:k_old]
+    rec.best_x = best_x
+    result.update({'record': rec, 'chain_steps': chain_steps, 'status': status})
     chain_state = sa.global_chain_state()
     if rank == 0 and write:
-        result.update(write_outputs(config, rec, sa if world == 1 and old_rec is None else None,
-                                    resume_state={'chain_state': chain_state, 'iterations_done': sa.iterations_done,
-                                                  'seed': sa.seed}))
-    _barrier()
+        if not fast:
+            result.update(write_result_files(config, rec, None))
+        if config.io.write:
+            dump_snapshot(config, rec, resume_state={'chain_state': chain_state, 'iterations_done': sa.iterations_done,
+                                                     'seed': sa.seed})
     return result
 
 
-def resume(config, prospect_folder):
+def resume(config, prospect_folder, max_rounds=64):
     """`prospect <folder>` (prospect/io.py:15-24, prospect/communication.py:30-36): continue the chains of an
-    interrupted annealing run from the state in its snapshot -- position, temperature, step size and step-size
+    interrupted run: an mcmc job from its chain files (run_mcmc), an annealing run from the state in its snapshot -- position, temperature, step size and step-size
     history, Philox step counter -- until every chain has run `profile.max_iterations` iterations (read from the
     folder's log.yaml, so raising it there extends a finished run).  The continued run is step for step the run
     that was never interrupted: same random streams, same records, same output files."""
     if config.run.jobtype == 'mcmc':
-        raise NotImplementedError('Resuming jobtype mcmc: start a new job with start_from_position / covmat instead.')
+        config.io.dir = config.config_dict['io']['dir'] = prospect_folder
+        return run_mcmc(config, max_rounds=max_rounds, resume_folder=prospect_folder)
     config.io.dir = config.config_dict['io']['dir'] = prospect_folder
     _, rec_old = load_record(prospect_folder)
     state = pio.load_pickle(prospect_folder, 'pb200_state')
@@ -162,8 +177,9 @@ def resume(config, prospect_folder):
                          resume_from=(state, rec_old))
 
 
-def write_outputs(config, rec, sa=None, resume_state=None):
-    """Analysis + result files + snapshot of a finished (or re-annealed) run; returns the analysis products."""
+def write_result_files(config, rec, sa=None):
+    """Analysis + result files of a finished (or re-annealed) run: profile/<p>.txt, <p>_intervals.txt, <p>_status.txt
+    or global_optimisation/results.txt.  Returns the analysis products and `t_results_written`."""
     prof = config.profile
     result = {}
     if config.run.jobtype == 'profile':
@@ -173,7 +189,7 @@ def write_outputs(config, rec, sa=None, resume_state=None):
             if sa is not None:
                 reduced = {k: v.cpu().numpy() for k, v in sa.reduce_over_iterations().items()}
             srt, profile, intervals = analysis.analyse_profile(rec, sub, prof.parameter, prof.confidence_levels,
-                                                               reduced)
+                                                               reduced, stamp=result)
         else:
             srt = analysis.sort_bestfits(rec)
             profile = analysis.compute_profile(rec, srt)
@@ -186,7 +202,13 @@ def write_outputs(config, rec, sa=None, resume_state=None):
         else:
             cb, ci = rec.per_chain_best()
             result['bestfits'] = {'chain_best': cb, 'chain_iter': ci, 'best_rep': int(np.argmin(cb[:, 0]))}
-    result['t_results_written'] = time.perf_counter()      # profile/<p>.txt (or results.txt) is on disk here
+    result.setdefault('t_results_written', time.perf_counter())      # profile/<p>.txt (or results.txt) is on disk here
+    return result
+
+
+def write_outputs(config, rec, sa=None, resume_state=None):
+    """Result files + snapshot (re-annealing, tests)."""
+    result = write_result_files(config, rec, sa)
     if config.io.write:
         dump_snapshot(config, rec, resume_state=resume_state)
     return result
@@ -335,10 +357,14 @@ def reanneal(yaml_schedule, prospect_folder):
 
 
 def gelman_rubin(means, covs, weights):
-    """R-1 from per-chain weighted means [C, n], covariances [C, n, n] and total weights [C]: largest
-    eigenvalue of W^-1/2 B W^-1/2 (between-chain covariance of the means in units of the mean within-chain
-    covariance).  PARITY UNPINNED: the reference delegates this to getdist, which is not installed here
-    (SURVEY.md O4)."""
+    """R-1 from per-chain weighted means [C, n], covariances [C, n, n] and total weights [C], following the
+    definition of getdist's MCSamples.getGelmanRubin (what prospect/analysis.py:27-32 calls): chains weighted by
+    their total weight, between-chain covariance of the means x C / (C - 1), largest eigenvalue of
+    L^-1 B L^-T with L the Cholesky factor of the weight-averaged within-chain covariance (getdist rescales both
+    matrices by the diagonal of the latter first, which leaves the eigenvalues unchanged).  PARITY UNPINNED: getdist
+    is not installed here and the reference ships no value of this statistic (SURVEY.md O4);
+    tests/test_host_logic.py pins the implementation to a hand-computed case and an independent transcription of
+    the definition."""
     w = np.asarray(weights, dtype=np.float64)
     w = w / w.sum()
     mean_all = (w[:, None] * means).sum(0)
@@ -375,7 +401,7 @@ def shard_chains(n_chains, rank, world):
     return n_chains * rank // world, n_chains * (rank + 1) // world
 
 
-def run_mcmc(config, max_rounds=64):
+def run_mcmc(config, max_rounds=64, resume_folder=None, stop_after_rounds=None):
     """jobtype mcmc (tasks/mcmc_task.py:10-81): N_chains chains advance `steps_per_iteration` per round on the
     GPU(s); after each round the chains are unpacked to <dir>/mcmc/<jobname>_<i>.txt (+ .paramnames / .ranges) and
     R-1 decides whether to continue.
@@ -383,7 +409,13 @@ def run_mcmc(config, max_rounds=64):
     Several GPUs (one process each): rank r owns the contiguous chain block shard_chains(); Philox streams are keyed
     by the GLOBAL chain index, so every chain is the same whatever the number of GPUs.  The only exchange is one
     all-reduce (sum, FP64) per round of the 2 + n + 2 n^2 sufficient statistics of the pooled covariance and R-1
-    (SURVEY.md section 8e); every rank writes its own chain files."""
+    (SURVEY.md section 8e); every rank writes its own chain files.
+
+    `resume_folder` (`prospect <folder>`, prospect/io.py:15-24 + tasks/mcmc_task.py:71-81): continue the chains of an
+    earlier run from its chain files -- last position (written with 18 digits: exact), step counter (= sum of the
+    multiplicities - 1) and the Philox key kept in pb200_mcmc_state.pkl -- until R-1 < convergence_Rm1.  The
+    continued run is step for step the run that was never interrupted.  `stop_after_rounds` ends a run early, as an
+    interruption would (tests)."""
     import torch
     from . import engine
     from .mcmc import initialise_mcmc
@@ -401,15 +433,31 @@ def run_mcmc(config, max_rounds=64):
     if rank != 0:
         kernel = initialise_kernel(config.kernel, out_dir, rank, device)
     lo, hi = shard_chains(int(mc.N_chains), rank, world)
-    sampler = initialise_mcmc(mc, kernel, seed=config.seed, n_chains=hi - lo,
-                              chain_ids=np.arange(lo, hi, dtype=np.uint32)) if hi > lo else None
     n = len(kernel.varying_param_names)
-    rounds, conv, mean, cov = 0, np.inf, None, None
+    seed, rounds, extra = config.seed, 0, {}
+    if resume_folder is not None:
+        from .initialise import load_mcmc
+        state = pio.load_pickle(resume_folder, 'pb200_mcmc_state')
+        seed, rounds = int(state['seed']), int(state['rounds'])
+        if int(state['n_chains']) != int(mc.N_chains) or int(state['steps_per_iteration']) != int(mc.steps_per_iteration):
+            raise ValueError('N_chains / steps_per_iteration of the resumed job differ from the interrupted one.')
+        if hi > lo:
+            prior = load_mcmc(os.path.join(resume_folder, 'mcmc', config.io.jobname), collapse=False,
+                              indices=range(lo, hi))
+            done = {int(round(np.sum(ch.mults))) - 1 for ch in prior}
+            if done != {rounds * int(mc.steps_per_iteration)}:
+                raise ValueError(f'chain files hold {sorted(done)} steps, the snapshot says '
+                                 f'{rounds * int(mc.steps_per_iteration)}')
+            extra = dict(chains=prior, preload=True, steps_done=rounds * int(mc.steps_per_iteration))
+    sampler = initialise_mcmc(mc, kernel, seed=seed, n_chains=hi - lo,
+                              chain_ids=np.arange(lo, hi, dtype=np.uint32), **extra) if hi > lo else None
+    conv, mean, cov = np.inf, None, None
     if world > 1:
         import torch.distributed as dist
         _barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
+    rounds_here = 0
     while rounds < max_rounds:
         if sampler is not None:
             sampler.run_steps(mc.steps_per_iteration)
@@ -417,6 +465,7 @@ def run_mcmc(config, max_rounds=64):
         else:
             stats = torch.zeros(2 + n + 2 * n * n, dtype=torch.float64, device=device)
         rounds += 1
+        rounds_here += 1
         if world > 1:
             if dist.get_backend() != 'nccl':
                 stats = stats.cpu()
@@ -425,13 +474,18 @@ def run_mcmc(config, max_rounds=64):
         if config.io.write and mc.unpack_at_dump and sampler is not None:
             pio.unpack_mcmc(kernel.param['varying'], os.path.join(config.io.dir, 'mcmc'), config.io.jobname,
                             *sampler.chains, first_index=lo, write_names=rank == 0)
-        if conv < mc.convergence_Rm1:
+        if config.io.write and rank == 0:
+            pio.dump_pickle({'format': STATE_FORMAT, 'jobtype': 'mcmc', 'seed': int(seed), 'rounds': rounds,
+                             'n_chains': int(mc.N_chains), 'steps_per_iteration': int(mc.steps_per_iteration),
+                             'Rm1': float(conv)}, config.io.dir, 'pb200_mcmc_state')
+            pio.dump_pickle(config, config.io.dir, 'pb200_config')
+        if conv < mc.convergence_Rm1 or (stop_after_rounds is not None and rounds_here >= stop_after_rounds):
             break
     torch.cuda.synchronize()
     _barrier()
     return {'sampler': sampler, 'rounds': rounds, 'Rm1': conv, 'mean': mean, 'covmat': cov,
             'loop_seconds': time.perf_counter() - t0, 'chain_range': (lo, hi),
-            'chain_steps': rounds * mc.steps_per_iteration * int(mc.N_chains)}
+            'chain_steps': rounds_here * mc.steps_per_iteration * int(mc.N_chains)}
 
 
 def run_from_shell(argv=None):

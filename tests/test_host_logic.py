@@ -424,3 +424,98 @@ def test_reference_reads_our_snapshot(toy20, tmp_path):
     # and our own reader understands PROSPECT's config.pkl without PROSPECT being importable
     from prospect_public_b200.io import load_profile
     assert len(load_profile(str(out))['x2']) == 10
+
+
+def test_parabola_vertex_bit_identical_to_the_reference():
+    """400 random triples through the reference's own AnalyseProfileTask.get_bestfit_parabola (frozen as exact hex
+    floats by tests/golden/make_golden_r2.py): x* and f* must agree in every bit, because both are printed at full
+    precision into the profile files."""
+    import json
+    with open(os.path.join(GOLDEN, 'ref_parabola_cases.json')) as f:
+        cases = json.load(f)
+    assert len(cases) == 400
+    for c in cases:
+        x, fv = [float.fromhex(v) for v in c['x']], [float.fromhex(v) for v in c['f']]
+        xb, fb = analysis.bestfit_parabola(x, fv)
+        assert xb == float.fromhex(c['x_best']) and fb == float.fromhex(c['f_best'])
+
+
+def test_shard_grid_covers_every_chain_once_even_with_more_ranks_than_repetitions():
+    """P >= world: contiguous point blocks; P < world: repetitions split -- with fewer repetitions than ranks some
+    ranks own nothing (global_optimisation with 3 repetitions on 8 GPUs), and that must still be a partition."""
+    from prospect_public_b200.distributed import global_chain_index, shard_grid
+    for n_points, reps, world in ((32, 256, 8), (5, 6, 3), (1, 3, 8), (3, 2, 8), (7, 1, 2)):
+        seen = np.zeros(n_points * reps, dtype=int)
+        sizes = []
+        for rank in range(world):
+            pt, rep = shard_grid(n_points, reps, rank, world)
+            sizes.append(len(pt))
+            if len(pt):
+                assert np.all(np.diff(global_chain_index(pt, rep, n_points)) > 0)      # rep-major, ascending
+                n_local = len(np.unique(pt))
+                assert np.array_equal(np.searchsorted(np.unique(pt), pt), np.arange(len(pt)) % n_local)  # c % P_local
+            seen[global_chain_index(pt, rep, n_points)] += 1
+        assert np.all(seen == 1)
+        assert (min(sizes) == 0) == (n_points < world and reps < world)
+
+
+def test_gathered_rows_start_as_did_not_run():
+    """Rows of the multi-GPU `gathered` tensor that were never shipped must decode as "chain did not run"
+    (loglkl = inf, accepted = -1), like a single-GPU Records: a partial run (stop_after) decodes every row."""
+    from prospect_public_b200.engine import Records
+    from prospect_public_b200.optimiser import blank_rows
+    rows, world, b = 4, 3, 5
+    scalar_len = 4 * b + (b + 1) // 2
+    g = blank_rows(rows, world, scalar_len, b, 'cpu').numpy()
+    dec = Records.decode(g[:, 1], b, b, 32, False)
+    assert np.all(np.isinf(dec['best_loglkl'])) and np.all(np.isinf(dec['last_loglkl']))
+    assert np.all(dec['accepted'] == -1)
+
+
+def test_gelman_rubin_follows_the_published_getdist_definition():
+    """R-1 as getdist's MCSamples.getGelmanRubin defines it (what prospect/analysis.py:27-32 calls): "the maximum
+    var(mean) / mean(var) of orthogonalized parameters, c.f. Brooks and Gelman 1997" -- per-chain weighted means and
+    (biased) covariances, chains weighted by their total weight, the between-chain covariance of the means scaled by
+    C / (C - 1), both matrices normalised by the diagonal of the mean covariance, largest eigenvalue of
+    L^-1 B L^-T with L the Cholesky factor of the mean covariance.  getdist is not installed here and the reference
+    ships no value for this statistic, so parity stays UNPINNED; this test pins the implementation to
+    a hand-computed case and to an independent transcription of the definition above, for both code paths
+    (per-chain moments and the all-reduced sufficient statistics)."""
+    from prospect_public_b200.run import convergence_from_statistics, gelman_rubin
+    # two 1-D chains {0, 2} and {4, 6}: means 1 and 5, variances 1, overall mean 3;
+    # between = ((1-3)^2 + (5-3)^2) / 2 * 2/(2-1) = 8, within = 1  ->  R-1 = 8
+    means = np.array([[1.0], [5.0]])
+    covs = np.array([[[1.0]], [[1.0]]])
+    assert abs(gelman_rubin(means, covs, np.array([2.0, 2.0])) - 8.0) < 1e-12
+    rng = np.random.default_rng(3)
+    n, chains = 3, []
+    for c in range(5):
+        rows = int(rng.integers(40, 90))
+        a = rng.normal(size=(n, n))
+        chains.append((rng.integers(1, 6, rows).astype(float),
+                       rng.normal(size=(rows, n)) @ a + rng.normal(scale=0.3, size=n)))
+
+    def independent(chains):                       # the definition, step by step
+        norms = np.array([w.sum() for w, _ in chains])
+        m_c = np.array([(w[:, None] * x).sum(0) / w.sum() for w, x in chains])
+        cov_c = np.array([np.cov(x, rowvar=False, bias=True, aweights=w) for w, x in chains])
+        mean = (norms[:, None] * m_c).sum(0) / norms.sum()
+        meancov = (norms[:, None, None] * cov_c).sum(0) / norms.sum()
+        dm = m_c - mean
+        meanscov = (norms[:, None, None] * dm[:, :, None] * dm[:, None, :]).sum(0) / norms.sum()
+        meanscov *= len(chains) / (len(chains) - 1)
+        d = np.diag(1.0 / np.sqrt(np.diag(meancov)))
+        meancov, meanscov = d @ meancov @ d, d @ meanscov @ d
+        li = np.linalg.inv(np.linalg.cholesky(meancov))
+        return float(np.linalg.eigvalsh(li @ meanscov @ li.T).max()), m_c, cov_c, norms
+
+    expect, m_c, cov_c, norms = independent(chains)
+    assert abs(gelman_rubin(m_c, cov_c, norms) - expect) < 1e-10 * expect
+    # the sufficient statistics the GPU reduces and the ranks all-reduce: [sw, swx, swxx, sum_c swx_c swx_c^T / sw_c, C]
+    sw = norms.sum()
+    swx = sum((w[:, None] * x).sum(0) for w, x in chains)
+    swxx = sum((w[:, None, None] * x[:, :, None] * x[:, None, :]).sum(0) for w, x in chains)
+    syy = sum(np.outer((w[:, None] * x).sum(0), (w[:, None] * x).sum(0)) / w.sum() for w, x in chains)
+    stats = np.concatenate([[sw], swx, swxx.reshape(-1), syy.reshape(-1), [len(chains)]])
+    got, mean, cov = convergence_from_statistics(stats, n)
+    assert abs(got - expect) < 1e-9 * expect
