@@ -246,12 +246,11 @@ class Configuration:
         """Make rank 0's resolved output folder and Philox key those of every rank of a torch.distributed job (every
         rank builds its own Configuration: a late rank could otherwise de-duplicate io.dir differently, and ranks
         without a numpy_random_seed would each draw their own key).  No-op for a single process."""
-        try:
-            import torch.distributed as dist
-        except ImportError:
+        from . import distributed
+        rank, world, active = distributed.dist_info()
+        if not active or world == 1:
             return self
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
-            return self
+        import torch.distributed as dist
         payload = [{'dir': self.io.dir, 'seed': self.seed}]
         dist.broadcast_object_list(payload, src=0)
         self.io.dir = self.config_dict['io']['dir'] = payload[0]['dir']

@@ -346,6 +346,57 @@ __device__ __forceinline__ void materialise(const float* __restrict__ lt_pt, int
         x_out[r] = __dadd_rn(base[r], (double)__fadd_rn(__fadd_rn(a[r][0], a[r][1]), __fadd_rn(a[r][2], a[r][3])));
 }
 
+// The same for warps that hold SEVERAL chains (LPC < 32) of a 32-coordinate problem, when only some of them need their
+// position: in `materialise` every lane group runs the full n x n mat-vec whenever ANY group of the warp asks for it
+// (the call sits under warp-uniform control), so one accepting chain makes its three neighbours do -- and wait for --
+// 128 L1 loads + FMAs per lane.  Here the warp works through the asking chains one at a time, all 32 lanes on ONE
+// chain: lane i forms output coordinate i (32 coalesced loads + FMAs, the same four interleaved partial sums over j,
+// hence the same bits) and the sums travel back to the owning lanes by shuffle.  ncu (65 536 chains, wide step): the
+// per-group form was 62 % of the MH kernel's stall samples and held the LSU pipe at 65 %.
+//   want: this group's position is needed (others get x_out = base);  stage rows of the warp's groups are contiguous.
+template <int LPC, int CPL>
+__device__ __forceinline__ void materialise_selected(const float* __restrict__ lt_pt, int gl, int gi, bool want,
+                                                     const double (&base)[CPL], const float (&w)[CPL], float* ws,
+                                                     double (&x_out)[CPL]) {
+    constexpr int NPAD = LPC * CPL, G = 32 / LPC;
+    static_assert(NPAD == 32 && LPC < 32, "one output coordinate per lane");
+    const int lane = gi * LPC + gl;
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) ws[gl + LPC * r] = w[r];
+    __syncwarp();
+    const unsigned asking = __ballot_sync(kFull, want);
+    float sum[CPL];
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) sum[r] = 0.0f;
+    const unsigned long long my_lt = (unsigned long long)(uintptr_t)lt_pt;
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+        if (((asking >> (g * LPC)) & 1u) == 0u) continue;                      // warp-uniform
+        const float* __restrict__ lt_g =
+            (const float*)(uintptr_t)__shfl_sync(kFull, my_lt, g * LPC);         // the chain's point may differ per group
+        // stage row of group g: rows are [NPAD] doubles apart
+        const float4* __restrict__ w4 = reinterpret_cast<const float4*>(ws + (g - gi) * NPAD * 2);
+        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f, a3 = 0.0f;
+#pragma unroll
+        for (int j = 0; j < NPAD / 4; ++j) {
+            const float4 v = w4[j];
+            a0 = __fmaf_rn(__ldg(lt_g + (4 * j + 0) * NPAD + lane), v.x, a0);
+            a1 = __fmaf_rn(__ldg(lt_g + (4 * j + 1) * NPAD + lane), v.y, a1);
+            a2 = __fmaf_rn(__ldg(lt_g + (4 * j + 2) * NPAD + lane), v.z, a2);
+            a3 = __fmaf_rn(__ldg(lt_g + (4 * j + 3) * NPAD + lane), v.w, a3);
+        }
+        const float s = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2, a3));
+#pragma unroll
+        for (int r = 0; r < CPL; ++r) {
+            const float mine = __shfl_sync(kFull, s, gl + LPC * r);              // coordinate gl + LPC r lives on that lane
+            if (gi == g) sum[r] = mine;
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < CPL; ++r) x_out[r] = __dadd_rn(base[r], (double)sum[r]);
+}
+
 // Squared whitened radius inside which base + Lt*w provably stays in the prior box:
 //   |x_i - base_i| <= lt_norm_i * |w|  (Cauchy-Schwarz)  =>  safe while |w| < min_i dist_i / lt_norm_i.
 // 0.999 absorbs FP32 rounding of |w|^2 and of the later materialisation.  +inf without a box.

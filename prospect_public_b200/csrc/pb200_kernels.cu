@@ -129,7 +129,10 @@ template <int LPC, int CPL, bool WITH_RADIUS>
 __device__ __forceinline__ BoxProbe<CPL> probe_box_body(const pb200_problem& p, int pt, const float* __restrict__ lt_pt,
                                                         int gl, int gi, bool exact, const BoxIn<CPL>& in, float* ws) {
     BoxProbe<CPL> o;
-    materialise<LPC, CPL>(lt_pt, gl, in.xref, in.wt, ws, o.xt);
+    if constexpr (LPC < 32 && LPC * CPL == 32)      // several chains per warp: only the chains that ask pay
+        materialise_selected<LPC, CPL>(lt_pt, gl, gi, exact, in.xref, in.wt, ws, o.xt);
+    else
+        materialise<LPC, CPL>(lt_pt, gl, in.xref, in.wt, ws, o.xt);
     bool outside = false;
 #pragma unroll
     for (int r = 0; r < CPL; ++r) {

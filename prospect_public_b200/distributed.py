@@ -33,11 +33,14 @@ def init_from_env(backend='nccl'):
     os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
     os.environ.setdefault('MASTER_PORT', '29500')
     local = int(os.environ.get('LOCAL_RANK', os.environ.get('RANK', '0')))
+    # a mismatched collective must fail within minutes, not hold the GPUs for the default 10: PB200_DIST_TIMEOUT_S
+    from datetime import timedelta
+    limit = timedelta(seconds=int(os.environ.get('PB200_DIST_TIMEOUT_S', '180')))
     if backend == 'nccl':
         torch.cuda.set_device(local)
-        dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local))
+        dist.init_process_group(backend='nccl', device_id=torch.device('cuda', local), timeout=limit)
     else:
-        dist.init_process_group(backend=backend)
+        dist.init_process_group(backend=backend, timeout=limit)
     return dist_info()
 
 

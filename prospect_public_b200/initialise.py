@@ -137,7 +137,7 @@ def initialise_optimiser(config, kernel, shard=None):
             pos = np.delete(pos, pidx)
         if cov.shape[0] == len(all_names):
             cov = drop(cov)
-        mine = np.arange(n_pts)                    # nothing to compute: every rank fills all values itself
+        mine, world = np.arange(n_pts), 1          # nothing to compute: every rank fills all values itself
         positions = {p: pos for p in mine}
         covmats = {p: cov for p in mine}
     elif prof.start_from_profile is not None:
@@ -182,7 +182,8 @@ def initialise_optimiser(config, kernel, shard=None):
         raise ValueError('InitialiseOptimiserTask could not construct an initial position and/or covariance '
                          'matrix. Make sure to supply either "start_from_mcmc" or "start_from_position" and '
                          '"start_from_covmat" in the profile section of the input.')
-    if world > 1 and len(mine) < n_pts:           # every rank gets every value's start point / covariance
+    if world > 1:           # every rank gets every value's start point / covariance (ALL ranks take part, whatever
+                            # their own share -- also a rank that happens to own every value, or none)
         import torch.distributed as dist
         parts = [None] * world
         dist.all_gather_object(parts, (positions, covmats, indices))

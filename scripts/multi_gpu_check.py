@@ -32,6 +32,43 @@ for label, kw in (('points sharded (10 values x 6 reps)', dict(repetitions=6)),
               f'chain_steps {res["chain_steps"]}')
         assert err <= 1e-3 and ran and files
     dist.barrier()
+# N-invariance, bit for bit: the sharded job's gathered records == the same job run by rank 0 alone as a single-rank job
+# (Philox streams are keyed by the global chain id); incl. fewer repetitions than ranks (ranks without chains)
+from prospect_public_b200 import optimiser as opt_mod
+from prospect_public_b200 import run as run_mod
+for label, kw in (('10 values x 6 reps', dict(repetitions=6, max_iterations=5)),
+                  ('global optimisation, 3 repetitions (fewer chains than ranks at N = 8)',
+                   dict(repetitions=3, max_iterations=5, jobtype='global_optimisation'))):
+    jt = kw.pop('jobtype', 'profile')
+    multi = run(annealing_yaml(paths, os.path.join(base, 'out_inv'), jobtype=jt, **kw))
+    dist.barrier()
+    if dist_info()[0] == 0:
+        from prospect_public_b200 import distributed as dist_mod
+        real, real_ws = dist_mod.dist_info, os.environ['WORLD_SIZE']
+        opt_mod.dist_info = run_mod.dist_info = dist_mod.dist_info = lambda: (0, 1, False)
+        os.environ['WORLD_SIZE'] = '1'
+        try:
+            alone = run(annealing_yaml(paths, os.path.join(base, 'out_alone'), jobtype=jt, **kw))
+        finally:
+            opt_mod.dist_info = run_mod.dist_info = dist_mod.dist_info = real
+            os.environ['WORLD_SIZE'] = real_ws
+        same = all(np.array_equal(getattr(multi['record'], key), getattr(alone['record'], key))
+                   for key in ('best_loglkl', 'accepted', 'best_x', 'step_size', 'temperature'))
+        sub = 'profile/x2.txt' if jt == 'profile' else 'global_optimisation/results.txt'
+        a = open(os.path.join(base, 'out_inv', sub), 'rb').read()
+        b = open(os.path.join(base, 'out_alone', sub), 'rb').read()
+        print(f'N-invariance ({label}): world {dist_info()[1]} records identical to the single-rank run {same}, {sub} '
+              f'identical {a == b}')
+        assert same and a == b
+    dist.barrier()
+# the outputs of a run stopped early (rows that were never exchanged must read "did not run")
+part = run(annealing_yaml(paths, os.path.join(base, 'out_stop'), repetitions=6, max_iterations=8), stop_after=3)
+if dist_info()[0] == 0:
+    acc = part['record'].accepted
+    ok = bool((acc[:3] >= 0).all() and (acc[3:] == -1).all() and np.isinf(part['record'].best_loglkl[3:]).all())
+    print(f'stop_after: world {dist_info()[1]} rows 0-2 ran, rows 3-7 read "did not run": {ok}; chain_steps {part["chain_steps"]}')
+    assert ok and part['chain_steps'] == 60 * 3 * 250
+dist.barrier()
 # interrupted + resumed run (per-chain state gathered over the ranks) == uninterrupted run
 kw = dict(repetitions=6, max_iterations=8)
 full = run(annealing_yaml(paths, os.path.join(base, 'out_full'), **kw))
@@ -70,5 +107,18 @@ if dist_info()[0] == 0:
     assert abs(rm1 - res['Rm1']) <= 1e-9 * abs(rm1) and np.allclose(cov, res['covmat'], rtol=1e-9, atol=1e-15)
     print(f'mcmc sharded: world {dist_info()[1]} 19 chain files identical to a single-GPU run, R-1 {res["Rm1"]:.6f} '
           f'(single {rm1:.6f}), chain range of rank 0 {res["chain_range"]}')
+dist.barrier()
+# jobtype mcmc interrupted after one round and resumed from its chain files == the uninterrupted three rounds
+full_dir, part_dir = os.path.join(base, 'mc_full'), os.path.join(base, 'mc_part')
+full = run(mcmc_yaml(paths, full_dir, n_chains=11, steps=500, rm1=1e-12), max_rounds=3)
+run(mcmc_yaml(paths, part_dir, n_chains=11, steps=500, rm1=1e-12), stop_after=1)
+dist.barrier()
+cont = run(part_dir, max_rounds=3)
+dist.barrier()
+if dist_info()[0] == 0:
+    same = all(open(os.path.join(full_dir, 'mcmc', f'test_{i}.txt'), 'rb').read() ==
+               open(os.path.join(part_dir, 'mcmc', f'test_{i}.txt'), 'rb').read() for i in range(11))
+    print(f'mcmc resume: world {dist_info()[1]} chain files identical {same}, R-1 {cont["Rm1"]:.6f} vs {full["Rm1"]:.6f}')
+    assert same and abs(cont['Rm1'] - full['Rm1']) <= 1e-12 * full['Rm1'] and cont['rounds'] == 3
 dist.barrier()
 dist.destroy_process_group()

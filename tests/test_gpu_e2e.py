@@ -451,7 +451,7 @@ def test_interrupted_mcmc_job_resumes_to_identical_chain_files(tmp_path):
     part = run(mcmc_yaml(paths, str(tmp_path / 'part'), n_chains=6, steps=700, rm1=1e-12), stop_after=1)
     assert part['rounds'] == 1
     cont = run(str(tmp_path / 'part'), max_rounds=3)
-    assert cont['rounds'] == 3 and cont['Rm1'] == full['Rm1']
+    assert cont['rounds'] == 3 and abs(cont['Rm1'] - full['Rm1']) <= 1e-12 * full['Rm1']   # (reduction order differs)
     for i in range(6):
         a = open(os.path.join(str(tmp_path / 'full'), 'mcmc', f'test_{i}.txt'), 'rb').read()
         b = open(os.path.join(str(tmp_path / 'part'), 'mcmc', f'test_{i}.txt'), 'rb').read()
