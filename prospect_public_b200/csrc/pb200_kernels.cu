@@ -31,6 +31,9 @@
 #ifndef PB200_MIN_CTAS_8
 #define PB200_MIN_CTAS_8 4   // 8 lanes per chain: <= 128 registers
 #endif
+#ifndef PB200_PIPE_RNG
+#define PB200_PIPE_RNG 0     // experiment: draw the next Philox block in the shadow of the current one (8-lane geometry)
+#endif
 
 #include <cmath>
 #include <cstdio>
@@ -376,10 +379,31 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
                                                 ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring) {
     float z[CPL][4], e[4], zk[CPL];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
+#if PB200_PIPE_RNG
+    // software pipeline (small batches of the 8-lane geometry, where registers do not limit occupancy): the variates of
+    // block b + 1 -- independent of the chain state -- are drawn in the shadow of block b's dependent reduce ->
+    // compare -> commit chain
+    constexpr bool kPipe = SRC == kSrcPhilox && LPC == 8 && REC == PB200_RECORD_NONE && !EXACT;
+    float zn[kPipe ? CPL : 1][4], en[4];
+    if constexpr (kPipe) draw_block<LPC, CPL>(k0, k1, chain_id, t_begin >> 2, p.n, gl, zn, en);
+#else
+    constexpr bool kPipe = false;
+#endif
     while (i < n_steps) {
         const uint32_t t = t_begin + i;
         if constexpr (SRC == kSrcRing) {
             ring_fetch<LPC, CPL>(ring, gi * LPC + gl, gi, z, e);
+        } else if constexpr (kPipe) {
+#if PB200_PIPE_RNG
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) z[r][k] = zn[r][k];
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) e[k] = en[k];
+            draw_block<LPC, CPL>(k0, k1, chain_id, (t >> 2) + 1u, p.n, gl, zn, en);     // next block (unused after the last)
+#endif
         } else {
             draw_block<LPC, CPL>(k0, k1, chain_id, t >> 2, p.n, gl, z, e);
         }

@@ -233,7 +233,10 @@ def dump_snapshot(config, rec, reference_compatible=True, resume_state=None):
     pio.dump_pickle(state, config.io.dir, 'pb200_state')
     if reference_compatible:
         n_tasks = int((rec.accepted >= 0).sum())
-        compat.export_reference_snapshot(config, rec, config.io.dir, compact=n_tasks > 20000)
+        if n_tasks > 20000 and rec.temperature is not None and rec.step_size is not None and rec.best_x is not None:
+            compat.export_reference_snapshot_bulk(config, rec, config.io.dir)      # bytes assembled with numpy
+        else:
+            compat.export_reference_snapshot(config, rec, config.io.dir, compact=n_tasks > 20000)
     with open(os.path.join(config.io.dir, 'status.txt'), 'w') as f:
         ran = rec.accepted >= 0
         f.write(f"Status of job '{config.io.jobname}'\nJobtype: {config.run.jobtype}\n")

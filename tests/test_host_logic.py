@@ -381,11 +381,13 @@ def test_mcmc_statistics_all_reduce_world2_gloo():
 REFERENCE = '/root/reference'
 
 
+@pytest.mark.parametrize('writer', ['objects', 'bulk'])
 @pytest.mark.skipif(not os.path.isdir(REFERENCE), reason='the reference checkout only exists in the build container')
-def test_reference_reads_our_snapshot(toy20, tmp_path):
-    """N1: config.pkl / state.pkl written by compat.export_reference_snapshot are consumed by the UNMODIFIED
-    reference (`prospect.run.load` -> `Scheduler.get_analysis_task().run`, `prospect.profile.load_profile`) and give
-    its own profile/x2.txt back."""
+def test_reference_reads_our_snapshot(toy20, tmp_path, writer):
+    """N1: config.pkl / state.pkl written by compat.export_reference_snapshot (Python objects) and by
+    compat.export_reference_snapshot_bulk (pickle byte stream assembled with numpy, used for large runs) are consumed
+    by the UNMODIFIED reference (`prospect.run.load` -> `Scheduler.get_analysis_task().run`,
+    `prospect.profile.load_profile`) and give its own profile/x2.txt back."""
     import subprocess
     import sys
     from prospect_public_b200 import compat
@@ -398,8 +400,12 @@ def test_reference_reads_our_snapshot(toy20, tmp_path):
     rec = _record_from_golden(gold, 19, 1, np.linspace(-1.0, 2.0, 10))
     rec.temperature = np.full(rec.best_loglkl.shape, 0.1)
     rec.step_size = np.full(rec.best_loglkl.shape, 0.1)
-    n_tasks = compat.export_reference_snapshot(cfg, rec, str(out))
-    assert n_tasks == 10 + 200
+    if writer == 'objects':
+        n_tasks = compat.export_reference_snapshot(cfg, rec, str(out))
+        assert n_tasks == 10 + 200
+    else:                                  # compact selection: each chain's best and last iteration
+        n_tasks = compat.export_reference_snapshot_bulk(cfg, rec, str(out))
+        assert 10 + 10 <= n_tasks <= 10 + 20
     script = (
         "import sys, json, numpy as np\n"
         "from prospect.run import load\n"
@@ -418,7 +424,7 @@ def test_reference_reads_our_snapshot(toy20, tmp_path):
     assert proc.returncode == 0, proc.stderr[-2000:]
     line = [ln for ln in proc.stdout.splitlines() if ln.startswith('RESULT')][0]
     res = json.loads(line[len('RESULT '):])
-    assert res == {'n': 10, 'types': ['InitialiseOptimiserTask', 'OptimiseTask'], 'ntasks': 210}
+    assert res == {'n': 10, 'types': ['InitialiseOptimiserTask', 'OptimiseTask'], 'ntasks': n_tasks}
     assert (out / 'profile' / 'x2.txt').read_text() == gold['files']['x2.txt']
     assert (out / 'profile' / 'x2_status.txt').read_text() == gold['files']['x2_status.txt']
     # and our own reader understands PROSPECT's config.pkl without PROSPECT being importable
@@ -519,3 +525,60 @@ def test_gelman_rubin_follows_the_published_getdist_definition():
     stats = np.concatenate([[sw], swx, swxx.reshape(-1), syy.reshape(-1), [len(chains)]])
     got, mean, cov = convergence_from_statistics(stats, n)
     assert abs(got - expect) < 1e-9 * expect
+
+
+@pytest.mark.parametrize('jobtype,n_points,reps', [('profile', 7, 40), ('global_optimisation', 1, 90)])
+def test_bulk_snapshot_writer_builds_the_same_object_graph(toy20, tmp_path, jobtype, n_points, reps):
+    """compat.export_reference_snapshot_bulk writes state.pkl as bytes (one OptimiseTask laid out as a pickle template,
+    tiled and filled with numpy); pickle.load must give exactly the object graph of the object-by-object exporter in
+    its compact mode -- same keys in the same order, same values, same sharing inside a task."""
+    import pickle
+    from prospect_public_b200 import compat
+    rng = np.random.default_rng(5)
+    k_rows, n = 6, 19 if jobtype == 'profile' else 20
+    b = n_points * reps
+    acc = rng.integers(0, 100, (k_rows, b)).astype(np.int32)
+    acc[4:, ::5] = -1                              # chains that stopped early
+    acc[:, 3] = -1                                 # a chain that never ran
+    names = [f'x{i}' for i in range(1, 21) if not (jobtype == 'profile' and i == 2)]
+    rec = analysis.RunRecord(np.linspace(-1.0, 2.0, n_points) if jobtype == 'profile' else np.zeros(0), reps, names,
+                             rng.uniform(0, 50, (k_rows, b)), acc, rng.normal(size=(k_rows, b, n)), rng.random(b) < 0.2,
+                             rng.uniform(0, 5, n_points), rng.normal(size=(n_points, n)),
+                             np.stack([np.eye(n) * (p + 1) for p in range(n_points)]),
+                             rng.uniform(0, 1, (k_rows, b)), rng.uniform(0, 1, (k_rows, b)))
+    kw = {'values': f'np.linspace(-1.0, 2.0, {n_points})'} if jobtype == 'profile' else {}
+    cfg = Configuration(annealing_yaml(toy20, str(tmp_path / 'o'), jobtype=jobtype, write=False, repetitions=reps, **kw))
+    dirs = [tmp_path / 'a', tmp_path / 'b']
+    for d_ in dirs:
+        d_.mkdir()
+    n_a = compat.export_reference_snapshot(cfg, rec, str(dirs[0]), compact=True)
+    n_b = compat.export_reference_snapshot_bulk(cfg, rec, str(dirs[1]))
+    assert n_a == n_b
+
+    def same(a, b_, path=''):
+        assert type(a) is type(b_) or (isinstance(a, (float, np.floating)) and isinstance(b_, (float, np.floating))), path
+        if isinstance(a, dict):
+            assert list(a.keys()) == list(b_.keys()), path
+            for key in a:
+                if not (isinstance(key, str) and key.startswith('time_')):
+                    same(a[key], b_[key], f'{path}[{key}]')
+        elif isinstance(a, (list, tuple)):
+            assert len(a) == len(b_), path
+            for i, (x, y) in enumerate(zip(a, b_)):
+                same(x, y, f'{path}[{i}]')
+        elif isinstance(a, np.ndarray):
+            assert np.array_equal(a, b_), path
+        elif hasattr(a, '__dict__') and not isinstance(a, type):
+            same(a.__dict__, b_.__dict__, f'{path}.{type(a).__name__}')
+        else:
+            assert a == b_, (path, a, b_)
+
+    with compat._Registered():
+        with open(dirs[0] / 'state.pkl', 'rb') as f:
+            sa = pickle.load(f)
+        with open(dirs[1] / 'state.pkl', 'rb') as f:
+            sb = pickle.load(f)
+        same(sa.__dict__, sb.__dict__)
+        task = list(sb.done.values())[-1]
+        assert task.optimise_settings is task.optimiser.settings
+        assert task.optimiser.bestfit['position'] is task.optimise_settings['initial_position']
