@@ -513,10 +513,13 @@ def main():
         from prospect_public_b200.toy import annealing_yaml
         tmp = tempfile.mkdtemp(prefix=f'pb200_ttp_r{rank}_')
         pkw = dict(workload_profile_kw('profile30', world)[1])
-        ycfg = annealing_yaml(toy_inputs(tmp)[0], os.path.join(tmp, 'ttp'), jobtype='profile', write=True, **pkw)
+        ttp_paths = toy_inputs(tmp)[0]
         first = None
         for attempt in range(2):       # the first run of a new job shape pays one-off set-up (kernel loading, pinned
-            barrier()                  # staging and, for N > 1, the peer-memory rendezvous of the exchange buffers)
+            # staging and, for N > 1, the peer-memory rendezvous of the exchange buffers); a fresh output folder per
+            # attempt (deleting the previous run's ~100 MB snapshot is not part of the job)
+            ycfg = annealing_yaml(ttp_paths, os.path.join(tmp, f'ttp{attempt}'), jobtype='profile', write=True, **pkw)
+            barrier()
             t0 = time.perf_counter()
             res_job = run_job(ycfg)
             barrier()
