@@ -76,3 +76,47 @@ def test_reference_tasks_run_on_the_cuda_kernel(tmp_path, monkeypatch):
     txt = [open(os.path.join(str(tmp_path / tag), 'profile', 'x2.txt')).read() for tag in ('plain', 'cuda')]
     rows = [[[float(t) for t in ln.split('\t')[:5]] for ln in s.strip().split('\n')[1:]] for s in txt]
     assert np.allclose(rows[0], rows[1], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.skipif(not rh.available(), reason='oracle/_ref is absent')
+def test_reference_scheduler_drives_the_gpu_batch_executor(tmp_path):
+    """Executor protocol (prospect/run.py:27-58): the UNMODIFIED reference's Scheduler --
+    its task objects, priorities, emit_tasks / chi2 bookkeeping, AnalyseProfileTask -- runs a 20-D profile job of 10
+    values x 8 repetitions x 12 iterations with `GpuBatchExecutor` in the place of its process pool.  Every
+    OptimiseTask the scheduler emits comes back from a batched launch (one launch per wave of ready tasks, not one
+    per task), the reference's own analysis writes profile/x2.txt from them, and the profile agrees with the analytic
+    one and with the package's own driver on the same schedule."""
+    rh.activate()
+    from oracle import closed_form
+    from prospect.communication import Scheduler
+    from prospect.input import Configuration
+    from prospect.io import prepare_run
+    from prospect_public_b200.executor import GpuBatchExecutor
+    from prospect_public_b200.run import run as gpu_run
+
+    k, m = golden('toy20_kernel.npz'), golden('toy20_mcmc.npz')
+    paths = write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], [m[f'chain_{i}'] for i in range(4)])
+    kw = dict(repetitions=8, max_iterations=12, temperature_range=[0.1, 1.0e-5], steps_per_iteration=250,
+              plot_profile=False, plot_schedule=False)
+    y = annealing_yaml(paths, str(tmp_path / 'ref'), **kw)
+    y['run']['mode'] = 'serial'                     # (a value the reference's schema accepts; the executor is ours)
+    y['io']['snapshot_interval'] = 1.0e9
+    with rh.quiet():
+        config = Configuration(copy.deepcopy(y))
+        prepare_run(config)
+        sched = Scheduler(config, False)
+        with GpuBatchExecutor() as executor, rh.truncated_annealing(12):
+            sched.delegate(executor)
+        task = sched.get_analysis_task()
+        task.run([t for t in sched.tasks.done.values() if t.id in task.required_task_ids])
+    assert len(sched.tasks.failed) == 0
+    opt = [t for t in sched.tasks.done.values() if t.type == 'OptimiseTask']
+    assert len(opt) == 10 * 8 * 12
+    assert executor.tasks_batched == len(opt) and executor.launches <= 3 * 12       # waves, not tasks
+    rows = [[float(v) for v in ln.split('\t')[:3]] for ln in
+            open(os.path.join(str(tmp_path / 'ref'), 'profile', 'x2.txt')).read().strip().split('\n')[1:]]
+    values = np.array([r[0] for r in rows])
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, values)
+    assert np.max(2 * np.abs(np.array([r[2] for r in rows]) - cf)) <= 1e-3
+    ours = gpu_run(annealing_yaml(paths, str(tmp_path / 'ours'), **kw))
+    assert np.max(2 * np.abs(ours['profile']['loglkls'] - np.array([r[2] for r in rows]))) <= 1e-3
