@@ -62,9 +62,30 @@ def get_points_in_bin(chain, param_val, param_name, n_points):
     return np.argsort(distance)[:n_points]
 
 
+# Above this many MCMC rows the nearest-N selection of every profile value runs on the GPU (one distance matrix, one
+# partial sort for all values); below it numpy's argsort is exact, cheap (5 ms for the 2 477-row toy) and is what the
+# bit-exact bookkeeping tests pin.
+GPU_BINNING_MIN_ROWS = 200_000
+
+
 def get_fraction_of_points_in_bin(chain, param_val, param_name, fraction):
     n_points = int(np.ceil(fraction * len(chain.mults)))
     return get_points_in_bin(chain, param_val, param_name, n_points)
+
+
+def get_points_in_bins_gpu(column, values, n_points, device):
+    """get_points_in_bin for ALL profile values at once on the device: indices [P, n_points] of the rows nearest to each
+    value, nearest first.  Same result as np.argsort(|x - v|)[:n_points] whenever the distances involved are distinct
+    (numpy's default argsort is not stable either, so the order inside a tie is not defined by the reference)
+    (tasks/initialise_optimiser_task.py:186-196)."""
+    import torch
+    x = torch.as_tensor(np.asarray(column, dtype=np.float64), device=device)
+    v = torch.as_tensor(np.asarray(values, dtype=np.float64), device=device)
+    out = []
+    for lo in range(0, len(v), 16):                                  # bounded scratch: 16 values x N rows at a time
+        dist = (x[None, :] - v[lo:lo + 16, None]).abs()
+        out.append(torch.topk(dist, n_points, dim=1, largest=False, sorted=True).indices)
+    return torch.cat(out, dim=0).cpu().numpy()
 
 
 def _weighted_cov_gpu(x, mults, device):
@@ -165,8 +186,15 @@ def initialise_optimiser(config, kernel, shard=None):
     elif prof.start_from_mcmc is not None:
         chain = _reduced_chain(load_mcmc(prof.start_from_mcmc), kernel)
         indices, xs, ms = {}, [], []
+        gpu_idx = None
+        if is_profile and len(chain.mults) >= GPU_BINNING_MIN_ROWS and len(mine):
+            n_bin = int(np.ceil(prof.start_bin_fraction * len(chain.mults)))
+            gpu_idx = dict(zip(mine, get_points_in_bins_gpu(chain.positions[prof.parameter], values[mine], n_bin,
+                                                            kernel.device)))
         for p in mine:
-            if is_profile:
+            if gpu_idx is not None:
+                idx = gpu_idx[p]
+            elif is_profile:
                 idx = get_fraction_of_points_in_bin(chain, values[p], prof.parameter, prof.start_bin_fraction)
             else:
                 idx = np.arange(len(chain.mults))

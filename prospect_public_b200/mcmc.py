@@ -207,6 +207,22 @@ class MetropolisHastings:
         self.accepted += acc.cpu().numpy()
         self.steps += steps_per_iteration
 
+    def run_minutes(self, minutes_per_iteration, chunk=1024):
+        """BaseMCMC.run_minutes (prospect/mcmc.py:140-151): keep stepping until the wall-clock budget is used up.  The
+        reference checks the clock after every step of its one chain; here every chain of the batch advances `chunk`
+        steps per launch and the clock is read between launches, so all chains take the same number of steps (a
+        multiple of `chunk`) -- how many depends on the hardware, as it does in the reference."""
+        import time
+        import torch
+        t_end = time.perf_counter() + 60.0 * float(minutes_per_iteration)
+        done = 0
+        while True:
+            self.run_steps(int(chunk))
+            done += int(chunk)
+            torch.cuda.synchronize()
+            if time.perf_counter() >= t_end:
+                return done
+
     def samples_numpy(self):
         """(x [B, cap, n], loglkl [B, cap], mult [B, cap], count [B]) of everything recorded so far."""
         s = self._samples

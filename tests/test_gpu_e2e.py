@@ -456,3 +456,42 @@ def test_interrupted_mcmc_job_resumes_to_identical_chain_files(tmp_path):
         a = open(os.path.join(str(tmp_path / 'full'), 'mcmc', f'test_{i}.txt'), 'rb').read()
         b = open(os.path.join(str(tmp_path / 'part'), 'mcmc', f'test_{i}.txt'), 'rb').read()
         assert a == b, i
+
+
+def test_gpu_binning_of_a_large_starting_mcmc_matches_numpy(tmp_path, monkeypatch):
+    """for a starting MCMC of several 1e5 rows the nearest-N selection of all profile values runs on the
+    device.  Indices equal numpy's argsort selection (distinct distances), and the whole initialisation -- start
+    points, bin covariances, initial_loglkl -- equals the host path."""
+    from prospect_public_b200 import initialise as ini
+    from prospect_public_b200.kernels import initialise_kernel
+    rng = np.random.default_rng(11)
+    col = rng.normal(0.5, 1.0, 300_000)
+    vals = np.linspace(-1.0, 2.0, 21)
+    got = ini.get_points_in_bins_gpu(col, vals, 30_000, 'cuda:0')
+    for p, v in enumerate(vals):
+        assert np.array_equal(got[p], np.argsort(np.abs(col - v))[:30_000]), p
+    # end to end through initialise_optimiser: force the device path on the (small) toy chain
+    paths, k = _inputs(tmp_path, 20)
+    cfg = Configuration(annealing_yaml(paths, str(tmp_path / 'o'), write=False))
+    host = ini.initialise_optimiser(cfg, initialise_kernel(cfg.kernel, None, 0))[0]
+    monkeypatch.setattr(ini, 'GPU_BINNING_MIN_ROWS', 1)
+    dev = ini.initialise_optimiser(cfg, initialise_kernel(cfg.kernel, None, 0))[0]
+    for a, b in zip(host.indices, dev.indices):      # the toy's four chains all start at 0: exact distance ties, whose
+        assert np.array_equal(np.sort(a), np.sort(b))    # order neither sort defines -> the same SET of rows
+    assert np.array_equal(host.positions, dev.positions) and np.array_equal(host.initial_loglkl, dev.initial_loglkl)
+    assert np.allclose(host.covmats, dev.covmats, rtol=1e-10, atol=1e-16)    # (summation order follows the row order)
+
+
+def test_mcmc_run_minutes_uses_the_time_budget(tmp_path):
+    """BaseMCMC.run_minutes (mcmc.py:140-151): step until the wall-clock budget is spent; the chains stay a valid
+    continuation (sum of multiplicities = steps + 1)."""
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.mcmc import initialise_mcmc
+    paths, k = _inputs(tmp_path, 20)
+    cfg = Configuration(mcmc_yaml(paths, str(tmp_path / 'o'), n_chains=8, steps=100, write=False))
+    sampler = initialise_mcmc(cfg.mcmc, initialise_kernel(cfg.kernel, None, 0), seed=3)
+    import time
+    t0 = time.perf_counter()
+    steps = sampler.run_minutes(0.01, chunk=512)            # 0.6 s
+    assert 0.6 <= time.perf_counter() - t0 < 5.0 and steps >= 512 and steps % 512 == 0
+    assert all(int(np.sum(ch.mults)) == steps + 1 for ch in sampler.chains)

@@ -582,3 +582,47 @@ def test_bulk_snapshot_writer_builds_the_same_object_graph(toy20, tmp_path, jobt
         task = list(sb.done.values())[-1]
         assert task.optimise_settings is task.optimiser.settings
         assert task.optimiser.bestfit['position'] is task.optimise_settings['initial_position']
+
+
+def _sync_worker(rank, world, port, inputs, base, q):
+    """Two ranks build their own Configuration (no seed in the yaml, an output folder that already exists for rank 1
+    only ... ) and call synchronise(); the all_gather_object of the sharded initialisation is exercised with the same
+    payload shape it has in initialise_optimiser."""
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    y = annealing_yaml(inputs, os.path.join(base, f'private_{rank}'), seed=None)
+    y['run']['numpy_random_seed'] = None
+    cfg = Configuration(y)
+    before = (cfg.io.dir, cfg.seed)
+    cfg.synchronise()
+    mine = np.array_split(np.arange(5), world)[rank]
+    parts = [None] * world
+    dist.all_gather_object(parts, ({int(p_): np.full(3, float(p_)) for p_ in mine}, {int(p_): np.eye(2) * p_ for p_ in mine},
+                                   None))
+    merged = {}
+    for pos, cov, idx in parts:
+        merged.update(pos)
+    q.put((rank, before, (cfg.io.dir, cfg.seed, cfg.seed), sorted(merged)))
+    dist.destroy_process_group()
+
+
+def test_configuration_synchronise_world2_gloo(toy20, tmp_path):
+    """Every rank of a torch.distributed job builds its own Configuration; without a numpy_random_seed each would draw
+    its own Philox key, and a late rank could resolve a different output folder.  synchronise() makes rank 0's
+    values the job's; the seed is drawn ONCE per Configuration (two reads give the same key)."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29900 + (os.getpid() % 90)
+    procs = [ctx.Process(target=_sync_worker, args=(rank, 2, port, toy20, str(tmp_path), q)) for rank in range(2)]
+    for pr in procs:
+        pr.start()
+    outs = {r: rest for r, *rest in (q.get(timeout=120) for _ in range(2))}
+    for pr in procs:
+        pr.join(timeout=60)
+    (before0, after0, pts0), (before1, after1, pts1) = outs[0], outs[1]
+    assert before0[0] != before1[0] and before0[1] != before1[1]          # they really disagreed
+    assert after0[:2] == before0 and after1[:2] == before0                # rank 0's folder and key everywhere
+    assert after1[1] == after1[2]                                         # cached: the same key on every read
+    assert pts0 == pts1 == [0, 1, 2, 3, 4]                                # every rank ends up with every value
