@@ -58,13 +58,15 @@ static int check_cuda(cudaError_t e, const char* what) {
 template <int LPC, int CPL>
 struct Geometry {
     static constexpr int NPAD = LPC * CPL, G = 32 / LPC;
-    // four-steps-per-reduction (block_step) pays where few lanes per chain make the butterfly short: measured on B200 it
-    // wins for 8 lanes per chain (+14 % at 4096 chains) and loses for 16 / 32 (more shuffle instructions, issue-bound)
-    // ... and for the wide geometries (32 lanes, >= 4 coordinates per lane: npad >= 128), which are latency-bound at
-    // every batch size that fits the register file (one chain per warp, <= 8 warps per SM): there the four dependent
-    // reduce -> compare -> branch chains of a block cost ~4 x 300 cycles of pure latency (ncu, 256-D) and the
-    // reduce-scatter form needs 32 shuffles per block instead of 20-40
-    static constexpr bool kBlockMode = (LPC == 8) || (LPC == 32 && CPL >= 4);
+    // four-steps-per-reduction (block_step): one reduce-scatter of 16 sums (30-32 shuffles) instead of four dependent
+    // reduce -> compare -> branch chains.  Measured on B200 (profiles/README.md): with 8 lanes per chain it wins at every
+    // batch size (+14 % at 4096 chains); with 16 / 32 lanes it wins where the batch is latency-bound -- which is exactly
+    // where choose_lanes picks those geometries for npad = 32 (<= 2560 chains: +6 % .. +13 % over the 8-lane kernel with
+    // producer warps) -- and loses 10-25 % on large batches (more shuffle instructions per chain-step, issue-bound),
+    // where choose_lanes does not pick them.  The wide geometries (32 lanes, >= 4 coordinates per lane: npad >= 128)
+    // are latency-bound at every batch size that fits the register file (one chain per warp, <= 8 warps per SM).
+    // npad = 64 keeps the step-by-step form (not measured).
+    static constexpr bool kBlockMode = (NPAD == 32) || (LPC == 32 && CPL >= 4);
     // register budget per geometry (65536 / (kMinCtas * 128 threads)): 72 / 96 / 128 for 1 / 2 / 4 coordinates per lane
     static constexpr int kMinCtas =
         (NPAD != 32 ? 1 : (LPC == 32 ? PB200_MIN_CTAS : (LPC == 16 ? PB200_MIN_CTAS_16 : PB200_MIN_CTAS_8))) * 4 / kWarpsPerCta;
@@ -290,6 +292,23 @@ __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf
             a2[i] = __fadd_rn(b1 ? a4[i + 2] : a4[i], __shfl_xor_sync(kFull, b1 ? a4[i] : a4[i + 2], 1));
 #pragma unroll
         for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(kFull, a2[j & 1], j >> 1, 8);
+    } else if constexpr (LPC == 16) {
+        // four levels (8 + 4 + 2 + 1 exchanges): the lane bits select the index bits, so sum j ends up in lane j of the
+        // group; one broadcast per sum -- 31 SHFL + 15 FADD
+        const bool b8 = (gl & 8) != 0, b4 = (gl & 4) != 0, b2 = (gl & 2) != 0, b1 = (gl & 1) != 0;
+        float a8[8], a4[4], a2[2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+            a8[i] = __fadd_rn(b8 ? v[i + 8] : v[i], __shfl_xor_sync(kFull, b8 ? v[i] : v[i + 8], 8));
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            a4[i] = __fadd_rn(b4 ? a8[i + 4] : a8[i], __shfl_xor_sync(kFull, b4 ? a8[i] : a8[i + 4], 4));
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            a2[i] = __fadd_rn(b2 ? a4[i + 2] : a4[i], __shfl_xor_sync(kFull, b2 ? a4[i] : a4[i + 2], 2));
+        const float a1 = __fadd_rn(b1 ? a2[1] : a2[0], __shfl_xor_sync(kFull, b1 ? a2[0] : a2[1], 1));
+#pragma unroll
+        for (int j = 0; j < 16; ++j) v[j] = __shfl_sync(kFull, a1, j, 16);
     } else if constexpr (LPC == 32) {
         // the same reduce-scatter over five levels (8 + 4 + 2 + 1 exchanges, then one full exchange): sum j ends up in
         // lanes 2 j and 2 j + 1, one broadcast per sum -- 32 SHFL + 16 FADD, each sum formed by the butterfly's own
@@ -1191,10 +1210,12 @@ int pb200_loglkl_batch(const pb200_problem* prob, const double* x, const int32_t
 // lanes per chain: small groups serve several chains per warp instruction, large groups give more warps.
 static int choose_lanes(int npad, int n_chains) {
     // Measured on B200 (30-D toy, profiles/README.md): fewer lanes per chain = fewer warp instructions per chain-step.
-    // npad = 32: the 8-lane geometry (four steps per reduction) wins at every batch size once small batches get
-    // producer warps (use_producer_warps); wider problems keep more lanes per chain.
+    // npad = 32 (all geometries take four steps per reduction): more lanes per chain = more warps, which is what a small,
+    // latency-bound batch needs -- 32 lanes up to 1536 chains (5.03e9 vs 4.46e9 chain-steps/s for the 8-lane kernel with
+    // producer warps at 1024 chains), 16 lanes up to 2560 (8.16e9 vs 7.73e9 at 2048), 8 lanes above (1.17e10 vs 1.06e10
+    // at 4096); wider problems keep more lanes per chain.
     if (npad > 64) return 32;
-    if (npad == 32) return 8;
+    if (npad == 32) return n_chains <= 1536 ? 32 : (n_chains <= 2560 ? 16 : 8);
     return n_chains >= 4096 ? 16 : 32;
 }
 

@@ -470,7 +470,10 @@ def test_misaligned_chains_in_one_warp_take_the_generic_path():
 
 
 def test_lane_choice_follows_batch_size():
-    assert engine.choose_lanes(32, 10) == 8 and engine.choose_lanes(32, 4096) == 8 and engine.choose_lanes(32, 65536) == 8
+    # npad = 32: more lanes per chain (more warps) for the small, latency-bound batches, 8 lanes once the GPU is filled
+    assert engine.choose_lanes(32, 10) == 32 and engine.choose_lanes(32, 1024) == 32
+    assert engine.choose_lanes(32, 2048) == 16
+    assert engine.choose_lanes(32, 4096) == 8 and engine.choose_lanes(32, 65536) == 8
     assert engine.choose_lanes(64, 65536) == 16 and engine.choose_lanes(64, 100) == 32
     assert engine.choose_lanes(256, 65536) == 32
     assert engine.uses_producer_warps(8, 1024) and not engine.uses_producer_warps(8, 4096)
