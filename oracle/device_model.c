@@ -199,6 +199,7 @@ typedef struct {
     const dm_problem *p;
     int pt, lpc;
     int exact;              /* PB200_EXACT_BOX: every likelihood-accepted step is materialised and box-tested */
+    int boxtest;            /* block_steps tests its accepted positions in place instead of asking for a replay */
     float Tf, sf;
     float gf[MAXN], hl[MAXN];
 } dm_run;
@@ -329,7 +330,21 @@ static int block_steps(dm_run *R, dm_state *s, const float *zb[4], const float e
     const int any = acc[0] || acc[1] || acc[2] || acc[3];
     const float s2 = sf + sf;
     const float half_bnd2 = fmaf(s2 * s2, S[14], S[15]);
-    if (any && !((half_bnd2 + half_bnd2) <= s->m2)) return 1;
+    if (any && !((half_bnd2 + half_bnd2) <= s->m2)) {
+        if (!R->boxtest) return 1;
+        /* MH kernels: test the positions the block would accept (the commit loop's own FMAs, one FP32 mat-vec each);
+           all inside -> commit without re-referencing, one outside -> replay step by step */
+        float wt[MAXN];
+        double xt[MAXN];
+        memcpy(wt, s->w, sizeof(float) * np);
+        for (int k = 0; k < 4; ++k) {
+            if (!acc[k]) continue;
+            for (int c = 0; c < np; ++c) wt[c] = fmaf(sf, c < n ? zb[k][c] : 0.0f, wt[c]);
+            materialise(p, R->pt, s->xref, wt, xt);
+            for (int c = 0; c < np; ++c)
+                if (xt[c] < p->lo[c] || xt[c] > p->hi[c]) return 1;
+        }
+    }
     for (int k = 0; k < 4; ++k) {
         s->ll = s->ll + (acc[k] ? (double)delta[k] : 0.0);      /* the kernel adds +0.0 for a rejected step */
         if (!acc[k]) continue;
@@ -350,11 +365,11 @@ static int block_steps(dm_run *R, dm_state *s, const float *zb[4], const float e
 
 static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain_id, uint32_t t_begin,
                       uint32_t n_steps, float Tf, float sf, int lpc, dm_state *s, const float *z_replay,
-                      const float *e_replay, uint32_t replay_step0, dm_recorder *rec, int exact) {
+                      const float *e_replay, uint32_t replay_step0, dm_recorder *rec, int exact, int boxtest) {
     const int np = p->npad, n = p->n;
     const float *lam = p->lam + (size_t)pt * np;
     dm_run R;
-    R.p = p; R.pt = pt; R.lpc = lpc; R.Tf = Tf; R.sf = sf; R.exact = exact;
+    R.p = p; R.pt = pt; R.lpc = lpc; R.Tf = Tf; R.sf = sf; R.exact = exact; R.boxtest = boxtest;
     const float half_s = 0.5f * sf;
     for (int c = 0; c < np; ++c) { R.gf[c] = (float)s->gt[c]; R.hl[c] = half_s * lam[c]; }
     float *zbuf = NULL, *ebuf = NULL;
@@ -444,7 +459,7 @@ void dm_anneal_chain(const dm_problem *p, const dm_schedule *s, dm_chain *c, int
         memcpy(st.bref, st.xref, sizeof(double) * np);
         memset(st.bw, 0, sizeof(float) * np);
         run_steps(p, c->point, seed, c->chain_id, c->steps_done, (uint32_t)s->steps_per_iteration,
-                  (float)c->temperature, (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, NULL, 0);
+                  (float)c->temperature, (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, NULL, 0, 0);
         c->steps_done += s->steps_per_iteration;
         materialise(p, c->point, st.bref, st.bw, bx);
         materialise(p, c->point, st.xref, st.w, c->x);
@@ -483,7 +498,8 @@ int32_t dm_mh_chain(const dm_problem *p, dm_chain *c, int32_t n_steps, uint64_t 
     while (done < (uint32_t)n_steps) {
         const uint32_t chunk = (uint32_t)n_steps - done < 256u ? (uint32_t)n_steps - done : 256u;
         run_steps(p, c->point, seed, c->chain_id, c->steps_done + done, chunk, (float)c->temperature,
-                  (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, mode ? &r : NULL, exact);
+                  (float)c->step_size, lpc, &st, z_replay, e_replay, replay0, mode ? &r : NULL, exact,
+                  1 /* the MH kernels test a block's accepted positions in place */);
         done += chunk;
         materialise(p, c->point, st.xref, st.w, c->x);
         anchor(p, c->point, c->x, &st, lpc);

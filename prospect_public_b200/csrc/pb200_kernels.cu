@@ -161,6 +161,115 @@ __device__ __noinline__ BoxProbe<CPL> probe_box_rare(const pb200_problem& p, int
     return probe_box_body<LPC, CPL, true>(p, pt, lt_pt, gl, gi, exact, in, ws);
 }
 
+// ----------------------------------------------------------------------------------------------
+// Tensor-core box filter of the MH kernels (8 lanes per chain, npad = 32: four chains per warp).  A Philox block has up
+// to 4 x 4 = 16 candidate positions per warp (chain x step); their offsets from the reference points are ONE
+// [16 x 32] . [32 x 32] product, 16 `mma.sync.m16n8k8` TF32 instructions, against ~100 instructions per candidate for the
+// FP32 mat-vec.  TF32 is not exact, so the product only FILTERS: a candidate whose every coordinate stays inside the box
+// by more than a rigorous error margin is provably inside for the exact FP32 test as well; the rest (one in ~10^3 on
+// the toy) go through the exact test.  Decisions therefore never depend on the tensor-core arithmetic -- the oracle
+// knows nothing of this filter and stays bit-identical.
+//   margin: operands truncated to TF32 (2^-10 relative each) => |d~ - d| <= 2^-9 sum_k |w_k Lt_kc| <= 2^-9 |w| |Lt_c|
+//   (Cauchy-Schwarz; |Lt_c| = lt_norm, |w| <= sqrt(2 (R0 + 4 s^2 E)), the block's own bound); 2^-8 is used.  The FP32
+//   roundings of the reference point, the box centre and the accumulation (< 2^-20 max(|lo|, |hi|) in all) are taken
+//   off the half-width once, at set-up (2^-19).
+// ----------------------------------------------------------------------------------------------
+struct __align__(16) BoxFilter {
+    float wc[32][24];       // candidate displacements [coordinate][4 * chain + step] (24: conflict-free fragment loads)
+    float xm[4][32];        // FP32 (reference point - box centre) of the warp's four chains: the accumulators' start
+    float2 bfrag[16][32];   // Lt of the warp's point in B-fragment order: [4 kt + nt][lane] = (b0, b1)
+    float mid[32], half[32], ltn[32];     // box centre, shrunk half-width, 2^-8 |Lt_c| per coordinate
+    int ok;                 // all chains of the warp share one point and every box side pair is finite or absent
+};
+
+__device__ __forceinline__ void box_filter_setup(BoxFilter& f, const pb200_problem& p, int pt, int lane) {
+    const int pt0 = __shfl_sync(kFull, pt, 0);
+    bool good = pt == pt0;
+    float mid = 0.0f, half = INFINITY;
+    if (lane < p.n) {
+        const double lo = __ldg(p.lo + lane), hi = __ldg(p.hi + lane);
+        if (isfinite(lo) && isfinite(hi)) {
+            mid = (float)(0.5 * (lo + hi));
+            half = __double2float_rd(0.5 * (hi - lo) - fmax(fabs(lo), fabs(hi)) * 0x1p-19);
+        } else if (!(isinf(lo) && isinf(hi))) {
+            good = false;                       // one-sided box: no bound on |x| for the rounding analysis
+        }
+    }
+    f.mid[lane] = mid;
+    f.half[lane] = half;
+    f.ltn[lane] = __fmul_ru(__ldg(p.lt_norm + (size_t)pt0 * 32 + lane), 0x1p-8f);
+    const float* __restrict__ lt = p.lt_t + (size_t)pt0 * 32 * 32;
+    const int q = lane & 3, row = lane >> 2;
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+            f.bfrag[kt * 4 + nt][lane] = make_float2(__ldg(lt + (kt * 8 + q) * 32 + nt * 8 + row),
+                                                     __ldg(lt + (kt * 8 + q + 4) * 32 + nt * 8 + row));
+    }
+    good = __all_sync(kFull, good);
+    if (lane == 0) f.ok = good ? 1 : 0;
+    __syncwarp();
+}
+
+// `wanted`: this group's candidate k is to be tested (bit k).  Returns true when some wanted candidate of the group
+// is not provably inside.  Called by the whole warp after every lane has staged its part of f.wc / f.xm; out of line
+// so that the 16 accumulators do not join the block's register budget (inlined: 148 bytes of spills in the hot loop).
+// The accumulators start at (reference point - box centre), so the product comes out as the signed distance from the
+// centre and a coordinate costs one FFMA + one compare.
+__device__ __noinline__ bool box_filter_mma(BoxFilter& f, int lane, float wmax, unsigned wanted) {
+    const int gi = lane >> 3;
+    // one word for the warp: bits [4 g, 4 g + 4) = wanted candidates of chain g = rows of the A operand
+    const unsigned w0 = __shfl_sync(kFull, wanted, 0), w1 = __shfl_sync(kFull, wanted, 8),
+                   w2 = __shfl_sync(kFull, wanted, 16), w3 = __shfl_sync(kFull, wanted, 24);
+    const unsigned cand = w0 | (w1 << 4) | (w2 << 8) | (w3 << 12);
+    __syncwarp();
+    // rows `row` / `row + 8` of the product: candidate (chain, step) = (row >> 2, row & 3) / (2 + (row >> 2), row & 3)
+    const int q = lane & 3, row = lane >> 2, c_lo = lane >> 4, c_hi = 2 + (lane >> 4);
+    float d[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float2 lo2 = *reinterpret_cast<const float2*>(&f.xm[c_lo][nt * 8 + 2 * q]);
+        const float2 hi2 = *reinterpret_cast<const float2*>(&f.xm[c_hi][nt * 8 + 2 * q]);
+        d[nt][0] = lo2.x; d[nt][1] = lo2.y; d[nt][2] = hi2.x; d[nt][3] = hi2.y;
+    }
+#pragma unroll
+    for (int kt = 0; kt < 4; ++kt) {
+        const uint32_t a0 = __float_as_uint(f.wc[kt * 8 + q][row]), a1 = __float_as_uint(f.wc[kt * 8 + q][row + 8]),
+                       a2 = __float_as_uint(f.wc[kt * 8 + q + 4][row]), a3 = __float_as_uint(f.wc[kt * 8 + q + 4][row + 8]);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+            const float2 b = f.bfrag[kt * 4 + nt][lane];
+            asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+                         "{%0,%1,%2,%3};"
+                         : "+f"(d[nt][0]), "+f"(d[nt][1]), "+f"(d[nt][2]), "+f"(d[nt][3])
+                         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(__float_as_uint(b.x)), "r"(__float_as_uint(b.y)));
+        }
+    }
+    const float wm_lo = __shfl_sync(kFull, wmax, 8 * c_lo), wm_hi = __shfl_sync(kFull, wmax, 8 * c_hi);
+    bool ok_lo = true, ok_hi = true;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+        const float2 half = *reinterpret_cast<const float2*>(&f.half[nt * 8 + 2 * q]);
+        const float2 ltn = *reinterpret_cast<const float2*>(&f.ltn[nt * 8 + 2 * q]);
+        ok_lo = ok_lo && (__fmaf_rn(ltn.x, wm_lo, fabsf(d[nt][0])) < half.x) &&
+                (__fmaf_rn(ltn.y, wm_lo, fabsf(d[nt][1])) < half.y);
+        ok_hi = ok_hi && (__fmaf_rn(ltn.x, wm_hi, fabsf(d[nt][2])) < half.x) &&
+                (__fmaf_rn(ltn.y, wm_hi, fabsf(d[nt][3])) < half.y);
+    }
+    const bool bad_lo = ((cand >> row) & 1u) != 0u && !ok_lo, bad_hi = ((cand >> (row + 8)) & 1u) != 0u && !ok_hi;
+    const unsigned blo = __ballot_sync(kFull, bad_lo), bhi = __ballot_sync(kFull, bad_hi);
+    __syncwarp();                                   // the staging rows are rewritten by the next block
+    const unsigned mine = gi < 2 ? (blo >> (16 * gi)) : (bhi >> (16 * (gi - 2)));
+    return (mine & 0xFFFFu) != 0u;
+}
+
+template <int LPC, int CPL>
+__device__ __noinline__ bool probe_box_outside(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
+                                               int gi, bool want, BoxIn<CPL> in, float* ws) {
+    return probe_box_body<LPC, CPL, false>(p, pt, lt_pt, gl, gi, want, in, ws).outside;
+}
+
 template <int LPC, int CPL, int REC, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
 __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
@@ -248,10 +357,21 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
 // SM) from being latency-bound.  Box safety for every intermediate point: |w_k| <= |w_0| + step * sum_j |z_j|
 // <= sqrt(R0) + 2 step sqrt(E), hence |w_k|^2 <= 2 (R0 + 4 step^2 E).  Returns true, with nothing committed, when
 // the group must replay the block step by step (bound not provably inside the safe radius).
+//
+// BOXTEST (the MH kernels): at the reference's wide step 2.4 / sqrt(d) the Cauchy-Schwarz radius is no use -- in 30-D
+// it is ~5x tighter than any single face, one accepted step (|s z| ~ 2.4) already leaves it -- so every block was
+// replayed step by step, each accepted step paying a mat-vec, a fresh FP64 safe radius and a re-reference (ncu / probe:
+// 55 % of the K5 kernel).  With BOXTEST a block whose bound fails tests the positions it would accept instead: one
+// FP32 mat-vec per likelihood-accepted step (the state the chain would hold after it, formed by the commit loop's own
+// FMAs), compared with the box; all inside -> the block commits as it stands (no re-reference: w simply keeps
+// growing until the next FP64 anchor), one outside -> replay.  Same predicate as the reference's (inside the box AND
+// likelihood-accept), evaluated on speculative accepts.
 // ----------------------------------------------------------------------------------------------
-template <int LPC, int CPL>
+template <int LPC, int CPL, bool BOXTEST = false>
 __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf, const float (&z)[CPL][4],
-                                           const float (&e)[4], ChainState<CPL>& c) {
+                                           const float (&e)[4], ChainState<CPL>& c, const pb200_problem* p = nullptr,
+                                           int pt = 0, const float* __restrict__ lt_pt = nullptr, int gi = 0,
+                                           float* ws = nullptr, BoxFilter* bf = nullptr) {
     float v[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = 0.0f;
@@ -354,7 +474,48 @@ __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf
     // (sqrt(R0) + 2 s sqrt(E))^2 <= 2 (R0 + 4 s^2 E): no square roots (each would be a MUFU + a slow-path branch)
     const float s2 = __fadd_rn(sf, sf);
     const float half_bnd2 = __fmaf_rn(__fmul_rn(s2, s2), v[14], v[15]);
-    if (any && !(__fadd_rn(half_bnd2, half_bnd2) <= c.m2)) return true;
+    const bool unsafe = any && !(__fadd_rn(half_bnd2, half_bnd2) <= c.m2);
+    if constexpr (!BOXTEST) {
+        if (unsafe) return true;
+    } else {
+        if (__any_sync(kFull, unsafe)) {
+            bool open = unsafe;                     // some accepted position of the group is not yet known to be inside
+            if constexpr (LPC == 8 && CPL == 4) {
+                if (bf != nullptr && bf->ok) {      // (warp-uniform)
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        float w = c.w[r], wk[4];
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            w = acc[k] ? __fmaf_rn(sf, z[r][k], w) : w;
+                            wk[k] = w;
+                        }
+                        *reinterpret_cast<float4*>(&bf->wc[gl + 8 * r][4 * gi]) = make_float4(wk[0], wk[1], wk[2], wk[3]);
+                        bf->xm[gi][gl + 8 * r] = __fsub_rn((float)c.xref[r], bf->mid[gl + 8 * r]);
+                    }
+                    const float wmax = __fmul_ru(__fsqrt_ru(__fadd_ru(half_bnd2, half_bnd2)), 1.0001f);
+                    const unsigned wanted = unsafe ? ((acc[0] ? 1u : 0u) | (acc[1] ? 2u : 0u) | (acc[2] ? 4u : 0u) |
+                                                      (acc[3] ? 8u : 0u)) : 0u;
+                    open = box_filter_mma(*bf, gi * 8 + gl, wmax, wanted);
+                }
+            }
+            if (__any_sync(kFull, open)) {          // the exact FP32 test of what the filter could not settle
+                BoxIn<CPL> in;
+#pragma unroll
+                for (int r = 0; r < CPL; ++r) { in.xref[r] = c.xref[r]; in.wt[r] = c.w[r]; }
+                bool bad = false;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+#pragma unroll
+                    for (int r = 0; r < CPL; ++r) in.wt[r] = acc[k] ? __fmaf_rn(sf, z[r][k], in.wt[r]) : in.wt[r];
+                    const bool want = open && acc[k];
+                    if (__any_sync(kFull, want))
+                        bad = (probe_box_outside<LPC, CPL>(*p, pt, lt_pt, gl, gi, want, in, ws) && want) || bad;
+                }
+                if (bad) return true;
+            }
+        }
+    }
     // scalar pass, branch-free: running loglkl (+0.0 for a rejected step), accept count, and which step (if any)
     // sets a new best
     int kb = -1;
@@ -391,11 +552,12 @@ __device__ __forceinline__ bool block_step(int gl, bool live, float Tf, float sf
 constexpr int kSrcPhilox = 0;   // drawn in place by the warp that uses them
 constexpr int kSrcRing = 2;     // produced by the partner warp into a shared-memory ring (anneal_ws_kernel)
 
-template <int LPC, int CPL, int REC, int SRC, bool EXACT>
+template <int LPC, int CPL, int REC, int SRC, bool EXACT, bool BOXTEST>
 __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl,
                                                 int gi, bool live, uint32_t k0, uint32_t k1, uint32_t chain_id,
                                                 uint32_t t_begin, uint32_t lead, uint32_t n_steps, float Tf, float sf,
-                                                ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring) {
+                                                ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring,
+                                                BoxFilter* bf = nullptr) {
     float z[CPL][4], e[4], zk[CPL];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
 #if PB200_PIPE_RNG
@@ -429,7 +591,7 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
         bool todo = live, cnt_done = false;
         if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && !EXACT && off == 0u && cnt == 4u) {
-            todo = block_step<LPC, CPL>(gl, live, Tf, sf, z, e, c);
+            todo = block_step<LPC, CPL, BOXTEST>(gl, live, Tf, sf, z, e, c, &p, pt, lt_pt, gi, ws, bf);
             if (!__any_sync(kFull, todo)) cnt_done = true;
         }
         // the (up to) four steps of this block, step index k static so that z[.][k] are plain registers (a dynamic
@@ -446,11 +608,13 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
     }
 }
 
-template <int LPC, int CPL, int REC, int SRC = kSrcPhilox, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
+template <int LPC, int CPL, int REC, int SRC = kSrcPhilox, bool EXACT = (REC == PB200_RECORD_ACCEPTED),
+          bool BOXTEST = false>
 __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                           bool live, uint32_t k0, uint32_t k1, uint32_t chain_id, uint32_t t_begin,
                                           uint32_t n_steps, float Tf, float sf, const float (&lam)[CPL],
-                                          ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring) {
+                                          ChainState<CPL>& c, float* ws, RecCursor& rc, Ring& ring,
+                                          BoxFilter* bf = nullptr) {
     asm volatile("" : "+f"(Tf), "+f"(sf));      // keep the FP32 copies live instead of re-converting the doubles
     const float half_s = __fmul_rn(0.5f, sf);
 #pragma unroll
@@ -462,15 +626,15 @@ __device__ __forceinline__ void run_steps(const pb200_problem& p, int pt, const 
     const uint32_t lead = __shfl_sync(kFull, t_begin, lm ? __ffs(lm) - 1 : 0) & 3u;
     if (SRC == kSrcRing || __all_sync(kFull, !live || (t_begin & 3u) == lead)) {
         // (ring: the kernel only pairs a producer with warps whose live chains share one alignment class)
-        run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead, n_steps, Tf,
-                                            sf, c, ws, rc, ring);
+        run_steps_class<LPC, CPL, REC, SRC, EXACT, BOXTEST>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t_begin, lead,
+                                                            n_steps, Tf, sf, c, ws, rc, ring, bf);
     } else {
 #pragma unroll 1
         for (uint32_t a = 0; a < 4u; ++a) {
             const bool mine = live && (t_begin & 3u) == a;
             if (__any_sync(kFull, mine))
-                run_steps_class<LPC, CPL, REC, SRC, EXACT>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
-                                                    n_steps, Tf, sf, c, ws, rc, ring);
+                run_steps_class<LPC, CPL, REC, SRC, EXACT, BOXTEST>(p, pt, lt_pt, gl, gi, mine, k0, k1, chain_id, t_begin, a,
+                                                                    n_steps, Tf, sf, c, ws, rc, ring, bf);
         }
     }
 }
@@ -762,6 +926,14 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
     const float* lt_pt = p.lt_t + (size_t)pt * NPAD * NPAD;
     double* qs = stage[wib][gi];
     float* ws = reinterpret_cast<float*>(qs);
+    // tensor-core box filter of the block path (see box_filter_mma): the geometry of the large batches only
+    constexpr bool kFilter = LPC == 8 && CPL == 4 && REC == PB200_RECORD_NONE && !EXACT;
+    __shared__ __align__(16) BoxFilter filt[kFilter ? kWarpsPerCta : 1];
+    BoxFilter* bf = nullptr;
+    if constexpr (kFilter) {
+        bf = &filt[wib];
+        box_filter_setup(*bf, p, pt, lane);
+    }
 
     float lam[CPL];
     double x[CPL];
@@ -799,8 +971,8 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
     Ring no_ring{};
     while (done < (uint32_t)n_steps) {
         const uint32_t chunk = min((uint32_t)n_steps - done, kResync);
-        run_steps<LPC, CPL, REC, kSrcPhilox, EXACT>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf, sf, lam, c, ws, rc,
-                                 no_ring);
+        run_steps<LPC, CPL, REC, kSrcPhilox, EXACT, true>(p, pt, lt_pt, gl, gi, live, k0, k1, chain_id, t + done, chunk, Tf,
+                                                          sf, lam, c, ws, rc, no_ring, bf);
         done += chunk;
         materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, x);
         anchor<LPC, CPL>(p, pt, gl, x, c, qs);
