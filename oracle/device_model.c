@@ -386,7 +386,9 @@ static void run_steps(const dm_problem *p, int pt, uint64_t seed, uint32_t chain
         const uint32_t t = t_begin + i;
         /* a whole Philox block in the geometries that take four steps per reduction: every geometry of npad = 32, and
            32 lanes with >= 4 coordinates per lane (npad >= 128) */
-        if ((np == 32 || (lpc == 32 && np >= 128)) && !recording && !exact && (t & 3u) == 0u && n_steps - i >= 4u) {
+        /* (thinned recording: blocks with no record step in them as well) */
+        const int no_record = !recording || (rec->mode == 2 && (t % (uint32_t)rec->thin) + 4u < (uint32_t)rec->thin);
+        if ((np == 32 || (lpc == 32 && np >= 128)) && no_record && !exact && (t & 3u) == 0u && n_steps - i >= 4u) {
             const float *zb[4] = {zs + (size_t)i * n, zs + (size_t)(i + 1) * n, zs + (size_t)(i + 2) * n,
                                   zs + (size_t)(i + 3) * n};
             if (block_steps(&R, s, zb, es + i))

@@ -270,6 +270,18 @@ __device__ __noinline__ bool probe_box_outside(const pb200_problem& p, int pt, c
     return probe_box_body<LPC, CPL, false>(p, pt, lt_pt, gl, gi, want, in, ws).outside;
 }
 
+// The thinned record of a step (one step in `thin`): materialise the position and append the row.  Out of line: four
+// inlined copies per Philox block made the hot loop of mh_kernel<.., RECORD_THINNED> miss the instruction cache (ncu:
+// `no_instruction` 1.56 stalls per issue, issue slots 55 % busy against 64 % without recording).
+template <int LPC, int CPL>
+__device__ __noinline__ int32_t record_thinned(const float* __restrict__ lt_pt, int gl, BoxIn<CPL> in, float* ws,
+                                               RecCursor rc, double ll, bool now) {
+    double xn[CPL];
+    materialise<LPC, CPL>(lt_pt, gl, in.xref, in.wt, ws, xn);
+    if (now) record_row<LPC, CPL>(rc, xn, ll, 1, gl);
+    return rc.count;
+}
+
 template <int LPC, int CPL, int REC, bool EXACT = (REC == PB200_RECORD_ACCEPTED)>
 __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const float* __restrict__ lt_pt, int gl, int gi,
                                          bool live, uint32_t tk, float Tf, float sf, const float (&zk)[CPL], float ek,
@@ -339,9 +351,10 @@ __device__ __forceinline__ void one_step(const pb200_problem& p, int pt, const f
     } else if (REC == PB200_RECORD_THINNED) {
         const bool now = live && ((tk + 1) % (uint32_t)rc.thin == 0);
         if (__any_sync(kFull, now)) {
-            double xn[CPL];
-            materialise<LPC, CPL>(lt_pt, gl, c.xref, c.w, ws, xn);
-            if (now) record_row<LPC, CPL>(rc, xn, c.ll, 1, gl);
+            BoxIn<CPL> in;
+#pragma unroll
+            for (int r = 0; r < CPL; ++r) { in.xref[r] = c.xref[r]; in.wt[r] = c.w[r]; }
+            rc.count = record_thinned<LPC, CPL>(lt_pt, gl, in, ws, rc, c.ll, now);
         }
     }
 }
@@ -560,6 +573,8 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
                                                 BoxFilter* bf = nullptr) {
     float z[CPL][4], e[4], zk[CPL];
     uint32_t i = 0;                             // steps done (warp-uniform); this group's step index is t_begin + i
+    uint32_t tmod = 0;                          // (t_begin + i) % thin of this group (thinned recording)
+    if constexpr (REC == PB200_RECORD_THINNED) tmod = t_begin % (uint32_t)rc.thin;
 #if PB200_PIPE_RNG
     // software pipeline (small batches of the 8-lane geometry, where registers do not limit occupancy): the variates of
     // block b + 1 -- independent of the chain state -- are drawn in the shadow of block b's dependent reduce ->
@@ -590,9 +605,19 @@ __device__ __forceinline__ void run_steps_class(const pb200_problem& p, int pt, 
         }
         const uint32_t off = (lead + i) & 3u, cnt = min(4u - off, n_steps - i);
         bool todo = live, cnt_done = false;
-        if (Geometry<LPC, CPL>::kBlockMode && REC == PB200_RECORD_NONE && !EXACT && off == 0u && cnt == 4u) {
-            todo = block_step<LPC, CPL, BOXTEST>(gl, live, Tf, sf, z, e, c, &p, pt, lt_pt, gi, ws, bf);
+        // thinned recording: a block with no record step in it ((tk + 1) % thin == 0 for none of its four steps) takes
+        // the block path as well -- per chain, the chains of a warp need not share their step counters
+        bool mine = live;
+        if constexpr (REC == PB200_RECORD_THINNED) mine = live && (tmod + 4u < (uint32_t)rc.thin);
+        if (Geometry<LPC, CPL>::kBlockMode && REC != PB200_RECORD_ACCEPTED && !EXACT && off == 0u && cnt == 4u &&
+            (REC == PB200_RECORD_NONE || __any_sync(kFull, mine))) {
+            todo = block_step<LPC, CPL, BOXTEST>(gl, mine, Tf, sf, z, e, c, &p, pt, lt_pt, gi, ws, bf);
+            todo = todo || (live && !mine);
             if (!__any_sync(kFull, todo)) cnt_done = true;
+        }
+        if constexpr (REC == PB200_RECORD_THINNED) {
+            tmod += cnt;
+            if (tmod >= (uint32_t)rc.thin) tmod %= (uint32_t)rc.thin;
         }
         // the (up to) four steps of this block, step index k static so that z[.][k] are plain registers (a dynamic
         // k costs a select ladder per coordinate and step); off / cnt are warp-uniform
@@ -927,7 +952,7 @@ mh_kernel(pb200_problem p, pb200_chains ch, int n_steps, uint32_t k0, uint32_t k
     double* qs = stage[wib][gi];
     float* ws = reinterpret_cast<float*>(qs);
     // tensor-core box filter of the block path (see box_filter_mma): the geometry of the large batches only
-    constexpr bool kFilter = LPC == 8 && CPL == 4 && REC == PB200_RECORD_NONE && !EXACT;
+    constexpr bool kFilter = LPC == 8 && CPL == 4 && REC != PB200_RECORD_ACCEPTED && !EXACT;
     __shared__ __align__(16) BoxFilter filt[kFilter ? kWarpsPerCta : 1];
     BoxFilter* bf = nullptr;
     if constexpr (kFilter) {

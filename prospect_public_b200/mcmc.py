@@ -185,10 +185,13 @@ class MetropolisHastings:
             self._samples = engine.Samples(self.problem, self.n_chains, need, mode, self.thin)
             self._used = 0
         else:
-            # grow: copy the rows recorded so far into a larger buffer
-            import torch
+            # grow geometrically (every round of a long run would otherwise re-allocate and copy everything recorded so
+            # far): copy the rows into a buffer of at least twice the size
             old = self._samples
-            cap = old.capacity + need
+            used = int(old.count.max().item())
+            if used + need <= old.capacity:
+                return old
+            cap = max(2 * old.capacity, used + need)
             new = engine.Samples(self.problem, self.n_chains, cap, mode, self.thin)
             new.x[:, :old.capacity] = old.x
             new.loglkl[:, :old.capacity] = old.loglkl

@@ -95,6 +95,46 @@ def _exchange_buffers(rows, world, scalar_len, n_alloc, device):
     return _EXCHANGE[key]
 
 
+_COPY_STREAMS = {}
+
+
+def _copy_stream(device):
+    import torch
+    key = str(device)
+    if key not in _COPY_STREAMS:
+        _COPY_STREAMS[key] = torch.cuda.Stream(device=device)
+    return _COPY_STREAMS[key]
+
+
+class PendingResults:
+    """A device-to-host read in flight (SimulatedAnnealing.results_async).  Keeps the device tensors alive until the
+    copy has completed."""
+
+    def __init__(self, optimiser, iteration, src, host, done):
+        self.optimiser, self.iteration, self._src, self._host, self._done = optimiser, iteration, src, host, done
+        self.d2h_bytes = sum(t.numel() * t.element_size() for t in host.values())
+
+    def get(self):
+        """(bestfit dict as `set_bestfit` builds it, {name: host tensor} of the reduced records)."""
+        self._done.synchronize()
+        sa, h = self.optimiser, self._host
+        acc = h['accepted'].numpy().copy()
+        ran = acc >= 0
+        names = sa.kernel.varying_param_names
+        steps = sa.schedule.steps_per_iteration
+        bx = h['best_x'].numpy()[:, :sa.problem.n].copy() if 'best_x' in h else None
+        sa.bestfit = {
+            'loglkl': np.where(ran, h['best_loglkl'].numpy(), np.inf),
+            'acceptance_rate': np.where(ran, (1 + acc) / (1.0 + steps), np.nan),
+            'accepted_steps': np.where(ran, 1 + acc, 0),
+            'iteration_number': self.iteration,
+            'position': {nm: bx[:, i] for i, nm in enumerate(names)} if bx is not None else {},
+        }
+        reduced = {name[len('reduced/'):]: t.clone() for name, t in h.items() if name.startswith('reduced/')}
+        self._src = self._host = None
+        return sa.bestfit, reduced
+
+
 class SimulatedAnnealing:
     """optimise_settings (arrays over the P profile points; P = 1 for a global optimisation):
         initial_position [P, n] (varying order), covmat [P, n, n], current_best_loglkl [P],
@@ -190,6 +230,33 @@ class SimulatedAnnealing:
             'position': {nm: bx[:, i] for i, nm in enumerate(names)} if bx is not None else {},
         }
         return self.bestfit
+
+    def results_async(self, iteration=None, reduced=None):
+        """Start the device-to-host read of one iteration's records (what `set_bestfit` returns) and, optionally, of the
+        tensors of `reduce_over_iterations()`, on a copy stream into pinned host memory, and return at once.
+        `PendingResults.get()` waits for the copy.  A caller with several independent jobs (the repetitions of a
+        reanneal, bench.py's end-to-end arm) builds and launches job k + 1 while job k is still on the device and its
+        results are on their way back; nothing in the kernels changes."""
+        import torch
+        k = self.iterations_done - 1 if iteration is None else iteration
+        r, dev = self.records, self.problem.device
+        src = {'accepted': r.accepted[k], 'best_loglkl': r.best_loglkl[k]}
+        if r.best_x is not None:
+            src['best_x'] = r.best_x[k]
+        for name, t in (reduced or {}).items():
+            src['reduced/' + name] = t
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        cs = _copy_stream(dev)
+        host = {}
+        with torch.cuda.stream(cs):
+            cs.wait_event(ready)
+            for name, t in src.items():
+                host[name] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+                host[name].copy_(t, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(cs)
+        return PendingResults(self, k, src, host, done)
 
     def get_next_iteration_settings(self):
         """The settings the next iteration will run with (already computed on the device, optimiser.py:87-162)."""

@@ -440,6 +440,54 @@ def test_results_do_not_depend_on_the_number_of_ranks(tmp_path, monkeypatch, wor
     assert empty_ranks == (2 if world == 8 else 0)
 
 
+def test_results_async_equals_set_bestfit_with_two_jobs_in_flight(tmp_path):
+    """SimulatedAnnealing.results_async: the records of job k come back through pinned memory on the copy stream while
+    job k + 1 is built, uploaded and launched; what `get()` returns is what `set_bestfit` / `reduce_over_iterations`
+    return for that job, and a job's device records are not disturbed by its successors."""
+    from prospect_public_b200.initialise import initialise_optimiser
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.optimiser import (SimulatedAnnealing, get_initial_step_size_change,
+                                                get_temperature_change)
+    paths, k = _inputs(tmp_path, 20)
+    cfg = Configuration(annealing_yaml(paths, str(tmp_path / 'o'), write=False, values=[-0.8, 0.4, 1.9],
+                                       repetitions=40, max_iterations=4, steps_per_iteration=120))
+    kernel = initialise_kernel(cfg.kernel, None, 0)
+    starts, values = initialise_optimiser(cfg, kernel)
+    n_iter = 4
+
+    def job(seed):
+        return SimulatedAnnealing(cfg, kernel, {
+            'current_best_loglkl': starts.initial_loglkl, 'initial_position': starts.positions, 'covmat': starts.covmats,
+            'temperature': 0.1, 'temperature_change': get_temperature_change(cfg), 'step_size': 0.1,
+            'step_size_change': get_initial_step_size_change(cfg), 'iteration_number': 0, 'repetitions': 40,
+            'fixed_param_val': values, 'max_rows': n_iter, 'seed': seed})
+
+    expect = []
+    for seed in range(5):                                        # the plain, synchronous way
+        sa = job(seed)
+        sa.run_schedule(n_iter)
+        red = sa.reduce_over_iterations()
+        bf = sa.set_bestfit(n_iter - 1)
+        expect.append((bf, {name: t.cpu() for name, t in red.items()}))
+    got, pending = [], None
+    for seed in range(5):                                        # two jobs in flight
+        sa = job(seed)
+        sa.run_schedule(n_iter)
+        nxt = sa.results_async(n_iter - 1, sa.reduce_over_iterations())
+        if pending is not None:
+            got.append(pending.get())
+        pending = nxt
+    got.append(pending.get())
+    assert pending.d2h_bytes > 0
+    for (bf_a, red_a), (bf_b, red_b) in zip(expect, got):
+        for key in ('loglkl', 'acceptance_rate', 'accepted_steps'):
+            assert np.array_equal(bf_a[key], bf_b[key])
+        assert bf_a['position'].keys() == bf_b['position'].keys()
+        assert all(np.array_equal(bf_a['position'][nm], bf_b['position'][nm]) for nm in bf_a['position'])
+        assert red_a.keys() == red_b.keys() and all(torch.equal(red_a[nm], red_b[nm]) for nm in red_a)
+    assert not np.array_equal(expect[0][0]['loglkl'], expect[1][0]['loglkl'])          # (the jobs do differ)
+
+
 def test_interrupted_mcmc_job_resumes_to_identical_chain_files(tmp_path):
     """`prospect <folder>` for jobtype mcmc (tasks/mcmc_task.py:71-81): a job stopped after its first round and
     resumed from the chain files it left is, step for step, the job that ran three rounds without interruption --
