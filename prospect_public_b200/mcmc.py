@@ -129,15 +129,20 @@ class MetropolisHastings:
         self.batch = engine.ChainBatch(self.problem, x0, 0, chain_id=ids, temperature=config_mcmc.temperature,
                                        step_size=config_mcmc.step_size,
                                        steps_done=mcmc_args.get('steps_done', 0))
-        # Prior-box test: deferred behind the whitened safe radius by default (re-referencing every few accepted steps
-        # when steps are wide).  `exact_box=True` tests the box at every likelihood-accepted step instead -- same
-        # decisions; it was the faster form for wide steps until the position mat-vec of multi-chain warps became
-        # selective (materialise_selected): measured at 65 536 chains, step 2.4 / sqrt(d): 7.0e9 exact vs 8.8e9 deferred
-        # chain-steps/s.  Recording accepted points always materialises every accepted step.
+        # Prior-box test: deferred by default -- a Philox block whose four steps provably stay inside the whitened safe
+        # radius needs no test at all; otherwise the positions the block would accept are tested in place (a TF32
+        # tensor-core filter in front of the exact FP32 mat-vec, see box_filter_mma in csrc/pb200_kernels.cu).
+        # `exact_box=True` materialises and tests every likelihood-accepted step instead -- same decisions; measured at
+        # 65 536 chains, step 2.4 / sqrt(d): 7.0e9 exact vs 1.12e10 deferred chain-steps/s.  Recording accepted points
+        # always materialises every accepted step.
         exact = mcmc_args.get('exact_box', 'auto')
         if exact == 'auto':
             exact = False
         self.exact_box = bool(exact)
+        # lanes per chain: chosen from the size of the WHOLE job (config N_chains), not of this rank's share, so that a
+        # chain's arithmetic -- and with it every chain file -- does not depend on the number of GPUs
+        self.lanes = int(mcmc_args.get('lanes_per_chain', 0)) or engine.choose_lanes(
+            self.problem.npad, max(b, int(mcmc_args.get('n_chains_global', config_mcmc.N_chains or b))))
         self.record = mcmc_args.get('record', 'accepted')
         self.thin = int(mcmc_args.get('thin', 1))
         self._prior = prior
@@ -206,7 +211,8 @@ class MetropolisHastings:
     def run_steps(self, steps_per_iteration):
         from . import engine
         smp = self._ensure_samples(steps_per_iteration)
-        acc = engine.mh_run(self.problem, self.batch, steps_per_iteration, self.seed, smp, exact_box=self.exact_box)
+        acc = engine.mh_run(self.problem, self.batch, steps_per_iteration, self.seed, smp, lanes=self.lanes,
+                            exact_box=self.exact_box)
         self.accepted += acc.cpu().numpy()
         self.steps += steps_per_iteration
 

@@ -189,7 +189,10 @@ class SimulatedAnnealing:
         self.keep_positions = keep_positions
         self.records = engine.Records(self.problem, self.batch.n_chains, self.max_rows, keep_positions,
                                       n_alloc=self.b_alloc)
-        self.lanes = int(s.get('lanes_per_chain', 0))
+        # lanes per chain: chosen from the size of the WHOLE job, not of this rank's shard, so that a chain's arithmetic
+        # (the order of its FP32 reductions) -- and with it every record -- does not depend on the number of GPUs
+        self.lanes = int(s.get('lanes_per_chain', 0)) or engine.choose_lanes(self.problem.npad,
+                                                                             self.n_points * self.reps)
         self.seed = int(s.get('seed', 0))
         self.step_counter = 0                 # MH steps taken so far by every live chain (they advance in lockstep)
         self.iterations_done = int(s.get('iteration_number', 0))

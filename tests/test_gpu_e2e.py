@@ -391,13 +391,15 @@ def test_ignore_prior_lifts_the_box(tmp_path):
         assert outside == expect_outside
 
 
-@pytest.mark.parametrize('world', [2, 3, 8])
-def test_results_do_not_depend_on_the_number_of_ranks(tmp_path, monkeypatch, world):
+@pytest.mark.parametrize('world,reps', [(2, 6), (3, 6), (8, 6), (8, 400)])
+def test_results_do_not_depend_on_the_number_of_ranks(tmp_path, monkeypatch, world, reps):
     """N-invariance of the sharded job, with the ranks emulated one after the other on one GPU: every rank of a
     `world`-rank job builds its own SimulatedAnnealing (its shard of the point x repetition grid, its global chain
     ids), runs the schedule, and the shards are assembled by global chain index -- bit-identical to the single-rank
     run.  5 points x 6 repetitions: 2 / 3 ranks shard by point, 8 ranks split the repetitions and leave two ranks
-    WITHOUT chains (fewer repetitions than GPUs).  (The exchange itself -- NCCL / peer-memory stores -- is covered by
+    WITHOUT chains (fewer repetitions than GPUs).  5 x 400 = 2000 chains: the job as a whole runs with 16 lanes per
+    chain, a 250-chain shard on its own would pick 32 -- the geometry (hence the order of the FP32 reductions) is chosen
+    from the size of the whole job, so the shards still reproduce the single-rank run.  (The exchange itself -- NCCL / peer-memory stores -- is covered by
     test_fused_exchange_fills_every_ranks_buffer, the gloo tests and scripts/multi_gpu_check.py on real ranks.)"""
     from prospect_public_b200 import optimiser as opt_mod
     from prospect_public_b200.distributed import global_chain_index
@@ -407,10 +409,10 @@ def test_results_do_not_depend_on_the_number_of_ranks(tmp_path, monkeypatch, wor
                                                 get_temperature_change)
     paths, k = _inputs(tmp_path, 20)
     cfg = Configuration(annealing_yaml(paths, str(tmp_path / 'o'), write=False, values=[-0.8, -0.1, 0.4, 1.1, 1.9],
-                                       repetitions=6, max_iterations=3, steps_per_iteration=90))
+                                       repetitions=reps, max_iterations=3, steps_per_iteration=90))
     kernel = initialise_kernel(cfg.kernel, None, 0)
     starts, values = initialise_optimiser(cfg, kernel)
-    n_pts, reps, n_iter = 5, 6, 3
+    n_pts, n_iter = 5, 3
     settings = {'current_best_loglkl': starts.initial_loglkl, 'initial_position': starts.positions,
                 'covmat': starts.covmats, 'temperature': 0.1, 'temperature_change': get_temperature_change(cfg),
                 'step_size': 0.1, 'step_size_change': get_initial_step_size_change(cfg), 'iteration_number': 0,
@@ -437,7 +439,10 @@ def test_results_do_not_depend_on_the_number_of_ranks(tmp_path, monkeypatch, wor
             assert np.array_equal(part[key], single[key][:, ids]), (key, rank)
         assert np.array_equal(part['best_x'], single['best_x'][:, ids]) and np.array_equal(part['final_x'], single['final_x'][ids])
     assert np.all(seen == 1)                       # every chain ran on exactly one rank
-    assert empty_ranks == (2 if world == 8 else 0)
+    assert empty_ranks == (2 if (world, reps) == (8, 6) else 0)
+    if reps == 400:
+        from prospect_public_b200 import engine
+        assert engine.choose_lanes(32, n_pts * reps) == 16 and engine.choose_lanes(32, n_pts * reps // world) == 32
 
 
 def test_results_async_equals_set_bestfit_with_two_jobs_in_flight(tmp_path):
