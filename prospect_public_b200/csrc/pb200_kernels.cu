@@ -39,6 +39,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -1264,6 +1265,26 @@ static bool use_wide_path(const pb200_problem* prob, const pb200_chains* chains)
     return true;
 }
 
+constexpr int kWideMaxSub = 8;
+#ifndef PB200_WIDE_SUB_DEFAULT
+#define PB200_WIDE_SUB_DEFAULT 4
+#endif
+// Side streams of the wide pipeline's sub-batches (created once per device, never destroyed).
+static int wide_sub_streams(int n, cudaStream_t* out) {
+    static std::mutex mu;
+    static cudaStream_t pool[16][kWideMaxSub - 1] = {};
+    int dev = 0;
+    if (check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return 1;
+    if (dev < 0 || dev >= 16) return fail("wide path: device index out of range");
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n; ++i) {
+        if (!pool[dev][i] && check_cuda(cudaStreamCreateWithFlags(&pool[dev][i], cudaStreamNonBlocking), "cudaStreamCreate"))
+            return 1;
+        out[i] = pool[dev][i];
+    }
+    return 0;
+}
+
 // Annealing iterations of a wide problem as three launches each (pb200_wide.cuh).  Scratch memory is stream-ordered
 // (cudaMallocAsync on `st`), so the call stays asynchronous and owns nothing afterwards.
 template <int NPAD>
@@ -1293,7 +1314,6 @@ static int anneal_launch_wide(const pb200_problem& prob, const pb200_chains& cha
     WideWs ws{(double*)(mem + o_base), (float*)(mem + o_hi), (float*)(mem + o_lo), (double*)(mem + o_bx),
               (double*)(mem + o_q), (double*)(mem + o_v), (int32_t*)(mem + o_nacc), (int32_t*)(mem + o_ran)};
     const int n_rt = (reps + kWideTileRows - 1) / kWideTileRows, n_at = (reps + kAnchorTileRows - 1) / kAnchorTileRows;
-    const int steps_blocks = (chains.n_chains + kWarpsPerCta - 1) / kWarpsPerCta;
     const size_t anchor_smem = sizeof(double) * kAnchorStages * (kAnchorTileRows * kWideKChunk + kWideKChunk * kAnchorTileCols);
     static bool attr_set[2] = {false, false};
     if (!attr_set[NPAD == 256]) {
@@ -1315,36 +1335,71 @@ static int anneal_launch_wide(const pb200_problem& prob, const pb200_chains& cha
         marks.push_back(e);
     };
     mark();
+    const WideSub all{0, P};
     wide_check_layout_kernel<<<1, 256, 0, st>>>(chains, P);
     wide_residual_kernel<NPAD><<<148 * 2, 256, 0, st>>>(prob, chains, ws);
-    wide_anchor_kernel<NPAD><<<2 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x3);
+    wide_anchor_kernel<NPAD><<<2 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x3, all);
     mark();
     // producer warps pay while the chain warps alone leave the schedulers short of instruction streams (measured:
     // profiles/README.md); PB200_WIDE_WS=0 / 1 forces the choice
     bool ws_steps = chains.n_chains <= 148 * 4;          // up to one pair per scheduler
     if (const char* env = std::getenv("PB200_WIDE_WS")) ws_steps = env[0] != '0';
-    const int ws_blocks = (chains.n_chains + kWideWsPairs - 1) / kWideWsPairs;
+    // Sub-batches of profile points on parallel streams: the steps kernel is latency-bound (its time hardly depends
+    // on the number of chains), the two GEMMs are short and throughput-bound, so with the batch cut into groups of
+    // points the GEMMs of one group can run in the shadow of another group's steps.  Same results (chains are
+    // independent).  Measured (scripts/r02_wide_sub.sh, ms per 20-iteration call, 1 / 2 / 4 / 8 groups): 1024 chains
+    // 3.85 / 3.66 / 3.96 / 3.93 (8 points), 3.77 / 3.88 / 3.92 / 3.97 (16 points): nothing to gain, the steps kernels
+    // of the groups share the same schedulers; 4096 chains 12.96 / 12.36 / 11.92 / 12.06: +9 %.  So: four groups from
+    // 4096 chains up, one below.  PB200_WIDE_SUB=n forces the number of groups.
+    int n_sub = (P >= 2 && chains.n_chains >= 4096 && !timing) ? std::min(P, PB200_WIDE_SUB_DEFAULT) : 1;
+    if (const char* env = std::getenv("PB200_WIDE_SUB"))
+        if (std::atoi(env) >= 1) n_sub = std::min(std::min(P, kWideMaxSub), std::atoi(env));
+    if (!mma.enabled) n_sub = 1;            // the SIMT position GEMM works on the whole batch
+    cudaStream_t streams[kWideMaxSub];
+    streams[0] = st;
+    if (n_sub > 1 && wide_sub_streams(n_sub - 1, streams + 1)) return 1;
+    cudaEvent_t fork = nullptr, join[kWideMaxSub] = {};
+    if (n_sub > 1) {
+        if (check_cuda(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming), "cudaEventCreate")) return 1;
+        cudaEventRecord(fork, st);
+        for (int g = 1; g < n_sub; ++g) cudaStreamWaitEvent(streams[g], fork, 0);
+    }
+    auto sub_of = [&](int g) { return WideSub{(int)((long long)P * g / n_sub), (int)((long long)P * (g + 1) / n_sub - (long long)P * g / n_sub)}; };
+    auto launch_steps = [&](int g, int flags, int it, bool ring) {
+        const WideSub sub = sub_of(g);
+        const int nb = sub.np * reps;
+        if (ring)
+            wide_steps_ws_kernel<CPL><<<(nb + kWideWsPairs - 1) / kWideWsPairs, 64 * kWideWsPairs, 0, streams[g]>>>(
+                prob, chains, sched, rec, ws, k0, k1, flags, it, n_iter, progress, peers, sub);
+        else
+            wide_steps_kernel<CPL><<<(nb + kWarpsPerCta - 1) / kWarpsPerCta, 32 * kWarpsPerCta, 0, streams[g]>>>(
+                prob, chains, sched, rec, ws, k0, k1, flags, it, n_iter, progress, peers, sub);
+    };
     for (int it = 0; it < n_iter; ++it) {
         const int flags = (it > 0 ? kWideFinish : 0) | kWideRun;
-        if (ws_steps)
-            wide_steps_ws_kernel<CPL><<<ws_blocks, 64 * kWideWsPairs, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
-                                                                               flags, it, n_iter, progress, peers);
-        else
-            wide_steps_kernel<CPL><<<steps_blocks, 32 * kWarpsPerCta, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
-                                                                               flags, it, n_iter, progress, peers);
-        mark();
-        if (mma.enabled) {
-            if (wide_mma_launch<NPAD>(prob, chains, ws, reps, mma, st)) return 1;
-        } else {
-            wide_materialise_simt_kernel<NPAD><<<2 * P * n_rt, NPAD, 0, st>>>(prob, chains, ws, reps);
+        for (int g = 0; g < n_sub; ++g) {
+            const WideSub sub = sub_of(g);
+            launch_steps(g, flags, it, ws_steps);
+            mark();
+            if (mma.enabled) {
+                if (wide_mma_launch<NPAD>(prob, chains, ws, reps, mma, streams[g], sub)) return 1;
+            } else {                // (SIMT position GEMM: whole batch, n_sub is 1 -- see below)
+                wide_materialise_simt_kernel<NPAD><<<2 * P * n_rt, NPAD, 0, st>>>(prob, chains, ws, reps);
+            }
+            mark();
+            wide_anchor_kernel<NPAD><<<3 * sub.np * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, streams[g]>>>(
+                prob, chains, ws, reps, 0x7, sub);
+            mark();
         }
-        mark();
-        wide_anchor_kernel<NPAD><<<3 * P * n_at * (NPAD / kAnchorTileCols), 256, anchor_smem, st>>>(prob, chains, ws, reps, 0x7);
-        mark();
     }
-    wide_steps_kernel<CPL><<<steps_blocks, 32 * kWarpsPerCta, 0, st>>>(prob, chains, sched, rec, ws, k0, k1,
-                                                                        kWideFinish | kWideLast, n_iter, n_iter,
-                                                                        progress, peers);
+    for (int g = 0; g < n_sub; ++g) launch_steps(g, kWideFinish | kWideLast, n_iter, false);
+    for (int g = 1; g < n_sub; ++g) {
+        if (check_cuda(cudaEventCreateWithFlags(&join[g], cudaEventDisableTiming), "cudaEventCreate")) return 1;
+        cudaEventRecord(join[g], streams[g]);
+        cudaStreamWaitEvent(st, join[g], 0);
+        cudaEventDestroy(join[g]);          // (released once it has completed)
+    }
+    if (fork) cudaEventDestroy(fork);
     if (check_cuda(cudaGetLastError(), "wide annealing launches")) return 1;
     if (timing && marks.size() >= 2) {
         cudaStreamSynchronize(st);

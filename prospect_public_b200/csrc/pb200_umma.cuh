@@ -74,7 +74,7 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
 template <int NPAD>
 __global__ void __launch_bounds__(128, 1)
 wide_materialise_mma_kernel(pb200_chains ch, WideWs ws, const double* __restrict__ mu, int n_points, int reps,
-                            int box_rows,
+                            int box_rows, WideSub sub,
                             const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
                             const __grid_constant__ CUtensorMap map_lt_hi,
                             const __grid_constant__ CUtensorMap map_lt_lo) {
@@ -87,8 +87,8 @@ wide_materialise_mma_kernel(pb200_chains ch, WideWs ws, const double* __restrict
     int bid = blockIdx.x;
     const int nt = bid % NT; bid /= NT;
     const int mt = bid % n_mt; bid /= n_mt;
-    const int pt = bid % n_points;
-    const int which = bid / n_points;
+    const int pt = sub.p0 + bid % sub.np;
+    const int which = bid / sub.np;
     const uint32_t smem0 = (smem_addr(umma_smem_raw) + 1023u) & ~1023u;          // swizzle-128B atoms: 1024-byte aligned
     const uint32_t full0 = smem_addr(&bars[0]), empty0 = smem_addr(&bars[S]), done = smem_addr(&bars[2 * S]);
     if (tid == 0) {
@@ -258,11 +258,11 @@ static int wide_mma_prepare(const pb200_problem& prob, const pb200_chains& chain
 
 template <int NPAD>
 static int wide_mma_launch(const pb200_problem& prob, const pb200_chains& chains, const WideWs& ws, int reps,
-                           const WideMma& mma, cudaStream_t st) {
+                           const WideMma& mma, cudaStream_t st, WideSub sub) {
     const int n_mt = (reps + kMmaTileM - 1) / kMmaTileM;
-    const int grid = 2 * prob.n_points * n_mt * (NPAD / kMmaTileN);
+    const int grid = 2 * sub.np * n_mt * (NPAD / kMmaTileN);
     wide_materialise_mma_kernel<NPAD><<<grid, 128, kMmaSmemBytes, st>>>(chains, ws, prob.mu, prob.n_points, reps,
-                                                                        mma.box_rows,
+                                                                        mma.box_rows, sub,
                                                                         mma.w_hi, mma.w_lo, mma.lt_hi, mma.lt_lo);
     return check_cuda(cudaGetLastError(), "wide_materialise_mma_kernel launch");
 }

@@ -45,6 +45,20 @@ struct WideWs {
     int32_t* ran;       // [B]           1: the chain ran that iteration
 };
 
+// A launch of the wide pipeline covers the profile points [p0, p0 + np) of the batch (all their repetitions): the
+// per-iteration pipeline of a batch is issued as several such sub-batches on parallel streams, so that the position and
+// anchor GEMMs of one run in the shadow of another's (latency-bound) steps kernel.  Chains are independent, hence the
+// same results bit for bit.
+struct WideSub {
+    int p0, np;
+    // chain of local index j in this sub-batch (chain = rep * P + point), -1 past its end
+    __device__ __forceinline__ int chain_of(int j, int n_points, int n_chains) const {
+        const int reps = n_chains / n_points;
+        if (j >= np * reps) return -1;
+        return (j / np) * n_points + p0 + j % np;
+    }
+};
+
 constexpr int kWideFinish = 1;   // prologue: set_bestfit / records / next settings of the iteration run by the previous launch
 constexpr int kWideRun = 2;      // run the S steps of the next iteration
 constexpr int kWideLast = 4;     // last launch of the call: completion of the peer exchange
@@ -342,12 +356,12 @@ template <int CPL>
 __global__ void __launch_bounds__(32 * kWarpsPerCta)
 wide_steps_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, WideWs ws, uint32_t k0,
                   uint32_t k1, int flags, int it, int n_iter, uint32_t* __restrict__ progress,
-                  const __grid_constant__ pb200_peers peers) {
+                  const __grid_constant__ pb200_peers peers, WideSub sub) {
     constexpr int NPAD = 32 * CPL;
     __shared__ __align__(16) double stage[kWarpsPerCta][NPAD];
     const int wib = threadIdx.x >> 5;
-    const int chain = blockIdx.x * kWarpsPerCta + wib;
-    if (chain >= ch.n_chains) return;
+    const int chain = sub.chain_of(blockIdx.x * kWarpsPerCta + wib, p.n_points, ch.n_chains);
+    if (chain < 0) return;
     Ring none{};
     wide_steps_body<CPL, kSrcPhilox>(p, ch, s, rec, ws, k0, k1, flags, it, n_iter, progress, peers, chain, stage[wib],
                                      none);
@@ -364,7 +378,7 @@ template <int CPL>
 __global__ void __launch_bounds__(64 * kWideWsPairs, 8 / kWideWsPairs)
 wide_steps_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_records rec, WideWs ws, uint32_t k0,
                      uint32_t k1, int flags, int it, int n_iter, uint32_t* __restrict__ progress,
-                     const __grid_constant__ pb200_peers peers) {
+                     const __grid_constant__ pb200_peers peers, WideSub sub) {
     constexpr int NPAD = 32 * CPL;
     __shared__ __align__(16) unsigned char slots[kWideWsPairs][kRingDepth][ring_slot_bytes<CPL>()];
     __shared__ __align__(16) double stage[kWideWsPairs][NPAD];
@@ -376,8 +390,8 @@ wide_steps_ws_kernel(pb200_problem p, pb200_chains ch, pb200_schedule s, pb200_r
         for (int i = 0; i < 2 * kRingDepth; ++i) mbar_init(smem_addr(&bars[threadIdx.x][i]), 32u);
         stop[threadIdx.x] = 0u;
     }
-    const int chain = blockIdx.x * kWideWsPairs + pair;
-    const bool idle = chain >= ch.n_chains;
+    const int chain = sub.chain_of(blockIdx.x * kWideWsPairs + pair, p.n_points, ch.n_chains);
+    const bool idle = chain < 0;
     const int cc = idle ? ch.n_chains - 1 : chain;
     // the step counter the chain will have AFTER the finish phase of this launch (both warps of the pair compute it
     // from the same loads, before the consumer rewrites the chain state)
@@ -481,7 +495,7 @@ constexpr int kAnchorStages = 4;
 
 template <int NPAD>
 __global__ void __launch_bounds__(256, 2)
-wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cls_mask) {
+wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cls_mask, WideSub sub) {
     constexpr int TM = kAnchorTileRows, TN = kAnchorTileCols, KC = kWideKChunk, NCT = NPAD / TN, ST = kAnchorStages;
     constexpr int kStageDoubles = TM * KC + KC * TN;       // residual chunk [TM][KC] + matrix chunk [KC][TN]
     extern __shared__ __align__(16) unsigned char wide_smem[];
@@ -490,8 +504,8 @@ wide_anchor_kernel(pb200_problem p, pb200_chains ch, WideWs ws, int reps, int cl
     int bid = blockIdx.x;
     const int ct = bid % NCT; bid /= NCT;
     const int rt = bid % n_rt; bid /= n_rt;
-    const int pt = bid % P;
-    const int cls_idx = bid / P;
+    const int pt = sub.p0 + bid % sub.np;
+    const int cls_idx = bid / sub.np;
     int cls = 0;
     for (int seen = 0; cls < 3; ++cls)
         if ((cls_mask >> cls) & 1) { if (seen == cls_idx) break; ++seen; }
