@@ -280,6 +280,23 @@ def test_wide_path_tensor_core_positions(d, reps, monkeypatch):
     _check_against_per_iteration_replay(hp, out, x0, point, cb, s, 3, list(range(0, b, max(1, b // 24))) + [b - 1])
 
 
+@pytest.mark.parametrize('groups', ['2', '3', '8'])
+def test_wide_path_sub_batches_on_parallel_streams_change_nothing(groups, monkeypatch):
+    """PB200_WIDE_SUB: the per-iteration pipeline of the wide path issued as groups of profile points on parallel
+    streams (the default from 4096 chains up).  Chains are independent, so every record -- positions from the tensor-core
+    GEMM included -- equals the single-stream run bit for bit; 5 points in 2 / 3 / 5 (8 requested) uneven groups."""
+    monkeypatch.setenv('PB200_WIDE_MMA', '1')
+    hp, starts, init_ll = _spd_profile_problem(128, 5)
+    s = _toy_sched(S=37, s0=2.4 / np.sqrt(128))
+    monkeypatch.setenv('PB200_WIDE_SUB', '1')
+    one, *_ = _wide_mma_run(hp, starts, init_ll, 20, s, 4)
+    monkeypatch.setenv('PB200_WIDE_SUB', groups)
+    many, *_ = _wide_mma_run(hp, starts, init_ll, 20, s, 4)
+    assert (one['accepted'] >= 0).all()
+    for key in one:
+        assert np.array_equal(one[key], many[key]), key
+
+
 def test_k4_shape_256d_8_points_x_128_repetitions():
     """BASELINE.json configs[3] at its per-GPU shape: 256-D synthetic SPD Gaussian profile, 8 points x 128
     repetitions = 1024 chains, 20 iterations x 250 steps through the default path (wide pipeline, tensor-core
