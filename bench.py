@@ -121,16 +121,16 @@ class ClockSampler(threading.Thread):
 # the CPU side: the UNMODIFIED reference through its own scheduler (oracle/_ref), or -- only if that copy is missing
 # -- the pinned port (oracle/reference_port.py)
 # ------------------------------------------------------------------------------------------------------------------
-def reference_job_yaml(workload, tmp, tag, cores, kw):
-    """The yaml of a bounded sample of `workload` for the reference: one chain per host core (global30) or the 32
-    profile values x 1 repetition (profile30*), ALL 20 iterations."""
+def reference_job_yaml(workload, tmp, tag, cores, kw, chains_per_core=1):
+    """The yaml of a bounded sample of `workload` for the reference: `chains_per_core` chains per host core (global30) or
+    the 32 profile values x 1 repetition (profile30*), ALL 20 iterations."""
     from prospect_public_b200.toy import annealing_yaml
     paths, _, _ = toy_inputs(os.path.join(tmp, 'in_' + tag))
     prof = {k: v for k, v in kw.items() if k not in ('repetitions', 'values')}
     prof.update(plot_profile=False, plot_schedule=False)
     if workload == 'global30':
-        jobtype, prof['repetitions'] = 'global_optimisation', cores
-        sample = f'{cores} repetitions (one chain per host core) x 20 iterations x 250 steps'
+        jobtype, prof['repetitions'] = 'global_optimisation', cores * chains_per_core
+        sample = f'{cores * chains_per_core} repetitions ({chains_per_core} per host core) x 20 iterations x 250 steps'
     else:
         jobtype, prof['repetitions'], prof['values'] = 'profile', 1, 'np.linspace(-1.0, 2.0, 32)'
         sample = '32 profile values x 1 repetition x 20 iterations x 250 steps'
@@ -139,11 +139,11 @@ def reference_job_yaml(workload, tmp, tag, cores, kw):
     return y, sample
 
 
-def reference_rate(workload, tmp, tag, kw, cores, analyse=False):
+def reference_rate(workload, tmp, tag, kw, cores, analyse=False, chains_per_core=1):
     """(chain-steps/s, seconds, kind, sample, extra) of one bounded reference job on `cores` processes."""
     from oracle import ref_harness as rh
     if rh.available():
-        y, sample = reference_job_yaml(workload, tmp, tag, cores, kw)
+        y, sample = reference_job_yaml(workload, tmp, tag, cores, kw, chains_per_core)
         out = rh.run_reference(y, 20, mode='threaded' if cores > 1 else 'serial', num_processes=cores, analyse=analyse)
         extra = {'seconds_to_profile': out.get('seconds_to_profile'), 'tasks': out['n_optimise_tasks']}
         return out['chain_steps'] / out['seconds'], out['seconds'], 'reference', sample + \
@@ -408,7 +408,7 @@ def k5_record(world, rank, dev, barrier, dist, torch, engine):
         out[key] = {'value': rate, 'unit': UNIT, 'ms_per_round': ms,
                     'acceptance_rate': float(s.accepted.sum()) / ((hi - lo) * rounds_steps * (n_rounds + 1))}
         if key == 'no_recording' and world == 1:
-            out['roofline'] = stream_roofline(32, total * rounds_steps, ms, 'mh_kernel (8 lanes per chain, exact box test)')
+            out['roofline'] = stream_roofline(32, total * rounds_steps, ms, 'mh_kernel (8 lanes per chain; prior box: in-block test, TF32 mma.sync filter + exact FP32 mat-vec)')
         del s
     out['value'] = out['no_recording']['value']
     return out
@@ -473,7 +473,7 @@ def main():
     roofline = None
     if world == 1:
         roofline = stream_roofline(sa0.problem.npad, h.b_local * h.n_iter * h.steps, res['kernel_ms_per_job'], kernel_name,
-                                   'r01_final_global30_lanes8.json' if headline == 'global30' else None)
+                                   'r02_global30_lanes8.json' if headline == 'global30' else None)
         if sa0.problem.npad == 32:
             # measured instruction-pipe bound of this kernel (ncu opcode mix x the per-scheduler
             # throughputs of scripts/pipe_probe.cu -> ~50 FMA-pipe cycles per chain-step) at 1965 MHz
@@ -547,7 +547,7 @@ def main():
         cores = os.cpu_count() or 1
         tmp = tempfile.mkdtemp(prefix='pb200_cpu_')
         kw = workload_profile_kw(headline, 1)[1]
-        rate, secs, kind, sample, extra = reference_rate(headline, tmp, 'cb', kw, cores)
+        rate, secs, kind, sample, extra = reference_rate(headline, tmp, 'cb', kw, cores, chains_per_core=8)   # ~10 s
         cpu_baseline = {'value': rate, 'unit': UNIT, 'cores': cores, 'kind': kind,
                         'sample': f'{sample}; {secs:.1f} s'}
 
