@@ -187,7 +187,9 @@ class MetropolisHastings:
         mode = capi.RECORD_ACCEPTED if self.record == 'accepted' else capi.RECORD_THINNED
         need = n_steps + 1 if mode == capi.RECORD_ACCEPTED else n_steps // self.thin + 1
         if self._samples is None:
-            self._samples = engine.Samples(self.problem, self.n_chains, need, mode, self.thin)
+            # thinned rows are few: room for four rounds at once (accepted points: worst case of one round, n_steps + 1)
+            first = 4 * need if mode == capi.RECORD_THINNED else need
+            self._samples = engine.Samples(self.problem, self.n_chains, first, mode, self.thin)
             self._used = 0
         else:
             # grow geometrically (every round of a long run would otherwise re-allocate and copy everything recorded so
