@@ -8,6 +8,7 @@ OptimiseTask loop around it (prospect/tasks/optimise_task.py:16-54).  The method
 iterations per launch with set_bestfit / get_next_iteration_settings evaluated on the device.
 """
 import math
+import os
 
 import numpy as np
 
@@ -259,6 +260,12 @@ class SimulatedAnnealing:
                 host[name].copy_(t, non_blocking=True)
             done = torch.cuda.Event()
             done.record(cs)
+        if self.world > 1 and os.environ.get('PB200_ASYNC_MULTI_GPU', '0') != '1':
+            # Jobs sharded over several GPUs are kept one at a time: with two of them in flight a rank was seen to hang
+            # in an 8-GPU run (bench.py e2e, 2026-10; not understood: the kernel-side exchange protocol is ordered
+            # on the device and does not depend on the host), so the read is completed here, before the caller can
+            # launch the next job.
+            done.synchronize()
         return PendingResults(self, k, src, host, done)
 
     def get_next_iteration_settings(self):
