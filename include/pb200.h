@@ -30,7 +30,8 @@ extern "C" {
 /* 4: struct pb200_problem gained lt_hi / lt_lo (tensor-core operands of the wide path); the stand-alone variate
  *    generator entry points of version 3 (pb200_variates_*, pb200_anneal_run_streamed: measured slower than the fused
  *    kernel at every batch size) were removed; pb200_exchange_arrivals and pb200_launch_status are new */
-#define PB200_ABI_VERSION 4
+/* 5: additions only -- pb200_hosted, pb200_hosted_propose, pb200_hosted_accept (host-evaluated likelihoods) */
+#define PB200_ABI_VERSION 5
 
 /* chain status (pb200_chains.status) */
 #define PB200_ACTIVE     0
@@ -279,6 +280,47 @@ int pb200_choose_lanes(int32_t npad, int32_t n_chains);
  * environment forces the choice.
  */
 int pb200_uses_producer_warps(int32_t lanes_per_chain, int32_t n_chains);
+
+/*
+ * Host-evaluated likelihoods: the kernels of external codes (cobaya, MontePython, any
+ * BaseKernel subclass -- prospect/kernels/base_kernel.py:9-138) compute -log L on the CPU; everything else of
+ * MetropolisHastings.step (prospect/mcmc.py:163-190) is batched here.  One step of all chains is
+ *     pb200_hosted_propose  ->  (the host evaluates the proposals that are inside the box)  ->  pb200_hosted_accept.
+ * Used fields of pb200_chains: x, loglkl, temperature, step_size, point, chain_id, steps_done, status (chains whose
+ * status is not PB200_ACTIVE are left alone); pb200_schedule_update serves the annealing bookkeeping unchanged.
+ */
+typedef struct pb200_hosted {
+    int32_t n;               /* varying parameters */
+    int32_t npad;            /* row length of x / prop / best_x (>= n, a multiple of 32, <= 256) */
+    int32_t n_points;        /* P: proposal covariances (one per profile point) */
+    const double* factor_t;  /* device [P][npad*npad]  factor_t[j*npad+i] = F[i][j] with F F^T = covmat of the point
+                                (tasks/initialise_optimiser_task.py:126-130); pads zero */
+    const double* lo;        /* device [npad]  prior box (open sides / pads / ignore_prior: -inf) */
+    const double* hi;        /* device [npad]  (+inf) */
+} pb200_hosted;
+
+/*
+ * The proposal of every active chain, x' = x + step_size * F z with z ~ N(0, I) from the chain's Philox stream at its
+ * step counter -- numpy's multivariate_normal(x, covmat * step_size^2) of prospect/mcmc.py:182-190 in distribution --
+ * and its prior-box test (prospect/kernels/base_kernel.py:89-102; the reference skips the likelihood of an
+ * out-of-box proposal, mcmc.py:166-167, and so may the host).  Nothing of the chain state changes.
+ *   out_prop [B][npad] device (inactive chains: their current position), out_outside [B] device int32.
+ */
+int pb200_hosted_propose(const pb200_hosted* hosted, const pb200_chains* chains, uint64_t seed, double* out_prop,
+                         int32_t* out_outside, void* stream);
+
+/*
+ * Accept / reject with the host's likelihood values: accept iff the proposal is inside the box and
+ * exp((loglkl - prop_loglkl) / temperature) > u  (prospect/mcmc.py:170-180, strict), evaluated as
+ * prop_loglkl - loglkl < temperature * e with e = -ln u from the chain's Philox stream (NaN / +inf never accept).
+ * Accepted chains take the proposal (x, loglkl); every active chain's step counter advances by one.
+ *   prop [B][npad], prop_loglkl [B], outside [B]: device (prop_loglkl of an out-of-box proposal is not read);
+ *   accepted_flag [B] int32 out (may be NULL), n_accepted [B] int32 in/out (may be NULL),
+ *   best_loglkl [B] / best_x [B][npad] in/out (may be NULL): running bestfit, first minimum (optimiser.py:75).
+ */
+int pb200_hosted_accept(const pb200_hosted* hosted, const pb200_chains* chains, uint64_t seed, const double* prop,
+                        const double* prop_loglkl, const int32_t* outside, int32_t* accepted_flag,
+                        int32_t* n_accepted, double* best_loglkl, double* best_x, void* stream);
 
 /*
  * Stand-alone adaptive step-size / temperature bookkeeping for B chains (the same device function the

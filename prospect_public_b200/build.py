@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG, 'csrc')
 LIB_DIR = os.path.join(PKG, '_lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libpb200.so')
 SOURCES = [os.path.join(CSRC, 'pb200_kernels.cu')]
-HEADERS = [os.path.join(CSRC, h) for h in ('pb200_device.cuh', 'pb200_wide.cuh', 'pb200_umma.cuh')] + \
+HEADERS = [os.path.join(CSRC, h) for h in ('pb200_device.cuh', 'pb200_wide.cuh', 'pb200_umma.cuh', 'pb200_hosted.cuh')] + \
           [os.path.join(os.path.dirname(PKG), 'include', 'pb200.h')]
 
 NVCC_FLAGS = [

@@ -14,7 +14,7 @@ ACTIVE, CONVERGED, FAILED = 0, 1, 2
 STEP_EXPONENTIAL, STEP_ADAPTIVE_FIXED, STEP_ADAPTIVE_SECANT = 0, 1, 2
 RECORD_NONE, RECORD_ACCEPTED, RECORD_THINNED = 0, 1, 2
 EXACT_BOX = 0x100
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 _vp = C.c_void_p
 
@@ -57,6 +57,11 @@ class Peers(C.Structure):
                 ('progress', _vp * MAX_PEERS)]
 
 
+class Hosted(C.Structure):
+    _fields_ = [('n', C.c_int32), ('npad', C.c_int32), ('n_points', C.c_int32), ('factor_t', _vp), ('lo', _vp),
+                ('hi', _vp)]
+
+
 # name -> (restype, argtypes); every name here must be declared in include/pb200.h
 SIGNATURES = {
     'pb200_last_error': (C.c_char_p, []),
@@ -78,6 +83,9 @@ SIGNATURES = {
     'pb200_uses_producer_warps': (C.c_int, [C.c_int32, C.c_int32]),
     'pb200_exchange_arrivals': (C.c_int, [C.c_int32, C.c_int32, C.c_int32]),
     'pb200_launch_status': (C.c_int, [_vp]),
+    'pb200_hosted_propose': (C.c_int, [C.POINTER(Hosted), C.POINTER(Chains), C.c_uint64, _vp, _vp, _vp]),
+    'pb200_hosted_accept': (C.c_int, [C.POINTER(Hosted), C.POINTER(Chains), C.c_uint64, _vp, _vp, _vp, _vp, _vp, _vp,
+                                      _vp, _vp]),
     'pb200_schedule_update': (C.c_int, [C.POINTER(Chains), C.POINTER(Schedule), _vp, _vp, _vp]),
     'pb200_profile_reduce': (C.c_int, [_vp, _vp, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                        _vp, _vp, _vp, _vp, _vp, _vp]),

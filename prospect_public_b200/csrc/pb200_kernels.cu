@@ -15,9 +15,11 @@
 //   chain_moments_kernel      per-chain weighted first moments of recorded chains (Gelman-Rubin statistics).
 //   wide_* (pb200_wide.cuh, pb200_umma.cuh)  the per-iteration pipeline of wide problems (npad >= 128): steps ->
 //                             tcgen05 position GEMM -> FP64 anchor GEMM.
+//   hosted_* (pb200_hosted.cuh)  batched proposal / accept for likelihoods evaluated on the host.
 //   rng_kernel                test hook exposing the variates.
 // Chain state lives in HBM between launches and in registers inside one; there is no CPU fallback.
 #include "pb200_device.cuh"
+#include "pb200_hosted.cuh"
 
 // Minimum resident CTAs per SM (-> register budget 65536 / (CTAs * 128)) of the npad = 32 geometries; the values are
 // the measured optimum on B200 (profiles/README.md).  Tried and rejected: drawing the next Philox block piecewise
@@ -1664,6 +1666,42 @@ int pb200_schedule_update(const pb200_chains* chains, const pb200_schedule* sche
     schedule_kernel<<<(chains->n_chains + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*chains, *sched, accepted,
                                                                                        best_loglkl);
     return check_cuda(cudaGetLastError(), "schedule_kernel launch");
+}
+
+static int validate_hosted(const pb200_hosted* h, const pb200_chains* c, const char* who) {
+    if (!h || !c) return fail(std::string(who) + ": NULL argument");
+    if (h->npad < 32 || h->npad > 256 || h->npad % 32 != 0) return fail(std::string(who) + ": npad must be 32, 64, ..., 256");
+    if (h->n < 1 || h->n > h->npad) return fail(std::string(who) + ": need 1 <= n <= npad");
+    if (h->n_points < 1 || !h->factor_t || !h->lo || !h->hi) return fail(std::string(who) + ": incomplete pb200_hosted");
+    if (!c->x || !c->loglkl || !c->temperature || !c->step_size || !c->point || !c->chain_id || !c->steps_done ||
+        !c->status)
+        return fail(std::string(who) + ": chains have NULL device pointers");
+    return 0;
+}
+
+int pb200_hosted_propose(const pb200_hosted* hosted, const pb200_chains* chains, uint64_t seed, double* out_prop,
+                         int32_t* out_outside, void* stream) {
+    if (validate_hosted(hosted, chains, "hosted_propose")) return 1;
+    if (!out_prop || !out_outside) return fail("hosted_propose: NULL output");
+    if (chains->n_chains <= 0) return 0;
+    hosted_propose_kernel<<<(chains->n_chains + kHostedWarps - 1) / kHostedWarps, 32 * kHostedWarps,
+                            sizeof(double) * kHostedWarps * hosted->npad, (cudaStream_t)stream>>>(
+        *hosted, *chains, (uint32_t)seed, (uint32_t)(seed >> 32), out_prop, out_outside);
+    return check_cuda(cudaGetLastError(), "hosted_propose_kernel launch");
+}
+
+int pb200_hosted_accept(const pb200_hosted* hosted, const pb200_chains* chains, uint64_t seed, const double* prop,
+                        const double* prop_loglkl, const int32_t* outside, int32_t* accepted_flag,
+                        int32_t* n_accepted, double* best_loglkl, double* best_x, void* stream) {
+    if (validate_hosted(hosted, chains, "hosted_accept")) return 1;
+    if (!prop || !prop_loglkl || !outside) return fail("hosted_accept: NULL input");
+    if ((best_loglkl == nullptr) != (best_x == nullptr)) return fail("hosted_accept: best_loglkl and best_x go together");
+    if (chains->n_chains <= 0) return 0;
+    hosted_accept_kernel<<<(chains->n_chains + kHostedWarps - 1) / kHostedWarps, 32 * kHostedWarps, 0,
+                           (cudaStream_t)stream>>>(*hosted, *chains, (uint32_t)seed, (uint32_t)(seed >> 32), prop,
+                                                   prop_loglkl, outside, accepted_flag, n_accepted, best_loglkl,
+                                                   best_x);
+    return check_cuda(cudaGetLastError(), "hosted_accept_kernel launch");
 }
 
 int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int64_t stride_best,

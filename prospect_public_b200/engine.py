@@ -260,6 +260,23 @@ def mh_run(problem, chains: ChainBatch, n_steps, seed, samples: Samples = None, 
     return accepted
 
 
+def hosted_propose(hosted, chains: ChainBatch, seed, out_prop, out_outside, stream=None):
+    """Proposals x' = x + step * F z of every active chain + their prior-box test (pb200_hosted_propose)."""
+    _count()
+    capi.check(capi.lib().pb200_hosted_propose(C.byref(hosted.c), C.byref(chains.c), C.c_uint64(seed),
+                                               capi.ptr(out_prop), capi.ptr(out_outside), _stream_ptr(stream)))
+
+
+def hosted_accept(hosted, chains: ChainBatch, seed, prop, prop_loglkl, outside, accepted_flag=None, n_accepted=None,
+                  best_loglkl=None, best_x=None, stream=None):
+    """Accept / reject with host-evaluated likelihood values and advance the chains (pb200_hosted_accept)."""
+    _count()
+    capi.check(capi.lib().pb200_hosted_accept(C.byref(hosted.c), C.byref(chains.c), C.c_uint64(seed), capi.ptr(prop),
+                                              capi.ptr(prop_loglkl), capi.ptr(outside), capi.ptr(accepted_flag),
+                                              capi.ptr(n_accepted), capi.ptr(best_loglkl), capi.ptr(best_x),
+                                              _stream_ptr(stream)))
+
+
 def schedule_update(chains: ChainBatch, schedule, accepted, best_loglkl, stream=None):
     _count()
     capi.check(capi.lib().pb200_schedule_update(C.byref(chains.c), C.byref(schedule), capi.ptr(accepted),

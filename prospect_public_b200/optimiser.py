@@ -16,9 +16,14 @@ from . import capi
 from .distributed import dist_info, global_chain_index, shard_grid
 
 
-def initialise_optimiser(config, kernel, optimise_settings):
+def initialise_optimiser(config, kernel, optimise_settings, **kwargs):
+    """prospect/optimiser.py:6-11.  A kernel whose likelihood is evaluated on the host (kernels.HostKernelAdapter)
+    gets the optimiser that batches everything BUT the likelihood call (hosted.HostedSimulatedAnnealing)."""
     if config.profile.optimiser == 'simulated annealing':
-        return SimulatedAnnealing(config, kernel, optimise_settings)
+        if getattr(kernel, 'host_evaluated', False):
+            from .hosted import HostedSimulatedAnnealing
+            return HostedSimulatedAnnealing(config, kernel, optimise_settings, **kwargs)
+        return SimulatedAnnealing(config, kernel, optimise_settings, **kwargs)
     raise ValueError('You have specified a non-existing optimizer type.')
 
 
@@ -169,7 +174,8 @@ class SimulatedAnnealing:
         self.local_points = np.unique(pt) if len(pt) else np.array([0])
         point_local = np.searchsorted(self.local_points, pt).astype(np.int32)
         fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
-        self.problem = kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covs[self.local_points])
+        self.fixed_local = fixed_local
+        self.problem = self._device_problem(kernel, fixed_local, covs[self.local_points])
         cb = np.broadcast_to(np.asarray(s.get('current_best_loglkl', math.inf), dtype=np.float64), (self.n_points,))
         gid = global_chain_index(pt, rep, self.n_points)
         resumed = s.get('chain_state')            # global-order per-chain state of an interrupted run (run.resume)
@@ -206,6 +212,10 @@ class SimulatedAnnealing:
     @property
     def n_chains(self):
         return self.batch.n_chains
+
+    def _device_problem(self, kernel, fixed_local, covmats_local):
+        """Device image of what the chains of this rank sample with (hosted.HostedSimulatedAnnealing overrides it)."""
+        return kernel.device_problem(fixed_values=fixed_local, proposal_covmats=covmats_local)
 
     # --- the reference's three verbs -------------------------------------------------------------
     def optimise(self, n_iterations=1, stream=None):

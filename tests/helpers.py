@@ -49,3 +49,53 @@ def conditional_covariance(covmat, fixed_index):
     s = 0.5 * (s + s.T)
     n = covmat.shape[0] - 1
     return np.linalg.inv(s[:n, :n])
+
+
+class ToyHostKernel:
+    """A likelihood that only exists on the HOST, behind the reference's kernel plugin surface
+    (prospect/kernels/base_kernel.py:9-138: `param`, `set_fixed_parameters`, `loglkl(position dict)`, `logprior`,
+    defaults): a correlated Gaussian plus a non-Gaussian ripple, so nothing on the device could have evaluated it.
+    Parameters x1..xd, ranges `box`; every call is counted."""
+
+    def __init__(self, d, seed=3, box=(-2.5, 2.5), ignore_prior=False):
+        mu, cov = spd_target(d, seed=seed, lam_range=(5e-3, 2e-1))
+        self.mu, self.prec = mu, np.linalg.inv(cov)
+        self.names = [f'x{i}' for i in range(1, d + 1)]
+        self.param = {'varying': {n: {'range': list(box)} for n in self.names}, 'fixed': {}, 'derived': {}}
+        self.ignore_prior = ignore_prior
+        self.calls = 0
+
+    def set_fixed_parameters(self, fixed_param_dict):            # base_kernel.py:46-51
+        for name, value in fixed_param_dict.items():
+            self.param['fixed'][name] = self.param['varying'].pop(name)
+            self.param['fixed'][name]['fixed_value'] = value
+
+    @property
+    def varying_param_names(self):
+        return list(self.param['varying'].keys())
+
+    def value(self, full):
+        r = np.asarray(full, dtype=np.float64) - self.mu
+        return float(0.5 * r @ self.prec @ r + 0.05 * np.sum(np.sin(3.0 * np.asarray(full)) ** 2))
+
+    def loglkl(self, prop):                                      # base_kernel.py:72-81
+        for name, par in self.param['fixed'].items():
+            prop[name] = [par['fixed_value']]
+        self.calls += 1
+        return self.value([prop[n][0] for n in self.names])
+
+    def logprior(self, position):                                # base_kernel.py:83-102
+        if self.ignore_prior:
+            return 0.0
+        for name, val in position.items():
+            if name in self.param['varying']:
+                lo, hi = self.param['varying'][name]['range']
+                if (lo is not None and val[0] < lo) or (hi is not None and val[0] > hi):
+                    return np.inf
+        return 0.0
+
+    def get_default_covmat(self):
+        return 0.005 * np.diag([5.0] * len(self.varying_param_names))
+
+    def finalize(self):
+        pass
