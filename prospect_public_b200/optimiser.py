@@ -198,15 +198,15 @@ class SimulatedAnnealing:
                                       n_alloc=self.b_alloc)
         # lanes per chain: chosen from the size of the WHOLE job, not of this rank's shard, so that a chain's arithmetic
         # (the order of its FP32 reductions) -- and with it every record -- does not depend on the number of GPUs
-        self.lanes = int(s.get('lanes_per_chain', 0)) or engine.choose_lanes(self.problem.npad,
-                                                                             self.n_points * self.reps)
+        # (PB200_LANES_PER_CHAIN: A/B runs of the geometries, scripts/r02_lanes4.sh)
+        self.lanes = int(s.get('lanes_per_chain', 0)) or int(os.environ.get('PB200_LANES_PER_CHAIN', '0') or 0) or \
+            engine.choose_lanes(self.problem.npad, self.n_points * self.reps)
         self.seed = int(s.get('seed', 0))
         self.step_counter = 0                 # MH steps taken so far by every live chain (they advance in lockstep)
         self.iterations_done = int(s.get('iteration_number', 0))
         self.bestfit = None
         self._gatherer = None
         self.signalled = True
-        import os
         self.fused_exchange = os.environ.get('PB200_EXCHANGE', 'fused') == 'fused'
 
     @property
