@@ -349,6 +349,8 @@ int pb200_profile_reduce(const double* best_loglkl, const int32_t* accepted, int
  * compute_covariance_matrix (prospect/mcmc.py:84-97, np.cov(..., bias=True, fweights=mults)).
  *   x [N][ld] device (first n columns used), w [N] device int32 (NULL: all 1),
  *   out [1 + n + n*n] device, zeroed by the call.
+ * Reproducible: per-CTA partial sums (stream-ordered scratch, <= 32 MB) added in a fixed order, no atomics -- the same
+ * rows give the same bits on every run.
  */
 int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, int32_t ld, int32_t n,
                            double* out, void* stream);

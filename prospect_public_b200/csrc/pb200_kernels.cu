@@ -37,6 +37,7 @@
 #define PB200_PIPE_RNG 0     // experiment: draw the next Philox block in the shadow of the current one (8-lane geometry)
 #endif
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -1130,12 +1131,16 @@ point_reduce_kernel(const double* __restrict__ chain_best, int n_points, int rep
 
 // Weighted moments: out[0] = sum w, out[1..n] = sum w x_i, out[1+n+i*n+j] = sum w x_i x_j.
 // Each CTA streams a strided set of 32-row tiles through shared memory (coalesced), every thread
-// keeps kPairs (i,j) accumulators in registers, one FP64 atomicAdd per accumulator at the end.
+// keeps kPairs (i,j) accumulators in registers and stores them into the CTA's own row of `partial`
+// ([gridDim.x][1 + n + n*n]); moments_reduce_kernel adds the rows in CTA order.  No atomics: the sums -- and with them
+// the bin covariances every proposal factor is built from -- are reproducible run to run (FP64 atomicAdd across CTAs
+// rounded differently from one run to the next, which the FP64 hosted path showed in the last bits).
 constexpr int kMomThreads = 256, kMomTile = 32, kPairs = 4;
+constexpr long long kMomScratchDoubles = 4LL << 20;      // <= 32 MB of partial sums per call
 
 __global__ void __launch_bounds__(kMomThreads)
 moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ w, long long n_rows, int ld, int n,
-               double* __restrict__ out) {
+               double* __restrict__ partial) {
     extern __shared__ double sm[];                 // [kMomTile][n+1]: row values then the weight
     const int stride = n + 1;
     const int chunk = blockIdx.y;                  // pairs [chunk*1024, chunk*1024 + 1024)
@@ -1169,13 +1174,22 @@ moments_kernel(const double* __restrict__ x, const int32_t* __restrict__ w, long
         }
         __syncthreads();
     }
+    double* __restrict__ out = partial + (size_t)blockIdx.x * (size_t)(1 + n + nn);
 #pragma unroll
     for (int q = 0; q < kPairs; ++q)
-        if (pi[q] >= 0) atomicAdd(out + 1 + n + pi[q] * n + pj[q], acc[q]);
+        if (pi[q] >= 0) out[1 + n + pi[q] * n + pj[q]] = acc[q];
     if (chunk == 0) {
-        if (threadIdx.x < n) atomicAdd(out + 1 + threadIdx.x, acc1);
-        if (threadIdx.x == 0) atomicAdd(out, acc0);
+        if (threadIdx.x < n) out[1 + threadIdx.x] = acc1;
+        if (threadIdx.x == 0) out[0] = acc0;
     }
+}
+
+__global__ void moments_reduce_kernel(const double* __restrict__ partial, int parts, int len, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= len) return;
+    double s = 0.0;
+    for (int p = 0; p < parts; ++p) s = __dadd_rn(s, partial[(size_t)p * len + i]);      // CTA order: reproducible
+    out[i] = s;
 }
 
 // Per-chain weighted first moments of the recorded chains (sufficient statistics of R-1 together with the pooled
@@ -1731,10 +1745,20 @@ int pb200_weighted_moments(const double* x, const int32_t* w, int64_t n_rows, in
     if (n_rows <= 0) return 0;
     const int chunks = (n * n + kMomThreads * kPairs - 1) / (kMomThreads * kPairs);
     const long long tiles = (n_rows + kMomTile - 1) / kMomTile;
-    const int gx = (int)std::min<long long>(tiles, 148LL * 4);
+    const int len = 1 + n + n * n;
+    const int gx = (int)std::max<long long>(1, std::min<long long>({tiles, 148LL * 4, kMomScratchDoubles / len}));
     const size_t smem = sizeof(double) * kMomTile * (n + 1);
-    moments_kernel<<<dim3(gx, chunks), kMomThreads, smem, st>>>(x, w, (long long)n_rows, ld, n, out);
-    return check_cuda(cudaGetLastError(), "moments_kernel launch");
+    if (gx == 1) {                                   // one CTA per pair chunk: its sums are the result
+        moments_kernel<<<dim3(1, chunks), kMomThreads, smem, st>>>(x, w, (long long)n_rows, ld, n, out);
+        return check_cuda(cudaGetLastError(), "moments_kernel launch");
+    }
+    double* partial = nullptr;
+    if (check_cuda(cudaMallocAsync(&partial, sizeof(double) * (size_t)gx * len, st), "weighted_moments: scratch")) return 1;
+    moments_kernel<<<dim3(gx, chunks), kMomThreads, smem, st>>>(x, w, (long long)n_rows, ld, n, partial);
+    moments_reduce_kernel<<<(len + 255) / 256, 256, 0, st>>>(partial, gx, len, out);
+    const int rc = check_cuda(cudaGetLastError(), "moments_kernel launch");
+    cudaFreeAsync(partial, st);
+    return rc;
 }
 
 int pb200_chain_moments(const double* x, const int32_t* mult, const int32_t* count, int32_t n_chains,

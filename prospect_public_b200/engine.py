@@ -325,7 +325,7 @@ def weighted_moments(x, n, weights=None, stream=None):
     -> (sum_w, sum_wx [n], sum_wxx [n, n]) device tensors."""
     x2 = x.reshape(-1, x.shape[-1])
     out = torch.empty(1 + n + n * n, dtype=torch.float64, device=x.device)
-    _count()
+    _count(1 if x2.shape[0] <= 32 else 2)          # partial sums per CTA + their ordered reduction (no atomics)
     capi.check(capi.lib().pb200_weighted_moments(capi.ptr(x2), capi.ptr(weights), x2.shape[0], x2.shape[1], int(n),
                                                  capi.ptr(out), _stream_ptr(stream)))
     return out[0], out[1:1 + n], out[1 + n:].reshape(n, n)

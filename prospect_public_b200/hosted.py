@@ -41,22 +41,35 @@ class HostKernelAdapter:
     """
     host_evaluated = True
 
-    def __init__(self, kernel, profile_parameter=None, ignore_prior=None, batch_loglkl=None):
+    def __init__(self, kernel, profile_parameter=None, ignore_prior=None, batch_loglkl=None, device=None):
         self.kernels = list(kernel) if isinstance(kernel, (list, tuple)) else [kernel]
         self.kernel = self.kernels[0]
-        self.profile_parameter = profile_parameter
+        self.profile_parameter = None
         self.batch_loglkl = batch_loglkl
         self.ignore_prior = bool(getattr(self.kernel, 'ignore_prior', False)) if ignore_prior is None \
             else bool(ignore_prior)
+        self.device = device                      # None: the current CUDA device when the optimiser is built
         if profile_parameter is not None:
-            for k in self.kernels:
-                if profile_parameter not in k.param['fixed']:
-                    if profile_parameter not in k.param['varying']:
-                        raise ValueError(f'The requested profile parameter {profile_parameter} is not recognized by '
-                                         'the kernel.')
-                    k.set_fixed_parameters({profile_parameter: 0.0})
+            self.set_fixed_parameters({profile_parameter: 0.0})
         self._pool = ThreadPoolExecutor(len(self.kernels)) if len(self.kernels) > 1 else None
         self.evaluations = 0
+
+    def set_fixed_parameters(self, fixed_param_dict):
+        """base_kernel.py:46-51 for every wrapped kernel object.  The (one) profiled parameter moves to `param['fixed']`
+        the first time; afterwards its value is whatever the chain being evaluated needs (loglkl_batch)."""
+        if len(fixed_param_dict) != 1:
+            raise ValueError('One parameter is profiled at a time.')
+        (name, value), = fixed_param_dict.items()
+        if self.profile_parameter not in (None, name):
+            raise ValueError(f"'{self.profile_parameter}' is already the profiled parameter of this kernel.")
+        for k in self.kernels:
+            if name in k.param['fixed']:
+                k.param['fixed'][name]['fixed_value'] = value
+            elif name in k.param['varying']:
+                k.set_fixed_parameters({name: value})
+            else:
+                raise ValueError(f'The requested profile parameter {name} is not recognized by the kernel.')
+        self.profile_parameter = name
 
     # the reference's plugin surface is the wrapped kernel's
     @property
@@ -68,7 +81,7 @@ class HostKernelAdapter:
         return list(self.kernel.param['varying'].keys())
 
     def __getattr__(self, name):          # get_default_covmat, read_covmat, logprior, ... of the wrapped kernel
-        if name in ('kernels', 'kernel'):
+        if name in ('kernels', 'kernel', 'device'):
             raise AttributeError(name)
         return getattr(self.kernel, name)
 
@@ -160,7 +173,7 @@ class HostedSimulatedAnnealing(SimulatedAnnealing):
 
     def __init__(self, config, kernel, optimise_settings, keep_positions=True, device=None):
         import torch
-        self._device = device or getattr(kernel, 'device', None) or 'cuda:0'
+        self._device = device or getattr(kernel, 'device', None) or f'cuda:{torch.cuda.current_device()}'
         super().__init__(config, kernel, optimise_settings, keep_positions=keep_positions)
         self.fused_exchange = False           # several GPUs: one launch set + one NCCL all-gather per iteration
         self.signalled = False

@@ -181,7 +181,7 @@ def initialise_optimiser(config, kernel, shard=None):
             else:
                 closest = int(np.argmin(start_profile['-loglkl']))
             positions[p] = np.array([start_profile[nm][closest] for nm in names])
-        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, kernel.device)):
+        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, _device_of(kernel))):
             covmats[p] = drop(cov)
     elif prof.start_from_mcmc is not None:
         chain = _reduced_chain(load_mcmc(prof.start_from_mcmc), kernel)
@@ -190,7 +190,7 @@ def initialise_optimiser(config, kernel, shard=None):
         if is_profile and len(chain.mults) >= GPU_BINNING_MIN_ROWS and len(mine):
             n_bin = int(np.ceil(prof.start_bin_fraction * len(chain.mults)))
             gpu_idx = dict(zip(mine, get_points_in_bins_gpu(chain.positions[prof.parameter], values[mine], n_bin,
-                                                            kernel.device)))
+                                                            _device_of(kernel))))
         for p in mine:
             if gpu_idx is not None:
                 idx = gpu_idx[p]
@@ -204,7 +204,7 @@ def initialise_optimiser(config, kernel, shard=None):
             ms.append(np.take(chain.mults, idx))
             start = x[int(np.argmin(np.take(chain.loglkls, idx)))]
             positions[p] = np.delete(start, pidx) if pidx is not None else start
-        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, kernel.device)):
+        for p, cov in zip(mine, _weighted_covs_gpu(xs, ms, _device_of(kernel))):
             covmats[p] = drop(cov)
     else:
         raise ValueError('InitialiseOptimiserTask could not construct an initial position and/or covariance '
@@ -226,7 +226,11 @@ def initialise_optimiser(config, kernel, shard=None):
     # initial_loglkl = kernel.loglkl(start) with the profile parameter fixed (initialise_optimiser_task.py:124): one
     # batched likelihood launch over all values on a likelihood-only device image (no per-point proposal factors --
     # those are only built for the points a rank actually anneals)
-    if is_profile:
+    if getattr(kernel, 'host_evaluated', False):       # hosted.HostKernelAdapter: one host batch
+        if is_profile:
+            kernel.set_fixed_parameters({prof.parameter: float(values[0])})
+        init_ll = kernel.loglkl_batch(positions, values if is_profile else None)
+    elif is_profile:
         kernel.set_fixed_parameters({prof.parameter: float(values[0])})
         prob = kernel.device_problem(fixed_values=values, likelihood_only=True)
         init_ll = kernel.loglkl_batch(positions, points=np.arange(n_pts), problem=prob)
@@ -234,6 +238,15 @@ def initialise_optimiser(config, kernel, shard=None):
         prob = kernel.device_problem(likelihood_only=True)
         init_ll = kernel.loglkl_batch(positions, problem=prob)
     return StartingPoints(names, positions, covmats, init_ll, indices), values
+
+
+def _device_of(kernel):
+    """Device of the kernel's GPU work (a host-evaluated kernel may leave it open: the current CUDA device)."""
+    dev = getattr(kernel, 'device', None)
+    if dev is None:
+        import torch
+        dev = f'cuda:{torch.cuda.current_device()}'
+    return dev
 
 
 def _reduced_chain(chain, kernel):

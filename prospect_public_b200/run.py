@@ -26,6 +26,7 @@ from .distributed import dist_info, init_from_env
 from .initialise import initialise_optimiser
 from .kernels import initialise_kernel
 from .optimiser import SimulatedAnnealing, get_initial_step_size_change, get_temperature_change
+from .optimiser import initialise_optimiser as build_optimiser
 
 STATE_FORMAT = 'pb200-state-v1'
 
@@ -44,17 +45,19 @@ def _barrier():
         dist.barrier()
 
 
-def run(user_inp, quiet=True, stop_after=None, max_rounds=64):
+def run(user_inp, quiet=True, stop_after=None, max_rounds=64, kernel=None):
     """Run a job (a .yaml file or dict) or resume one (the folder of an earlier run, prospect/io.py:15-24).  Returns
     a dict with the records, the analysis products and timings.  `stop_after` ends an annealing job after that
     many iterations (an mcmc job after that many rounds) with a complete snapshot, as an interrupted run would leave
-    it; `max_rounds` bounds the rounds of an mcmc job that does not reach convergence_Rm1."""
+    it; `max_rounds` bounds the rounds of an mcmc job that does not reach convergence_Rm1.  `kernel` (annealing jobs):
+    a kernel object, or a callable (config_kernel, output_folder, rank, device) -> kernel, used instead of the yaml's
+    `kernel.type` factory -- e.g. a hosted.HostKernelAdapter around a likelihood that stays on the host."""
     t_start = time.perf_counter()
     config_yaml, is_folder = pio.read_user_input(user_inp) if isinstance(user_inp, str) else (user_inp, False)
     rank, world, _ = init_from_env('nccl') if int(os.environ.get('WORLD_SIZE', '1')) > 1 else dist_info()
     config = Configuration(config_yaml).synchronise()      # rank 0's output folder and Philox key for every rank
     if is_folder:
-        out = resume(config, user_inp, max_rounds=max_rounds)
+        out = resume(config, user_inp, max_rounds=max_rounds, kernel=kernel)
         out['time_to_result_s'] = time.perf_counter() - t_start
         out['config'] = config
         return out
@@ -64,7 +67,7 @@ def run(user_inp, quiet=True, stop_after=None, max_rounds=64):
     if config.run.jobtype == 'mcmc':
         out = run_mcmc(config, max_rounds=max_rounds, stop_after_rounds=stop_after)
     else:
-        out = run_annealing(config, stop_after=stop_after)
+        out = run_annealing(config, stop_after=stop_after, kernel=kernel)
     out['time_to_result_s'] = time.perf_counter() - t_start          # incl. the snapshot pickles
     if 't_results_written' in out:
         out['time_to_profile_s'] = out['t_results_written'] - t_start  # yaml read -> result files written
@@ -73,7 +76,7 @@ def run(user_inp, quiet=True, stop_after=None, max_rounds=64):
 
 
 def run_annealing(config, keep_positions=True, starts=None, values=None, seed=None, write=True, stop_after=None,
-                  resume_from=None):
+                  resume_from=None, kernel=None):
     """jobtype profile / global_optimisation.  `starts` / `values` / `seed` let reanneal() supply the start points;
     `resume_from` = (state dict, RunRecord) of an interrupted run continues its chains where they stopped."""
     import torch
@@ -83,11 +86,12 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
     if config.run.numpy_random_seed is not None:
         np.random.seed(int(config.run.numpy_random_seed))     # only used if a random kernel must be generated
     out_dir = config.io.dir if config.io.write else None
+    make_kernel = kernel if callable(kernel) else (initialise_kernel if kernel is None else (lambda *a: kernel))
     if rank == 0:
-        kernel = initialise_kernel(config.kernel, out_dir, 0, device)   # may create analytical/random_gauss.pkl
+        kernel = make_kernel(config.kernel, out_dir, 0, device)   # may create analytical/random_gauss.pkl
     _barrier()
     if rank != 0:
-        kernel = initialise_kernel(config.kernel, out_dir, rank, device)
+        kernel = make_kernel(config.kernel, out_dir, rank, device)
     if starts is None:
         starts, values = initialise_optimiser(config, kernel, shard=(rank, world))
     elif config.run.jobtype == 'profile':
@@ -114,7 +118,7 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
     }
     if resume_from is not None:
         settings['chain_state'] = resume_from[0]['chain_state']
-    sa = SimulatedAnnealing(config, kernel, settings, keep_positions=keep_positions)
+    sa = build_optimiser(config, kernel, settings, keep_positions=keep_positions)    # fused, or hosted for host kernels
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     if to_run > 0:
@@ -157,7 +161,7 @@ def run_annealing(config, keep_positions=True, starts=None, values=None, seed=No
     return result
 
 
-def resume(config, prospect_folder, max_rounds=64):
+def resume(config, prospect_folder, max_rounds=64, kernel=None):
     """`prospect <folder>` (prospect/io.py:15-24, prospect/communication.py:30-36): continue the chains of an
     interrupted run: an mcmc job from its chain files (run_mcmc), an annealing run from the state in its snapshot -- position, temperature, step size and step-size
     history, Philox step counter -- until every chain has run `profile.max_iterations` iterations (read from the
@@ -174,7 +178,7 @@ def resume(config, prospect_folder, max_rounds=64):
     from .initialise import StartingPoints
     starts = StartingPoints(rec_old.names, rec_old.initial_position, rec_old.initial_covmat, rec_old.initial_loglkl)
     return run_annealing(config, starts=starts, values=rec_old.values, seed=int(state['seed']),
-                         resume_from=(state, rec_old))
+                         resume_from=(state, rec_old), kernel=kernel)
 
 
 def write_result_files(config, rec, sa=None):

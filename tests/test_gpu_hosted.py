@@ -225,3 +225,51 @@ def test_reference_analytical_kernel_behind_the_hosted_optimiser(tmp_path):
     excess = best - cf
     assert np.all(excess > -1e-9) and np.all(excess < 5e-2), excess
     assert ref_kernel.param['fixed']['x2']['fixed_value'] in values          # the adapter re-values the fixed parameter
+
+
+@pytest.mark.skipif(not rh.available(), reason='oracle/_ref is absent (python oracle/make_ref.py builds it where '
+                                               '/root/reference exists)')
+def test_whole_profile_job_with_a_host_kernel_through_run(tmp_path):
+    """yaml -> run(kernel=...) -> PROSPECT's output tree with the UNMODIFIED reference AnalyticalKernel as a host
+    likelihood: start points / bin covariances from the MCMC (GPU moments), initial_loglkl from one host batch, hosted
+    annealing, the same analysis and writers; and an interrupted + resumed job (`prospect <folder>`) ends with the files
+    and records of the uninterrupted one."""
+    from prospect.kernels.analytical_kernel import AnalyticalKernel
+    from prospect_public_b200.io import load_profile
+    from prospect_public_b200.run import run
+    rh.activate()
+    k, m = golden('toy20_kernel.npz'), golden('toy20_mcmc.npz')
+    paths = write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], [m[f'chain_{i}'] for i in range(4)])
+    built = []
+
+    def factory(config_kernel, output_folder, rank, device):
+        with rh.quiet():
+            ref = AnalyticalKernel(config_kernel, rank, output_folder=output_folder)
+        built.append(ref)
+        return HostKernelAdapter(ref, device=device)
+
+    kw = dict(values=[-0.4, 0.5, 1.3], repetitions=2, max_iterations=6, steps_per_iteration=80)
+    full = run(annealing_yaml(paths, str(tmp_path / 'full'), **kw), kernel=factory)
+    assert isinstance(full['optimiser'], HostedSimulatedAnnealing) and full['chain_steps'] == 3 * 2 * 6 * 80
+    for fn in ('log.yaml', 'config.pkl', 'state.pkl', 'profile/x2.txt', 'profile/x2_status.txt',
+               'profile/x2_intervals.txt', 'analytical/random_gauss.pkl'):
+        assert os.path.isfile(os.path.join(str(tmp_path / 'full'), fn)), fn
+    prof = load_profile(str(tmp_path / 'full'))
+    assert np.allclose(prof['x2'], kw['values'], atol=1e-12)
+    cf = closed_form.profile_curve(k['means'], k['covmat'], 1, np.asarray(kw['values']))
+    assert np.all(prof['-loglkl'] - cf > -1e-9) and np.all(prof['-loglkl'] < prof['initial_loglkl'])
+    # the reported chi^2 IS the host kernel's value at the reported position
+    names = [f'x{i}' for i in range(1, 21) if i != 2]
+    ref = built[0]
+    for row in range(3):
+        ref.param['fixed']['x2']['fixed_value'] = float(prof['x2'][row])
+        assert ref.loglkl({nm: [float(prof[nm][row])] for nm in names}) == pytest.approx(prof['-loglkl'][row], rel=1e-9)
+    part = run(annealing_yaml(paths, str(tmp_path / 'part'), **kw), stop_after=2, kernel=factory)
+    assert part['iterations_done'] == 2
+    res = run(str(tmp_path / 'part'), kernel=factory)
+    assert res['iterations_done'] == 6
+    for key in ('best_loglkl', 'accepted', 'best_x', 'temperature', 'step_size'):
+        assert np.array_equal(getattr(res['record'], key), getattr(full['record'], key)), key
+    for name in ('x2.txt', 'x2_status.txt', 'x2_intervals.txt'):
+        with open(tmp_path / 'part' / 'profile' / name, 'rb') as fa, open(tmp_path / 'full' / 'profile' / name, 'rb') as fb:
+            assert fa.read() == fb.read(), name

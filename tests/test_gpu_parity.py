@@ -422,6 +422,18 @@ def test_weighted_moments_match_np_cov(n, rows):
     assert sw1.item() == rows
 
 
+def test_weighted_moments_are_reproducible_bit_for_bit():
+    """Many CTAs contribute to every sum; their partial sums are added in CTA order (no atomics), so repeated launches --
+    and with them the bin covariances, proposal factors and every FP64 result built on them -- agree in every bit."""
+    rng = np.random.default_rng(12)
+    x = torch.as_tensor(rng.standard_normal((40000, 32)) * rng.uniform(1e-3, 1e3, 32), device=DEV)
+    w = torch.as_tensor(rng.integers(1, 9, 40000).astype(np.int32), device=DEV)
+    first = [t.clone() for t in engine.weighted_moments(x, 30, w)]
+    for _ in range(5):
+        again = engine.weighted_moments(x, 30, w)
+        assert all(torch.equal(a, b) for a, b in zip(first, again))
+
+
 def test_weighted_moments_on_the_shipped_bootstrap_chain():
     """The covariance the reference's InitialiseOptimiserTask derives for x2 = 0.0 (golden fixture)."""
     from tests.helpers import mcmc_rows
