@@ -249,3 +249,157 @@ class HostedSimulatedAnnealing(SimulatedAnnealing):
                 engine.schedule_update(self.batch, self.schedule, self._nacc, self._best_ll)
             self.iterations_done += 1
             self.step_counter += self.schedule.steps_per_iteration
+
+
+class HostedMetropolisHastings:
+    """mcmc.MetropolisHastings for a HostKernelAdapter (prospect/mcmc.py:104-190 for `n_chains` chains at once): the
+    proposal, box test and accept rule run on the device, the likelihood on the host, and the accepted points are
+    recorded on the host (they are already there: the host evaluated them) as rows (multiplicity, -log L, position),
+    the reference's Chain layout (mcmc.py:25-82).  Same constructor arguments as mcmc.MetropolisHastings
+    (n_chains, seed, chain_ids, chains, steps_done)."""
+
+    def __init__(self, config_mcmc, kernel, **mcmc_args):
+        import torch
+        from . import engine
+        self.config_mcmc, self.kernel = config_mcmc, kernel
+        self.seed = int(mcmc_args.get('seed', 0))
+        names = kernel.varying_param_names
+        n = len(names)
+        if config_mcmc.start_from_covmat is not None:
+            cm = config_mcmc.start_from_covmat
+            self.covmat = np.array(cm) if not isinstance(cm, str) else kernel.read_covmat(cm)
+        else:
+            self.covmat = kernel.get_default_covmat()
+        prior = mcmc_args.get('chains')
+        self.n_chains = b = len(prior) if prior is not None else int(mcmc_args.get('n_chains', config_mcmc.N_chains))
+        if prior is not None:
+            x0 = np.array([[ch.positions[nm][-1] for nm in names] for ch in prior], dtype=np.float64)
+        elif config_mcmc.start_from_position is not None:
+            x0 = np.tile(np.asarray(kernel.read_initial_position(config_mcmc.start_from_position), dtype=float), (b, 1))
+        else:
+            start = kernel.get_default_initial_position()
+            x0 = np.tile(np.array([start[nm][0] for nm in names], dtype=np.float64), (b, 1))
+        device = mcmc_args.get('device') or getattr(kernel, 'device', None) or f'cuda:{torch.cuda.current_device()}'
+        lo, hi = kernel.bounds()
+        self.problem = HostedProblem(n, np.asarray(self.covmat, dtype=np.float64)[None], lo, hi, device)
+        self.batch = engine.ChainBatch(self.problem, x0, 0, chain_id=mcmc_args.get('chain_ids'),
+                                       temperature=config_mcmc.temperature, step_size=config_mcmc.step_size,
+                                       steps_done=mcmc_args.get('steps_done', 0))
+        fixed = kernel.param['fixed']
+        self._fixed = None if not fixed else np.full(b, float(next(iter(fixed.values()))['fixed_value']))
+        # the chain starts with its first point (mcmc.py:118-129); a continued chain knows that point's likelihood
+        ll0 = (np.array([ch.loglkls[-1] for ch in prior], dtype=np.float64) if prior is not None
+               else kernel.loglkl_batch(x0, self._fixed))
+        dev = self.problem.device
+        self.batch.loglkl.copy_(torch.as_tensor(ll0, device=dev))
+        npad = self.problem.npad
+        self._prop = torch.zeros((b, npad), dtype=torch.float64, device=dev)
+        self._outside = torch.zeros(b, dtype=torch.int32, device=dev)
+        self._prop_ll = torch.zeros(b, dtype=torch.float64, device=dev)
+        self._flag = torch.zeros(b, dtype=torch.int32, device=dev)
+        self._nacc = torch.zeros(b, dtype=torch.int32, device=dev)
+        self._prop_host = torch.empty((b, npad), dtype=torch.float64, pin_memory=True)
+        self._outside_host = torch.empty(b, dtype=torch.int32, pin_memory=True)
+        self._flag_host = torch.empty(b, dtype=torch.int32, pin_memory=True)
+        self._ll_host = torch.empty(b, dtype=torch.float64, pin_memory=True)
+        self._names, self._prior = names, prior
+        self._x = np.zeros((b, 64, n))
+        self._ll = np.zeros((b, 64))
+        self._mult = np.zeros((b, 64), dtype=np.int64)
+        self._count = np.ones(b, dtype=np.int64)
+        self._x[:, 0], self._ll[:, 0], self._mult[:, 0] = x0, ll0, 1
+        self.accepted = np.zeros(b, dtype=np.int64)
+        self.steps = 0
+
+    def _grow(self, need):
+        cap = self._ll.shape[1]
+        if need <= cap:
+            return
+        new = max(2 * cap, need)
+        for name in ('_x', '_ll', '_mult'):
+            old = getattr(self, name)
+            big = np.zeros((old.shape[0], new) + old.shape[2:], dtype=old.dtype)
+            big[:, :cap] = old
+            setattr(self, name, big)
+
+    def step(self):
+        """MetropolisHastings.step (mcmc.py:163-180) of every chain."""
+        import torch
+        from . import engine
+        b, n = self.n_chains, self.problem.n
+        if b == 0:
+            return
+        engine.hosted_propose(self.problem, self.batch, self.seed, self._prop, self._outside)
+        self._prop_host.copy_(self._prop, non_blocking=True)
+        self._outside_host.copy_(self._outside, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        inside = self._outside_host.numpy() == 0
+        prop = self._prop_host.numpy()[:, :n]
+        ll = self.kernel.loglkl_batch(prop, self._fixed, inside)
+        self._ll_host.numpy()[:] = ll
+        self._prop_ll.copy_(self._ll_host, non_blocking=True)
+        engine.hosted_accept(self.problem, self.batch, self.seed, self._prop, self._prop_ll, self._outside, self._flag,
+                             self._nacc)
+        self._flag_host.copy_(self._flag, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        acc = self._flag_host.numpy() != 0
+        # Chain.push_position for the accepted proposals, mults[-1] += 1 for the others (mcmc.py:176-180)
+        self._grow(int(self._count.max()) + 1)
+        idx = np.flatnonzero(acc)
+        rows = self._count[idx]
+        self._x[idx, rows], self._ll[idx, rows], self._mult[idx, rows] = prop[idx], ll[idx], 1
+        self._count[idx] += 1
+        rej = np.flatnonzero(~acc)
+        self._mult[rej, self._count[rej] - 1] += 1
+        self.accepted += acc
+        self.steps += 1
+
+    def run_steps(self, steps_per_iteration):
+        for _ in range(int(steps_per_iteration)):
+            self.step()
+
+    def run_minutes(self, minutes_per_iteration):
+        """BaseMCMC.run_minutes (mcmc.py:140-151): step until the wall-clock budget is used up."""
+        import time
+        t_end = time.perf_counter() + 60.0 * float(minutes_per_iteration)
+        done = 0
+        while True:
+            self.step()
+            done += 1
+            if time.perf_counter() >= t_end:
+                return done
+
+    def samples_numpy(self):
+        """(x [B, cap, n], loglkl [B, cap], mult [B, cap], count [B]) of everything recorded so far."""
+        return self._x, self._ll, self._mult.astype(np.int32), self._count.astype(np.int32)
+
+    @property
+    def chains(self):
+        """list[mcmc.Chain]; a continued chain is its earlier rows followed by the new ones, the open last row of the
+        earlier segment keeps its multiplicity count (Chain.mults[-1] += 1)."""
+        from .mcmc import Chain
+        fixed = {nm: par['fixed_value'] for nm, par in self.kernel.param['fixed'].items()}
+        out = []
+        for c in range(self.n_chains):
+            r = int(self._count[c])
+            ch = Chain.from_arrays(self._names, self._mult[c, :r], self._ll[c, :r], self._x[c, :r])
+            for nm, val in fixed.items():
+                ch.positions[nm] = [val] * r
+            if self._prior is not None:
+                prev = self._prior[c]
+                merged = Chain(list(prev.mults), list(prev.loglkls), {k: list(v) for k, v in prev.positions.items()})
+                merged.mults[-1] += ch.mults[0] - 1
+                merged.mults += ch.mults[1:]
+                merged.loglkls += ch.loglkls[1:]
+                for k in merged.positions:
+                    merged.positions[k] += ch.positions[k][1:]
+                ch = merged
+            out.append(ch)
+        return out
+
+    @property
+    def chain(self):
+        return self.chains[0]
+
+    def finalize(self):
+        pass

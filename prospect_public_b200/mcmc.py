@@ -90,7 +90,12 @@ def compute_covariance_matrix(chain_list, device='cuda:0'):
 
 
 def initialise_mcmc(config_mcmc, kernel, **mcmc_args):
+    """prospect/mcmc.py:13-18.  A kernel whose likelihood is evaluated on the host (hosted.HostKernelAdapter) gets the
+    sampler that batches everything BUT the likelihood call."""
     if config_mcmc.algorithm in ('MetropolisHastings', 'Metropolis Hastings'):
+        if getattr(kernel, 'host_evaluated', False):
+            from .hosted import HostedMetropolisHastings
+            return HostedMetropolisHastings(config_mcmc, kernel, **mcmc_args)
         return MetropolisHastings(config_mcmc, kernel, **mcmc_args)
     raise ValueError('You have specified a non-existing MCMC type.')
 

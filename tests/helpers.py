@@ -97,5 +97,8 @@ class ToyHostKernel:
     def get_default_covmat(self):
         return 0.005 * np.diag([5.0] * len(self.varying_param_names))
 
+    def get_default_initial_position(self):
+        return {n: [0.3] for n in self.varying_param_names}
+
     def finalize(self):
         pass

@@ -273,3 +273,50 @@ def test_whole_profile_job_with_a_host_kernel_through_run(tmp_path):
     for name in ('x2.txt', 'x2_status.txt', 'x2_intervals.txt'):
         with open(tmp_path / 'part' / 'profile' / name, 'rb') as fa, open(tmp_path / 'full' / 'profile' / name, 'rb') as fb:
             assert fa.read() == fb.read(), name
+
+
+def test_hosted_mh_sampler_matches_scalar_replay():
+    """jobtype-mcmc sampler for a host kernel (initialise_mcmc -> HostedMetropolisHastings): every chain is, row for row
+    (multiplicity, -log L, position), the scalar replay of MetropolisHastings.step with the GPU's variates; a sampler
+    continued from the chains of another picks up their Philox streams and open last rows."""
+    from types import SimpleNamespace
+    from prospect_public_b200.mcmc import initialise_mcmc
+    d, b = 5, 6
+    host = ToyHostKernel(d, box=(-0.2, 1.2))
+    kernel = HostKernelAdapter(host)
+    rng = np.random.default_rng(3)
+    a = rng.standard_normal((d, d))
+    cov = 0.05 * (a @ a.T / d + 0.5 * np.eye(d))
+    cfg = SimpleNamespace(algorithm='MetropolisHastings', N_chains=b, temperature=0.7, step_size=0.9,
+                          start_from_covmat=cov, start_from_position=None, steps_per_iteration=37)
+    mh = initialise_mcmc(cfg, kernel, seed=SEED)
+    mh.run_steps(37)
+    mh.run_steps(20)
+    second = initialise_mcmc(cfg, kernel, seed=SEED, chains=mh.chains, steps_done=57)
+    second.run_steps(30)
+    chains = second.chains
+    factor = np.linalg.cholesky(cov)
+    lo, hi = np.full(d, -0.2), np.full(d, 1.2)
+    outside = 0
+    for c in range(b):
+        z, e = engine.rng_variates(DEV, SEED, c, 0, 87, d)
+        z, e = z.cpu().numpy(), e.cpu().numpy()
+        x = np.full(d, 0.3)
+        ll = host.value(x)
+        rows = [[1, ll, x]]
+        for t in range(87):
+            acc, prop, llp, out = hm.step(host.value, x, ll, factor, lo, hi, 0.7, 0.9, z[t], e[t])
+            outside += out
+            if acc:
+                x, ll = prop, llp
+                rows.append([1, llp, prop])
+            else:
+                rows[-1][0] += 1
+        ch = chains[c]
+        assert list(ch.mults) == [r[0] for r in rows], c
+        assert np.allclose(ch.loglkls, [r[1] for r in rows], rtol=1e-12, atol=0)
+        got = np.stack([ch.positions[nm] for nm in kernel.varying_param_names], axis=1)
+        assert np.max(np.abs(got - np.array([r[2] for r in rows]))) <= 1e-12
+        assert sum(ch.mults) == 88                                  # start point + one count per step
+    assert outside > 0
+    assert int(mh.accepted.sum() + second.accepted.sum()) == sum(len(ch.mults) - 1 for ch in chains)
