@@ -130,9 +130,12 @@ def _validate_section(name, sec):
         if not os.path.isfile(os.path.join(os.getcwd(), sec['param'])):
             raise ConfigError(f"The file pointed to in the 'param' field of the 'kernel' input, which has the "
                               f"value {sec['param']}, could not be found.")
-        if sec['type'] == 'montepython' or sec['type'] == 'cobaya':
-            raise ConfigError(f"kernel.type '{sec['type']}' wraps an external Boltzmann/likelihood code and is out "
-                              "of scope of the B200 path; use 'analytical'.")
+        # 'montepython' / 'cobaya' wrap external CPU codes: the yaml is valid (the reference's schema), the kernel object
+        # has to be supplied by the caller -- run(yaml, kernel=hosted.HostKernelAdapter(...)); kernels.initialise_kernel
+        # refuses to build one
+        if sec['type'] == 'montepython' and not os.path.isdir(os.path.join(os.getcwd(), sec['path'])):
+            raise ConfigError(f"The directory pointed to in the 'path' field of the 'kernel' input, which has the "
+                              f"value {sec['path']}, could not be found.")          # base_kernel.py:176-180
     if name in ('profile', 'mcmc'):
         if sec['steps_per_iteration'] is not None and sec['minutes_per_iteration'] is not None:
             raise ConfigError("Give either 'steps_per_iteration' or 'minutes_per_iteration', not both.")

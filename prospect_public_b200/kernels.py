@@ -24,8 +24,9 @@ def initialise_kernel(config_kernel, output_folder, task_id, device='cuda:0'):
     if config_kernel.type in ('analytical', 'cuda_gaussian'):
         return CudaGaussianKernel(config_kernel, task_id, output_folder=output_folder, device=device)
     if config_kernel.type in ('montepython', 'cobaya'):
-        raise ValueError(f"Kernel type '{config_kernel.type}' needs an external likelihood code and is not "
-                         'part of the B200 path.')
+        raise ValueError(f"Kernel type '{config_kernel.type}' needs an external likelihood code that is evaluated on "
+                         'the host: build the reference kernel object yourself, wrap it in '
+                         'prospect_public_b200.hosted.HostKernelAdapter and pass it as run(yaml, kernel=...).')
     raise ValueError('You have specified a non-existing kernel type.')
 
 

@@ -78,3 +78,26 @@ def test_hosted_model_step_is_the_pinned_ports_step(monkeypatch):
             x, ll, accepted = prop, llp, accepted + 1
             assert np.array_equal(chain.positions[-1], prop) and chain.loglkls[-1] == llp
     assert 20 < accepted < 380 and outside_seen > 0
+
+
+def test_external_kernel_types_validate_and_point_to_the_hosted_path(tmp_path):
+    """`kernel.type: cobaya | montepython` yaml files are valid input (the reference's schema, base_kernel.py:143-186);
+    the factory refuses to build those kernels and says how a host-evaluated kernel is run instead."""
+    from prospect_public_b200.config import ConfigError, Configuration
+    from prospect_public_b200.kernels import initialise_kernel
+    from prospect_public_b200.toy import annealing_yaml, write_toy_inputs
+    k = golden('toy20_kernel.npz')
+    paths = write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], None)
+    y = annealing_yaml(paths, str(tmp_path / 'o'), write=False)
+    y['kernel']['type'] = 'cobaya'
+    cfg = Configuration(y)
+    assert cfg.kernel.type == 'cobaya' and cfg.kernel.path == ''
+    with pytest.raises(ValueError, match='HostKernelAdapter'):
+        initialise_kernel(cfg.kernel, None, 0)
+    y['kernel'].update(type='montepython', path=str(tmp_path / 'no_such_dir'))
+    with pytest.raises(ConfigError, match="'path'"):
+        Configuration(y)
+    os_path = tmp_path / 'montepython'
+    os_path.mkdir()
+    y['kernel'].update(path=str(os_path), conf=paths['kernel_yaml'])
+    assert Configuration(y).kernel.type == 'montepython'
