@@ -303,11 +303,24 @@ class HostedMetropolisHastings:
         self._flag_host = torch.empty(b, dtype=torch.int32, pin_memory=True)
         self._ll_host = torch.empty(b, dtype=torch.float64, pin_memory=True)
         self._names, self._prior = names, prior
-        self._x = np.zeros((b, 64, n))
-        self._ll = np.zeros((b, 64))
-        self._mult = np.zeros((b, 64), dtype=np.int64)
-        self._count = np.ones(b, dtype=np.int64)
-        self._x[:, 0], self._ll[:, 0], self._mult[:, 0] = x0, ll0, 1
+        if prior is not None and mcmc_args.get('preload', False):
+            # continue the chains in place (`prospect <folder>` for jobtype mcmc, tasks/mcmc_task.py:71-81): their
+            # earlier rows go back into the record, the open last row keeps counting
+            rows = np.array([len(ch.mults) for ch in prior], dtype=np.int64)
+            cap = int(rows.max()) + 64
+            self._x, self._ll = np.zeros((b, cap, n)), np.zeros((b, cap))
+            self._mult, self._count = np.zeros((b, cap), dtype=np.int64), rows
+            for c, ch in enumerate(prior):
+                self._x[c, :rows[c]] = np.stack([np.asarray(ch.positions[nm], dtype=np.float64) for nm in names], axis=1)
+                self._ll[c, :rows[c]] = ch.loglkls
+                self._mult[c, :rows[c]] = np.asarray(ch.mults, dtype=np.int64)
+            self._prior = None
+        else:
+            self._x = np.zeros((b, 64, n))
+            self._ll = np.zeros((b, 64))
+            self._mult = np.zeros((b, 64), dtype=np.int64)
+            self._count = np.ones(b, dtype=np.int64)
+            self._x[:, 0], self._ll[:, 0], self._mult[:, 0] = x0, ll0, 1
         self.accepted = np.zeros(b, dtype=np.int64)
         self.steps = 0
 
@@ -372,6 +385,20 @@ class HostedMetropolisHastings:
     def samples_numpy(self):
         """(x [B, cap, n], loglkl [B, cap], mult [B, cap], count [B]) of everything recorded so far."""
         return self._x, self._ll, self._mult.astype(np.int32), self._count.astype(np.int32)
+
+    @property
+    def _samples(self):
+        """The record as device buffers in engine.Samples' layout (what engine.chain_statistics reduces for R-1 and
+        the pooled covariance): uploaded when asked for, once per round."""
+        import torch
+        from types import SimpleNamespace
+        dev, n = self.problem.device, self.problem.n
+        cap = int(self._count.max())
+        x = torch.zeros((self.n_chains, cap, self.problem.npad), dtype=torch.float64, device=dev)
+        x[:, :, :n] = torch.as_tensor(self._x[:, :cap], device=dev)
+        return SimpleNamespace(x=x, loglkl=torch.as_tensor(self._ll[:, :cap], device=dev),
+                               mult=torch.as_tensor(self._mult[:, :cap].astype(np.int32), device=dev),
+                               count=torch.as_tensor(self._count.astype(np.int32), device=dev), capacity=cap)
 
     @property
     def chains(self):

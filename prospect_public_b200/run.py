@@ -65,7 +65,7 @@ def run(user_inp, quiet=True, stop_after=None, max_rounds=64, kernel=None):
         pio.prepare_run(config)
     _barrier()
     if config.run.jobtype == 'mcmc':
-        out = run_mcmc(config, max_rounds=max_rounds, stop_after_rounds=stop_after)
+        out = run_mcmc(config, max_rounds=max_rounds, stop_after_rounds=stop_after, kernel=kernel)
     else:
         out = run_annealing(config, stop_after=stop_after, kernel=kernel)
     out['time_to_result_s'] = time.perf_counter() - t_start          # incl. the snapshot pickles
@@ -169,7 +169,7 @@ def resume(config, prospect_folder, max_rounds=64, kernel=None):
     that was never interrupted: same random streams, same records, same output files."""
     if config.run.jobtype == 'mcmc':
         config.io.dir = config.config_dict['io']['dir'] = prospect_folder
-        return run_mcmc(config, max_rounds=max_rounds, resume_folder=prospect_folder)
+        return run_mcmc(config, max_rounds=max_rounds, resume_folder=prospect_folder, kernel=kernel)
     config.io.dir = config.config_dict['io']['dir'] = prospect_folder
     _, rec_old = load_record(prospect_folder)
     state = pio.load_pickle(prospect_folder, 'pb200_state')
@@ -408,7 +408,7 @@ def shard_chains(n_chains, rank, world):
     return n_chains * rank // world, n_chains * (rank + 1) // world
 
 
-def run_mcmc(config, max_rounds=64, resume_folder=None, stop_after_rounds=None):
+def run_mcmc(config, max_rounds=64, resume_folder=None, stop_after_rounds=None, kernel=None):
     """jobtype mcmc (tasks/mcmc_task.py:10-81): N_chains chains advance `steps_per_iteration` per round on the
     GPU(s); after each round the chains are unpacked to <dir>/mcmc/<jobname>_<i>.txt (+ .paramnames / .ranges) and
     R-1 decides whether to continue.
@@ -434,11 +434,12 @@ def run_mcmc(config, max_rounds=64, resume_folder=None, stop_after_rounds=None):
     if config.run.numpy_random_seed is not None:
         np.random.seed(int(config.run.numpy_random_seed))
     out_dir = config.io.dir if config.io.write else None
+    make_kernel = kernel if callable(kernel) else (initialise_kernel if kernel is None else (lambda *a: kernel))
     if rank == 0:
-        kernel = initialise_kernel(config.kernel, out_dir, 0, device)   # may create analytical/random_gauss.pkl
+        kernel = make_kernel(config.kernel, out_dir, 0, device)   # may create analytical/random_gauss.pkl
     _barrier()
     if rank != 0:
-        kernel = initialise_kernel(config.kernel, out_dir, rank, device)
+        kernel = make_kernel(config.kernel, out_dir, rank, device)
     lo, hi = shard_chains(int(mc.N_chains), rank, world)
     n = len(kernel.varying_param_names)
     seed, rounds, extra = config.seed, 0, {}

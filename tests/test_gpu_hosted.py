@@ -320,3 +320,38 @@ def test_hosted_mh_sampler_matches_scalar_replay():
         assert sum(ch.mults) == 88                                  # start point + one count per step
     assert outside > 0
     assert int(mh.accepted.sum() + second.accepted.sum()) == sum(len(ch.mults) - 1 for ch in chains)
+
+
+@pytest.mark.skipif(not rh.available(), reason='oracle/_ref is absent (python oracle/make_ref.py builds it where '
+                                               '/root/reference exists)')
+def test_mcmc_job_with_a_host_kernel_through_run_and_resume(tmp_path):
+    """jobtype mcmc through run(kernel=...) with the reference AnalyticalKernel on the host: chain files in the reference's
+    layout, R-1 from the device reductions, and a job stopped after its first round and resumed from its chain files
+    (tasks/mcmc_task.py:71-81) writes byte-identical chain files to the job that was never interrupted."""
+    from prospect.kernels.analytical_kernel import AnalyticalKernel
+    from prospect_public_b200.hosted import HostedMetropolisHastings
+    from prospect_public_b200.initialise import load_mcmc
+    from prospect_public_b200.run import run
+    from prospect_public_b200.toy import mcmc_yaml
+    rh.activate()
+    k = golden('toy20_kernel.npz')
+    paths = write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], None)
+
+    def factory(config_kernel, output_folder, rank, device):
+        with rh.quiet():
+            return HostKernelAdapter(AnalyticalKernel(config_kernel, rank, output_folder=output_folder), device=device)
+
+    kw = dict(n_chains=5, steps=120, rm1=1e-12)
+    full = run(mcmc_yaml(paths, str(tmp_path / 'full'), **kw), max_rounds=3, kernel=factory)
+    assert full['rounds'] == 3 and isinstance(full['sampler'], HostedMetropolisHastings)
+    assert np.isfinite(full['Rm1']) and full['chain_steps'] == 3 * 120 * 5
+    chains = load_mcmc(os.path.join(str(tmp_path / 'full'), 'mcmc', 'test'), collapse=False)
+    assert len(chains) == 5 and all(int(round(np.sum(ch.mults))) == 361 for ch in chains)
+    part = run(mcmc_yaml(paths, str(tmp_path / 'part'), **kw), stop_after=1, kernel=factory)
+    assert part['rounds'] == 1
+    cont = run(str(tmp_path / 'part'), max_rounds=3, kernel=factory)
+    assert cont['rounds'] == 3 and abs(cont['Rm1'] - full['Rm1']) <= 1e-12 * full['Rm1']
+    for i in range(5):
+        a = open(os.path.join(str(tmp_path / 'full'), 'mcmc', f'test_{i}.txt'), 'rb').read()
+        b = open(os.path.join(str(tmp_path / 'part'), 'mcmc', f'test_{i}.txt'), 'rb').read()
+        assert a == b, i
