@@ -228,8 +228,8 @@ class HostedSimulatedAnnealing(SimulatedAnnealing):
         b = self.batch.n_chains
         for _ in range(n_iterations):
             row = self.iterations_done
-            if b:
-                status_host = self.batch.status.cpu().numpy()
+            status_host = self.batch.status.cpu().numpy() if b else None
+            if b and (status_host == capi.ACTIVE).any():          # (every chain stopped: nothing left to run)
                 live = self.batch.status == capi.ACTIVE
                 # the chain of an iteration starts at the current point: it is the first bestfit candidate
                 self._best_ll.copy_(self.batch.loglkl)
