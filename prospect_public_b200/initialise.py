@@ -237,6 +237,7 @@ def initialise_optimiser(config, kernel, shard=None):
     else:
         prob = kernel.device_problem(likelihood_only=True)
         init_ll = kernel.loglkl_batch(positions, problem=prob)
+    covmats.setflags(write=False)      # results, not scratch: lets kernels.array_key cache device problems by identity
     return StartingPoints(names, positions, covmats, init_ll, indices), values
 
 

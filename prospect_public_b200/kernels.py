@@ -69,6 +69,26 @@ def load_kernel_settings(param_file, output_folder=None):
             'dimension': d, 'ranges': {n: [-2.5, 2.5] for n in names}}
 
 
+def array_key(a):
+    """Cache key of an array's CONTENT.  A read-only array (no writeable base anywhere under it: nothing can change
+    what it holds) is keyed by its address -- no pass over the data; the proposal covariances initialise_optimiser returns are
+    made read-only for exactly this (hashing the 4 MB of a 256-D job's covariances was 1.5 ms of every optimiser
+    construction).  Anything else is keyed by a hash of its bytes."""
+    if a is None:
+        return None
+    node, frozen = a, True
+    while isinstance(node, np.ndarray):
+        if node.flags.writeable:
+            frozen = False
+            break
+        node = node.base
+    if frozen and node is None:
+        # (the memory address, not id(): a fresh view of the same frozen data is the same content; the cache entry holds
+        # the array, so the address cannot be handed to another array while the entry lives)
+        return ('frozen', a.__array_interface__['data'][0], a.shape, a.strides)
+    return ('hash', hash(a.tobytes()), a.shape)
+
+
 class CudaGaussianKernel:
     """Gaussian likelihood evaluated by libpb200 on a B200.
 
@@ -150,16 +170,16 @@ class CudaGaussianKernel:
         fv = None if fixed_values is None else np.ascontiguousarray(fixed_values, dtype=np.float64)
         pc = None if proposal_covmats is None else np.ascontiguousarray(proposal_covmats, dtype=np.float64)
         fixed_now = None if fi is None or fv is not None else self.param['fixed'][self.names[fi]]['fixed_value']
-        key = (fi, fixed_now, None if fv is None else fv.tobytes(), None if pc is None else hash(pc.tobytes()),
-               None if pc is None else pc.shape, self.ignore_prior, str(self.device), bool(likelihood_only))
+        key = (fi, fixed_now, None if fv is None else fv.tobytes(), array_key(pc), self.ignore_prior, str(self.device),
+               bool(likelihood_only))
         cache = self.__dict__.setdefault('_problem_cache', {})
         hit = cache.get(key)
         if hit is None:
-            hit = DeviceProblem(self.host_problem(fixed_values, proposal_covmats, likelihood_only), self.device)
+            hit = (DeviceProblem(self.host_problem(fixed_values, proposal_covmats, likelihood_only), self.device), pc)
             if len(cache) >= 4:
                 cache.pop(next(iter(cache)))
-            cache[key] = hit
-        return hit
+            cache[key] = hit          # (the array travels with the entry: an identity key must not outlive its object)
+        return hit[0]
 
     def _scalar_problem(self):
         if self._problem is None:

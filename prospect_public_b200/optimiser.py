@@ -175,7 +175,9 @@ class SimulatedAnnealing:
         point_local = np.searchsorted(self.local_points, pt).astype(np.int32)
         fixed_local = None if fixed is None else np.asarray(fixed, dtype=np.float64)[self.local_points]
         self.fixed_local = fixed_local
-        self.problem = self._device_problem(kernel, fixed_local, covs[self.local_points])
+        # every point on this rank, in order: hand the caller's array through (a read-only one is cached by identity)
+        all_local = len(self.local_points) == self.n_points and np.array_equal(self.local_points, np.arange(self.n_points))
+        self.problem = self._device_problem(kernel, fixed_local, covs if all_local else covs[self.local_points])
         cb = np.broadcast_to(np.asarray(s.get('current_best_loglkl', math.inf), dtype=np.float64), (self.n_points,))
         gid = global_chain_index(pt, rep, self.n_points)
         resumed = s.get('chain_state')            # global-order per-chain state of an interrupted run (run.resume)

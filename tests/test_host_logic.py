@@ -626,3 +626,26 @@ def test_configuration_synchronise_world2_gloo(toy20, tmp_path):
     assert after0[:2] == before0 and after1[:2] == before0                # rank 0's folder and key everywhere
     assert after1[1] == after1[2]                                         # cached: the same key on every read
     assert pts0 == pts1 == [0, 1, 2, 3, 4]                                # every rank ends up with every value
+
+
+def test_array_key_identity_for_frozen_arrays_content_otherwise():
+    """kernels.array_key (the device-problem cache key of the proposal covariances): writeable arrays by content,
+    read-only ones (no writeable base) by address -- views of the same frozen data agree, copies do not alias."""
+    from prospect_public_b200.kernels import array_key
+    rng = np.random.default_rng(0)
+    a = rng.standard_normal((3, 5, 5))
+    b = a.copy()
+    assert array_key(a) == array_key(b) and array_key(a)[0] == 'hash'       # same content, different objects
+    b[1, 2, 3] += 1e-12
+    assert array_key(a) != array_key(b)
+    a.setflags(write=False)
+    ka = array_key(a)
+    assert ka[0] == 'frozen' and array_key(a) == ka and array_key(a[:]) == ka   # a fresh view of the same data
+    assert array_key(a[1:]) != ka and array_key(a.copy())[0] == 'hash'
+    c = rng.standard_normal((5, 5))
+    view = c[None]
+    view.setflags(write=False)                                                   # read-only view of a WRITEABLE base
+    assert array_key(view)[0] == 'hash'
+    c.setflags(write=False)
+    assert array_key(c[None]) == array_key(c[None]) and array_key(c[None])[0] == 'frozen'
+    assert array_key(None) is None
