@@ -4,8 +4,10 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): tests/test_gpu_hosted.py repl
 (pb200_rng_variates) through this model and compares every proposal, decision, bestfit and schedule value with what
 prospect_public_b200.hosted produced through pb200_hosted_propose / pb200_hosted_accept.
 
-Parity status: the step is oracle/reference_port.mh_step (PINNED against the reference's golden vectors) with its two
-numpy draws replaced by the variates handed in --
+Parity status: PINNED.  The step is oracle/reference_port.mh_step (itself pinned against the reference's golden vectors)
+with its two numpy draws replaced by the variates handed in; tests/test_hosted_host.py checks it, decision for decision
+and bit for bit, against that port and against the unmodified reference's MetropolisHastings.step (numpy's draws
+patched to the values the variates stand for) --
     prop = current + step_size * F z,  F F^T = covmat      for  multivariate_normal(current, covmat * step_size**2)
                                                             (prospect/mcmc.py:182-190; equal in distribution),
     accept iff  loglkl_prop - loglkl_cur < T * e, e = -ln u  for  exp((cur - prop) / T) > u  (mcmc.py:170-180)

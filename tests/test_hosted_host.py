@@ -101,3 +101,64 @@ def test_external_kernel_types_validate_and_point_to_the_hosted_path(tmp_path):
     os_path.mkdir()
     y['kernel'].update(path=str(os_path), conf=paths['kernel_yaml'])
     assert Configuration(y).kernel.type == 'montepython'
+
+
+def test_hosted_model_step_is_the_reference_step(tmp_path, monkeypatch):
+    """The same pin against the UNMODIFIED reference (oracle/_ref or /root/reference): its own AnalyticalKernel and
+    MetropolisHastings.step (prospect/mcmc.py:163-190), fed the draws the variates stand for, take the decisions of
+    oracle/hosted_model.step and build the same chain -- multiplicities, -log L values and positions, bit for bit."""
+    from types import SimpleNamespace
+    from oracle import ref_harness as rh
+    if not rh.available():
+        pytest.skip('the reference is not available here')
+    rh.activate()
+    from prospect.kernels.analytical_kernel import AnalyticalKernel
+    from prospect.mcmc import MetropolisHastings
+    from prospect_public_b200.toy import write_toy_inputs
+    k = golden('toy20_kernel.npz')
+    paths = write_toy_inputs(str(tmp_path / 'inp'), k['means'], k['covmat'], None)
+    (tmp_path / 'out' / 'analytical').mkdir(parents=True)
+    with rh.quiet():
+        kernel = AnalyticalKernel(SimpleNamespace(param=paths['kernel_yaml'], ignore_prior=False), 0,
+                                  output_folder=str(tmp_path / 'out'))
+    kernel.set_fixed_parameters({'x2': 0.4})
+    names = kernel.varying_param_names
+    kernel.param['varying']['x5']['range'] = [-2.5, float(k['means'][4]) + 0.03]    # a wall next to the mode
+    n = len(names)
+    rng = np.random.default_rng(4)
+    a = rng.standard_normal((n, n))
+    cov = 0.003 * (a @ a.T / n + np.eye(n))
+    factor = np.linalg.cholesky(cov)
+    temperature, step_size = 0.5, 0.4
+    cfg = SimpleNamespace(start_from_covmat=cov, start_from_position=None, temperature=temperature, step_size=step_size)
+    from prospect.mcmc import Chain
+    start = {nm: [0.] for nm in names}
+    # (the chain is seeded the way SimulatedAnnealing.__init__ does it, optimiser.py:56-62: the reference's
+    # get_default_initial_position fails once a parameter is fixed)
+    mh = MetropolisHastings(cfg, kernel, chain=Chain([1], [kernel.loglkl(start)], start))
+    lo = np.array([kernel.param['varying'][nm]['range'][0] for nm in names], dtype=float)
+    hi = np.array([kernel.param['varying'][nm]['range'][1] for nm in names], dtype=float)
+
+    def loglkl(x):
+        return kernel.loglkl({nm: [v] for nm, v in zip(names, x)})
+
+    x = np.zeros(n)
+    ll = mh.chain.loglkls[-1]
+    assert ll == loglkl(x)
+    # walk to the mode first (the default start is far out), then count
+    accepted = outside_seen = 0
+    for t in range(600):
+        z, e = rng.standard_normal(n), rng.exponential()
+        monkeypatch.setattr(np.random, 'multivariate_normal', lambda mean, c: mean + step_size * (factor @ z))
+        monkeypatch.setattr(np.random, 'uniform', lambda low=0, high=1: np.exp(-e))
+        rows_before = len(mh.chain.mults)
+        acc, prop, llp, outside = hm.step(loglkl, x, ll, factor, lo, hi, temperature, step_size, z, e)
+        with rh.quiet():
+            mh.step()
+        assert (len(mh.chain.mults) == rows_before + 1) == acc, t
+        outside_seen += outside
+        if acc:
+            x, ll, accepted = prop, llp, accepted + 1
+            assert mh.chain.loglkls[-1] == llp
+            assert np.array_equal([mh.chain.positions[nm][-1] for nm in names], prop)
+    assert accepted > 30 and outside_seen > 0 and sum(mh.chain.mults) == 601
