@@ -44,7 +44,7 @@ def test_struct_layouts_match_header():
         text = f.read()
     for cname, cls in (('pb200_problem', capi.Problem), ('pb200_chains', capi.Chains),
                        ('pb200_schedule', capi.Schedule), ('pb200_records', capi.Records),
-                       ('pb200_samples', capi.Samples), ('pb200_peers', capi.Peers)):
+                       ('pb200_samples', capi.Samples), ('pb200_peers', capi.Peers), ('pb200_hosted', capi.Hosted)):
         body = re.search(r'typedef struct %s \{(.*?)\} %s;' % (cname, cname), text, re.S).group(1)
         body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
         fields = [re.findall(r'(\w+)\s*(?:\[\w+\])?\s*;', line)[0] for line in body.split('\n') if ';' in line]
