@@ -144,3 +144,111 @@ def test_reference_kernel_behind_the_optimiser(fake_device, tmp_path):
     if not g.rh.available():
         pytest.skip('the reference is not available here')
     g.test_reference_analytical_kernel_behind_the_hosted_optimiser(tmp_path)
+
+
+@pytest.mark.parametrize('mode', ['adaptive', 'exponential', 'secant'])
+def test_hosted_optimiser_reproduces_the_unmodified_reference_chain_by_chain(fake_device, tmp_path, monkeypatch, mode):
+    """The strongest statement the CPU suite can make about the hosted path: with the reference's own AnalyticalKernel
+    as the host likelihood, every chain of HostedSimulatedAnnealing (its host logic + the device semantics the test
+    doubles restate) is the UNMODIFIED reference's SimulatedAnnealing -- optimise / set_bestfit /
+    get_next_iteration_settings (prospect/optimiser.py:40-162) over MetropolisHastings.step (mcmc.py:163-190) -- fed
+    the draws the chain's variates stand for: accepted steps, bestfit value and position, next temperature and step
+    size, last position, all EXACTLY equal, iteration by iteration."""
+    from types import SimpleNamespace
+    g = _gpu_module()
+    if not g.rh.available():
+        pytest.skip('the reference is not available here')
+    g.rh.activate()
+    from prospect.kernels.analytical_kernel import AnalyticalKernel
+    from prospect.optimiser import SimulatedAnnealing as RefSimulatedAnnealing
+    import os
+    ini = g.golden('toy20_init.npz')
+    sel, reps, n_iter, steps, seed = [2, 7], 2, 5, 40, 2024
+    values = [float(v) for v in ini['values'][sel]]
+    prof = dict(values=values, repetitions=reps, max_iterations=n_iter, steps_per_iteration=steps)
+    if mode == 'exponential':
+        prof.update(step_size_schedule='exponential', step_size_range=[0.5, 0.05])
+    elif mode == 'secant':
+        prof.update(step_size_adaptive_multiplier='adaptive', step_size_adaptive_interval=[0.02, 0.03])
+    cfg, paths, k = g._config(tmp_path, **prof)
+    step0 = 0.5 if mode == 'exponential' else 0.1
+
+    def new_ref_kernel(tag):
+        out = str(tmp_path / tag)
+        os.makedirs(os.path.join(out, 'analytical'))
+        with g.rh.quiet():
+            return AnalyticalKernel(cfg.kernel, 0, output_folder=out)
+
+    kernel = g.HostKernelAdapter(new_ref_kernel('ours'), profile_parameter='x2')
+    names = kernel.varying_param_names
+    starts, covs = ini['position'][sel][:, :-1], ini['covmat'][sel]
+    init_ll = kernel.loglkl_batch(starts, values)
+    settings = {'current_best_loglkl': init_ll, 'initial_position': starts, 'covmat': covs, 'temperature': 0.1,
+                'temperature_change': g.get_temperature_change(cfg), 'step_size': step0,
+                'step_size_change': g.get_initial_step_size_change(cfg), 'iteration_number': 0, 'repetitions': reps,
+                'fixed_param_val': values, 'max_rows': n_iter, 'seed': seed}
+    sa = g.initialise_optimiser(cfg, kernel, settings)
+    sa.run_schedule(n_iter)
+    rec, status, final_x = sa.global_records(), sa.global_status(), sa.batch.positions()
+    final_t, final_s = sa.batch.temperature.numpy(), sa.batch.step_size.numpy()
+
+    ref_cfg = SimpleNamespace(run=SimpleNamespace(jobtype='profile'),
+                              profile=SimpleNamespace(parameter='x2', steps_per_iteration=steps, minutes_per_iteration=None,
+                                                      temperature_schedule='exponential',
+                                                      step_size_schedule=cfg.profile.step_size_schedule,
+                                                      step_size_adaptive_multiplier=cfg.profile.step_size_adaptive_multiplier,
+                                                      step_size_adaptive_interval=cfg.profile.step_size_adaptive_interval))
+    ref_kernel = new_ref_kernel('ref')
+    failed_chains = 0
+    for rep in range(reps):
+        for p in range(len(values)):
+            c = rep * len(values) + p
+            z, e = dm.variates(seed, c, 0, n_iter * steps, len(names))
+            factor = np.linalg.cholesky(0.5 * (covs[p] + covs[p].T))       # the symmetrised covariance, lower factor
+            if 'x2' in ref_kernel.param['fixed']:
+                ref_kernel.param['fixed']['x2']['fixed_value'] = values[p]
+            else:
+                ref_kernel.set_fixed_parameters({'x2': values[p]})
+            state = {'t': 0, 'step': step0}
+
+            def normal(mean, cov, state=state, factor=factor, z=z):
+                return mean + state['step'] * (factor @ z[state['t']].astype(np.float64))
+
+            def uniform(low=0, high=1, state=state, e=e):
+                u = np.exp(-float(e[state['t']]))
+                state['t'] += 1
+                return u
+
+            monkeypatch.setattr(np.random, 'multivariate_normal', normal)
+            monkeypatch.setattr(np.random, 'uniform', uniform)
+            change = g.get_initial_step_size_change(cfg)
+            ref_settings = {'current_best_loglkl': init_ll[p], 'initial_position': {nm: [v] for nm, v in zip(names, starts[p])},
+                            'covmat': covs[p], 'temperature': 0.1, 'temperature_change': g.get_temperature_change(cfg),
+                            'step_size': step0, 'step_size_change': change, 'iteration_number': 0,
+                            'repetition_number': rep, 'fixed_param_val': values[p]}
+            for it in range(n_iter):
+                state['step'] = ref_settings['step_size']
+                with g.rh.quiet():
+                    ref = RefSimulatedAnnealing(ref_cfg, ref_kernel, ref_settings)
+                    ref.optimise()
+                    ref.set_bestfit()
+                bf = ref.bestfit
+                assert rec['accepted'][it, c] + 1 == bf['accepted_steps'], (c, it)
+                assert rec['best_loglkl'][it, c] == bf['loglkl'], (c, it)
+                assert np.array_equal(rec['best_x'][it, c], [bf['position'][nm][0] for nm in names]), (c, it)
+                assert rec['temperature'][it, c] == ref_settings['temperature'], (c, it)
+                assert rec['step_size'][it, c] == ref_settings['step_size'], (c, it)
+                try:
+                    nxt = ref.get_next_iteration_settings()
+                except UnboundLocalError:               # the reference's own failure path of the 'adaptive' multiplier
+                    assert status[c] == capi.FAILED
+                    failed_chains += 1
+                    break
+                nxt['iteration_number'] = it + 1
+                nxt['repetition_number'] = rep
+                ref_settings = nxt
+            else:
+                assert status[c] == capi.ACTIVE
+                assert np.array_equal(final_x[c], [ref_settings['initial_position'][nm][0] for nm in names])
+                assert final_t[c] == ref_settings['temperature'] and final_s[c] == ref_settings['step_size']
+    assert failed_chains < reps * len(values)
