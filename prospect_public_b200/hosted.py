@@ -404,7 +404,7 @@ class HostedMetropolisHastings:
     def chains(self):
         """list[mcmc.Chain]; a continued chain is its earlier rows followed by the new ones, the open last row of the
         earlier segment keeps its multiplicity count (Chain.mults[-1] += 1)."""
-        from .mcmc import Chain
+        from .mcmc import Chain, continue_chain
         fixed = {nm: par['fixed_value'] for nm, par in self.kernel.param['fixed'].items()}
         out = []
         for c in range(self.n_chains):
@@ -413,14 +413,7 @@ class HostedMetropolisHastings:
             for nm, val in fixed.items():
                 ch.positions[nm] = [val] * r
             if self._prior is not None:
-                prev = self._prior[c]
-                merged = Chain(list(prev.mults), list(prev.loglkls), {k: list(v) for k, v in prev.positions.items()})
-                merged.mults[-1] += ch.mults[0] - 1
-                merged.mults += ch.mults[1:]
-                merged.loglkls += ch.loglkls[1:]
-                for k in merged.positions:
-                    merged.positions[k] += ch.positions[k][1:]
-                ch = merged
+                ch = continue_chain(self._prior[c], ch)
             out.append(ch)
         return out
 

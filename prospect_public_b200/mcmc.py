@@ -76,6 +76,19 @@ def collapse_chains(chain_list):
     return total
 
 
+def continue_chain(previous, segment):
+    """The chain `previous` continued by `segment`, whose first row is previous' last point again (a sampler that was
+    started from it): that row's multiplicity count carries on in previous' open last row (Chain.mults[-1] += 1,
+    prospect/mcmc.py:178-180), the other rows follow.  Neither input is modified."""
+    merged = Chain(list(previous.mults), list(previous.loglkls), {k: list(v) for k, v in previous.positions.items()})
+    merged.mults[-1] += segment.mults[0] - 1
+    merged.mults += segment.mults[1:]
+    merged.loglkls += segment.loglkls[1:]
+    for k in merged.positions:
+        merged.positions[k] += segment.positions[k][1:]
+    return merged
+
+
 def compute_covariance_matrix(chain_list, device='cuda:0'):
     """np.cov(x, bias=True, fweights=mults) of the collapsed chains, reduced on the GPU in FP64
     (pb200_weighted_moments)."""
@@ -261,15 +274,7 @@ class MetropolisHastings:
             for nm, val in fixed.items():
                 ch.positions[nm] = [val] * r
             if self._prior is not None:
-                prev = self._prior[c]
-                merged = Chain(list(prev.mults), list(prev.loglkls), {k: list(v) for k, v in prev.positions.items()})
-                # row 0 of the new segment is the previous chain's last point: fold its multiplicity in
-                merged.mults[-1] += ch.mults[0] - 1
-                merged.mults += ch.mults[1:]
-                merged.loglkls += ch.loglkls[1:]
-                for k in merged.positions:
-                    merged.positions[k] += ch.positions[k][1:]
-                ch = merged
+                ch = continue_chain(self._prior[c], ch)     # row 0 of the new segment is the previous chain's last point
             out.append(ch)
         return out
 

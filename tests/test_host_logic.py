@@ -649,3 +649,18 @@ def test_array_key_identity_for_frozen_arrays_content_otherwise():
     c.setflags(write=False)
     assert array_key(c[None]) == array_key(c[None]) and array_key(c[None])[0] == 'frozen'
     assert array_key(None) is None
+
+
+def test_continue_chain_folds_the_repeated_first_row():
+    """mcmc.continue_chain: a segment sampled from a chain's last point continues that chain -- the repeated point's
+    multiplicity goes on counting in the open last row (Chain.mults[-1] += 1, prospect/mcmc.py:178-180)."""
+    from prospect_public_b200.mcmc import Chain, continue_chain
+    prev = Chain([2, 3], [5.0, 4.0], {'x1': [0.1, 0.2], 'x2': [1.0, 1.0]})
+    seg = Chain([4, 1, 2], [4.0, 3.5, 3.0], {'x1': [0.2, 0.3, 0.4], 'x2': [1.0, 1.0, 1.0]})
+    out = continue_chain(prev, seg)
+    assert out.mults == [2, 6, 1, 2] and out.loglkls == [5.0, 4.0, 3.5, 3.0]
+    assert out.positions['x1'] == [0.1, 0.2, 0.3, 0.4] and out.positions['x2'] == [1.0] * 4
+    assert prev.mults == [2, 3] and seg.mults == [4, 1, 2] and out.N == 4          # inputs untouched
+    assert sum(out.mults) == sum(prev.mults) + sum(seg.mults) - 1                  # one start row is not a step
+    lone = continue_chain(prev, Chain([7], [4.0], {'x1': [0.2], 'x2': [1.0]}))     # nothing accepted in the segment
+    assert lone.mults == [2, 9] and lone.loglkls == [5.0, 4.0]
